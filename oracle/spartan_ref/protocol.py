@@ -1,0 +1,749 @@
+"""
+ORACLE — TEST INFRASTRUCTURE ONLY (see core.py header).
+
+Restatement of the proof gadgets and the R1CS satisfiability proof of microsoft/Spartan:
+  src/unipoly.rs, src/nizk/mod.rs, src/nizk/bullet.rs, src/sumcheck.rs, src/dense_mlpoly.rs (PolyEvalProof),
+  src/r1csproof.rs.  Function docstrings cite the reference lines they follow.  Proof objects are
+dataclasses whose field order is the reference's struct order, so `ser()` yields the bytes
+`bincode::serialize` would.
+"""
+import dataclasses
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+
+from . import core as oc
+from .core import Q, inv
+
+
+# ----------------------------------------------------------------------------- bincode
+def ser(x):
+    """bincode 1.x default config: Scalar = 4 Montgomery limbs LE; CompressedGroup = 32 raw bytes;
+    Vec<T> = u64 length + items; structs / tuples / arrays = concatenation."""
+    if isinstance(x, (bytes, bytearray)):
+        assert len(x) == 32
+        return bytes(x)
+    if isinstance(x, (int, np.integer)):
+        return oc.mont_bytes(int(x))
+    if isinstance(x, list):
+        return len(x).to_bytes(8, "little") + b"".join(ser(i) for i in x)
+    if isinstance(x, tuple):
+        return b"".join(ser(i) for i in x)
+    if dataclasses.is_dataclass(x):
+        return b"".join(ser(getattr(x, f.name)) for f in dataclasses.fields(x))
+    raise TypeError(type(x))
+
+
+class ProofVerifyError(Exception):
+    pass
+
+
+# ----------------------------------------------------------------------------- unipoly.rs
+class UniPoly:
+    def __init__(self, coeffs):
+        self.coeffs = coeffs
+
+    @staticmethod
+    def from_evals(e):
+        """unipoly.rs:23-54"""
+        two_inv = inv(2)
+        if len(e) == 3:
+            c = e[0]
+            a = two_inv * (e[2] - e[1] - e[1] + c) % Q
+            b = (e[1] - c - a) % Q
+            return UniPoly([c, b, a])
+        assert len(e) == 4
+        six_inv = inv(6)
+        d = e[0]
+        a = six_inv * (e[3] - 3 * e[2] + 3 * e[1] - e[0]) % Q
+        b = two_inv * (2 * e[0] - 5 * e[1] + 4 * e[2] - e[3]) % Q
+        c = (e[1] - d - a - b) % Q
+        return UniPoly([d, c, b, a])
+
+    def degree(self):
+        return len(self.coeffs) - 1
+
+    def eval_at_zero(self):
+        return self.coeffs[0]
+
+    def eval_at_one(self):
+        return sum(self.coeffs) % Q
+
+    def evaluate(self, r):
+        """unipoly.rs:72-80"""
+        ev, power = self.coeffs[0], r
+        for c in self.coeffs[1:]:
+            ev = (ev + power * c) % Q
+            power = power * r % Q
+        return ev
+
+    def compress(self):
+        """unipoly.rs:82-88 -> CompressedUniPoly.coeffs_except_linear_term"""
+        return CompressedUniPoly(self.coeffs[:1] + self.coeffs[2:])
+
+    def append_to_transcript(self, label, t):
+        """unipoly.rs:112-120"""
+        t.append_message(label, b"UniPoly_begin")
+        for c in self.coeffs:
+            t.append_scalar(b"coeff", c)
+        t.append_message(label, b"UniPoly_end")
+
+
+@dataclass
+class CompressedUniPoly:
+    coeffs_except_linear_term: List[int]
+
+    def decompress(self, hint):
+        """unipoly.rs:96-108"""
+        c = self.coeffs_except_linear_term
+        linear = (hint - c[0] - c[0] - sum(c[1:])) % Q
+        return UniPoly([c[0], linear] + c[1:])
+
+
+# ----------------------------------------------------------------------------- nizk/mod.rs sigma protocols
+@dataclass
+class KnowledgeProof:
+    alpha: bytes
+    z1: int
+    z2: int
+
+    @staticmethod
+    def prove(gens_n, T, tape, x, r):
+        """nizk/mod.rs:27-52"""
+        T.append_protocol_name(b"knowledge proof")
+        t1 = tape.random_scalar(b"t1")
+        t2 = tape.random_scalar(b"t2")
+        Cc = oc.commit_scalar(x, r, gens_n).compress()
+        T.append_point(b"C", Cc)
+        alpha = oc.commit_scalar(t1, t2, gens_n).compress()
+        T.append_point(b"alpha", alpha)
+        c = T.challenge_scalar(b"c")
+        return KnowledgeProof(alpha, (x * c + t1) % Q, (r * c + t2) % Q), Cc
+
+    def verify(self, gens_n, T, Cc):
+        """nizk/mod.rs:54-75"""
+        T.append_protocol_name(b"knowledge proof")
+        T.append_point(b"C", Cc)
+        T.append_point(b"alpha", self.alpha)
+        c = T.challenge_scalar(b"c")
+        lhs = oc.commit_scalar(self.z1, self.z2, gens_n).compress()
+        rhs = (_unpack(Cc) * c + _unpack(self.alpha)).compress()
+        if lhs != rhs:
+            raise ProofVerifyError("KnowledgeProof")
+
+
+def _unpack(b):
+    p = oc.Point.decompress(b)
+    if p is None:
+        raise ProofVerifyError("DecompressionError")
+    return p
+
+
+@dataclass
+class EqualityProof:
+    alpha: bytes
+    z: int
+
+    @staticmethod
+    def prove(gens_n, T, tape, v1, s1, v2, s2):
+        """nizk/mod.rs:88-116"""
+        T.append_protocol_name(b"equality proof")
+        r = tape.random_scalar(b"r")
+        C1 = oc.commit_scalar(v1, s1, gens_n).compress()
+        T.append_point(b"C1", C1)
+        C2 = oc.commit_scalar(v2, s2, gens_n).compress()
+        T.append_point(b"C2", C2)
+        alpha = (gens_n.h * r).compress()
+        T.append_point(b"alpha", alpha)
+        c = T.challenge_scalar(b"c")
+        return EqualityProof(alpha, (c * (s1 - s2) + r) % Q), C1, C2
+
+    def verify(self, gens_n, T, C1, C2):
+        """nizk/mod.rs:118-143"""
+        T.append_protocol_name(b"equality proof")
+        T.append_point(b"C1", C1)
+        T.append_point(b"C2", C2)
+        T.append_point(b"alpha", self.alpha)
+        c = T.challenge_scalar(b"c")
+        Cd = _unpack(C1) - _unpack(C2)
+        rhs = (Cd * c + _unpack(self.alpha)).compress()
+        lhs = (gens_n.h * self.z).compress()
+        if lhs != rhs:
+            raise ProofVerifyError("EqualityProof")
+
+
+@dataclass
+class ProductProof:
+    alpha: bytes
+    beta: bytes
+    delta: bytes
+    z: Tuple[int, int, int, int, int]
+
+    @staticmethod
+    def prove(gens_n, T, tape, x, rX, y, rY, z, rZ):
+        """nizk/mod.rs:159-229"""
+        T.append_protocol_name(b"product proof")
+        b1, b2, b3, b4, b5 = (tape.random_scalar(l) for l in (b"b1", b"b2", b"b3", b"b4", b"b5"))
+        X = oc.commit_scalar(x, rX, gens_n).compress(); T.append_point(b"X", X)
+        Y = oc.commit_scalar(y, rY, gens_n).compress(); T.append_point(b"Y", Y)
+        Z = oc.commit_scalar(z, rZ, gens_n).compress(); T.append_point(b"Z", Z)
+        alpha = oc.commit_scalar(b1, b2, gens_n).compress(); T.append_point(b"alpha", alpha)
+        beta = oc.commit_scalar(b3, b4, gens_n).compress(); T.append_point(b"beta", beta)
+        gens_X = oc.MultiCommitGens(1, _unpack(X).buf.reshape(1, 20), gens_n.h)  # :199-204
+        delta = oc.commit_scalar(b3, b5, gens_X).compress(); T.append_point(b"delta", delta)
+        c = T.challenge_scalar(b"c")
+        zz = ((b1 + c * x) % Q, (b2 + c * rX) % Q, (b3 + c * y) % Q, (b4 + c * rY) % Q, (b5 + c * (rZ - rX * y)) % Q)
+        return ProductProof(alpha, beta, delta, zz), X, Y, Z
+
+    @staticmethod
+    def _check_equality(Pp, X, c, gens_n, z1, z2):
+        lhs = (_unpack(Pp) + _unpack(X) * c).compress()
+        return lhs == oc.commit_scalar(z1, z2, gens_n).compress()
+
+    def verify(self, gens_n, T, X, Y, Z):
+        """nizk/mod.rs:245-290"""
+        T.append_protocol_name(b"product proof")
+        for l, p in ((b"X", X), (b"Y", Y), (b"Z", Z), (b"alpha", self.alpha), (b"beta", self.beta), (b"delta", self.delta)):
+            T.append_point(l, p)
+        z1, z2, z3, z4, z5 = self.z
+        c = T.challenge_scalar(b"c")
+        gens_X = oc.MultiCommitGens(1, _unpack(X).buf.reshape(1, 20), gens_n.h)
+        ok = (ProductProof._check_equality(self.alpha, X, c, gens_n, z1, z2)
+              and ProductProof._check_equality(self.beta, Y, c, gens_n, z3, z4)
+              and ProductProof._check_equality(self.delta, Z, c, gens_X, z3, z5))
+        if not ok:
+            raise ProofVerifyError("ProductProof")
+
+
+@dataclass
+class DotProductProof:
+    delta: bytes
+    beta: bytes
+    z: List[int]
+    z_delta: int
+    z_beta: int
+
+    @staticmethod
+    def prove(gens_1, gens_n, T, tape, x_vec, blind_x, a_vec, y, blind_y):
+        """nizk/mod.rs:311-370"""
+        T.append_protocol_name(b"dot product proof")
+        n = len(x_vec)
+        assert len(a_vec) == n and gens_n.n == n and gens_1.n == 1
+        d_vec = tape.random_vector(b"d_vec", n)
+        r_delta = tape.random_scalar(b"r_delta")
+        r_beta = tape.random_scalar(b"r_beta")
+        Cx = oc.commit_vec(x_vec, blind_x, gens_n).compress(); T.append_point(b"Cx", Cx)
+        Cy = oc.commit_scalar(y, blind_y, gens_1).compress(); T.append_point(b"Cy", Cy)
+        T.append_scalars(b"a", a_vec)
+        delta = oc.commit_vec(d_vec, r_delta, gens_n).compress(); T.append_point(b"delta", delta)
+        dotp = sum(a * d for a, d in zip(a_vec, d_vec)) % Q
+        beta = oc.commit_scalar(dotp, r_beta, gens_1).compress(); T.append_point(b"beta", beta)
+        c = T.challenge_scalar(b"c")
+        z = [(c * x_vec[i] + d_vec[i]) % Q for i in range(n)]
+        return DotProductProof(delta, beta, z, (c * blind_x + r_delta) % Q, (c * blind_y + r_beta) % Q), Cx, Cy
+
+    def verify(self, gens_1, gens_n, T, a, Cx, Cy):
+        """nizk/mod.rs:372-405"""
+        T.append_protocol_name(b"dot product proof")
+        T.append_point(b"Cx", Cx)
+        T.append_point(b"Cy", Cy)
+        T.append_scalars(b"a", a)
+        T.append_point(b"delta", self.delta)
+        T.append_point(b"beta", self.beta)
+        c = T.challenge_scalar(b"c")
+        ok = (_unpack(Cx) * c + _unpack(self.delta)) == oc.commit_vec(self.z, self.z_delta, gens_n)
+        dz = sum(z * ai for z, ai in zip(self.z, a)) % Q
+        ok &= (_unpack(Cy) * c + _unpack(self.beta)) == oc.commit_scalar(dz, self.z_beta, gens_1)
+        if not ok:
+            raise ProofVerifyError("DotProductProof")
+
+
+class DotProductProofGens:
+    """nizk/mod.rs:407-419"""
+
+    def __init__(self, n, label):
+        self.n = n
+        self.gens_n, self.gens_1 = oc.MultiCommitGens.new(n + 1, label).split_at(n)
+
+
+# ----------------------------------------------------------------------------- nizk/bullet.rs
+@dataclass
+class BulletReductionProof:
+    L_vec: List[bytes]
+    R_vec: List[bytes]
+
+    @staticmethod
+    def prove(T, Qp, G_arr, H, a_vec, b_vec, blind, blinds_vec):
+        """nizk/bullet.rs:32-132.  a_vec / b_vec: lists of ints; G_arr (n,20) points"""
+        n = len(a_vec)
+        assert n & (n - 1) == 0 and len(G_arr) == n and len(b_vec) == n and len(blinds_vec) == oc.log_2(n)
+        G = [oc.Point(G_arr[i].copy()) for i in range(n)]
+        a, b = list(a_vec), list(b_vec)
+        L_vec, R_vec = [], []
+        blind_final = blind
+        QH = np.stack([Qp.buf, H.buf])
+        it = iter(blinds_vec)
+        while n != 1:
+            n //= 2
+            a_L, a_R, b_L, b_R, G_L, G_R = a[:n], a[n:2 * n], b[:n], b[n:2 * n], G[:n], G[n:2 * n]
+            c_L = sum(x * y for x, y in zip(a_L, b_R)) % Q
+            c_R = sum(x * y for x, y in zip(a_R, b_L)) % Q
+            blind_L, blind_R = next(it)
+            Lp = oc.msm(a_L + [c_L, blind_L], np.concatenate([oc.points_array(G_R), QH]))
+            Rp = oc.msm(a_R + [c_R, blind_R], np.concatenate([oc.points_array(G_L), QH]))
+            Lc, Rc = Lp.compress(), Rp.compress()
+            T.append_point(b"L", Lc)
+            T.append_point(b"R", Rc)
+            u = T.challenge_scalar(b"u")
+            u_inv = inv(u)
+            for i in range(n):
+                a_L[i] = (a_L[i] * u + u_inv * a_R[i]) % Q
+                b_L[i] = (b_L[i] * u_inv + u * b_R[i]) % Q
+                G_L[i] = oc.msm([u_inv, u], np.stack([G_L[i].buf, G_R[i].buf]))
+            blind_final = (blind_final + blind_L * u * u + blind_R * u_inv * u_inv) % Q
+            L_vec.append(Lc)
+            R_vec.append(Rc)
+            a, b, G = a_L, b_L, G_L
+        Gamma_hat = oc.msm([a[0], a[0] * b[0] % Q, blind_final], np.stack([G[0].buf, Qp.buf, H.buf]))
+        return BulletReductionProof(L_vec, R_vec), Gamma_hat, a[0], b[0], G[0], blind_final
+
+    def verification_scalars(self, n, T):
+        """nizk/bullet.rs:137-185"""
+        lg_n = len(self.L_vec)
+        if lg_n >= 32 or n != (1 << lg_n):
+            raise ProofVerifyError("bullet size")
+        ch = []
+        for Lc, Rc in zip(self.L_vec, self.R_vec):
+            T.append_point(b"L", Lc)
+            T.append_point(b"R", Rc)
+            ch.append(T.challenge_scalar(b"u"))
+        ch_inv = [inv(c) for c in ch]
+        allinv = 1
+        for c in ch_inv:
+            allinv = allinv * c % Q
+        ch_sq = [c * c % Q for c in ch]
+        ch_inv_sq = [c * c % Q for c in ch_inv]
+        s = [allinv]
+        for i in range(1, n):
+            lg_i = i.bit_length() - 1
+            k = 1 << lg_i
+            s.append(s[i - k] * ch_sq[(lg_n - 1) - lg_i] % Q)
+        return ch_sq, ch_inv_sq, s
+
+    def verify(self, n, a, T, Gamma, G_arr):
+        """nizk/bullet.rs:191-225"""
+        u_sq, u_inv_sq, s = self.verification_scalars(n, T)
+        Ls = [_unpack(p) for p in self.L_vec]
+        Rs = [_unpack(p) for p in self.R_vec]
+        G_hat = oc.msm(s, G_arr)
+        a_hat = sum(x * y for x, y in zip(a, s)) % Q
+        Gamma_hat = oc.msm(u_sq + u_inv_sq + [1], oc.points_array(Ls + Rs + [Gamma]))
+        return G_hat, Gamma_hat, a_hat
+
+
+@dataclass
+class DotProductProofLog:
+    bullet_reduction_proof: BulletReductionProof
+    delta: bytes
+    beta: bytes
+    z1: int
+    z2: int
+
+    @staticmethod
+    def prove(gens, T, tape, x_vec, blind_x, a_vec, y, blind_y):
+        """nizk/mod.rs:440-525.  x_vec / a_vec: lists of ints or Montgomery arrays"""
+        T.append_protocol_name(b"dot product proof (log)")
+        x_ints = oc.to_ints(x_vec) if isinstance(x_vec, np.ndarray) else list(x_vec)
+        a_ints = oc.to_ints(a_vec) if isinstance(a_vec, np.ndarray) else list(a_vec)
+        n = len(x_ints)
+        assert len(a_ints) == n and gens.n == n
+        d = tape.random_scalar(b"d")
+        r_delta = tape.random_scalar(b"r_delta")
+        r_beta = tape.random_scalar(b"r_delta")  # sic: label reused, nizk/mod.rs:459
+        lg_n = oc.log_2(n)
+        v1 = tape.random_vector(b"blinds_vec_1", lg_n)
+        v2 = tape.random_vector(b"blinds_vec_2", lg_n)
+        blinds_vec = list(zip(v1, v2))
+        Cx = oc.commit_vec(x_ints, blind_x, gens.gens_n).compress(); T.append_point(b"Cx", Cx)
+        Cy = oc.commit_scalar(y, blind_y, gens.gens_1).compress(); T.append_point(b"Cy", Cy)
+        T.append_scalars(b"a", a_ints)
+        r = T.challenge_scalar(b"r")
+        gens_1_scaled = gens.gens_1.scale(r)
+        blind_Gamma = (blind_x + r * blind_y) % Q
+        brp, _Gamma_hat, x_hat, a_hat, g_hat, rhat_Gamma = BulletReductionProof.prove(
+            T, gens_1_scaled.g(0), gens.gens_n.G, gens.gens_n.h, x_ints, a_ints, blind_Gamma, blinds_vec)
+        y_hat = x_hat * a_hat % Q
+        gens_hat = oc.MultiCommitGens(1, g_hat.buf.reshape(1, 20), gens.gens_1.h)
+        delta = oc.commit_scalar(d, r_delta, gens_hat).compress(); T.append_point(b"delta", delta)
+        beta = oc.commit_scalar(d, r_beta, gens_1_scaled).compress(); T.append_point(b"beta", beta)
+        c = T.challenge_scalar(b"c")
+        z1 = (d + c * y_hat) % Q
+        z2 = (a_hat * (c * rhat_Gamma + r_beta) + r_delta) % Q
+        return DotProductProofLog(brp, delta, beta, z1, z2), Cx, Cy
+
+    def verify(self, n, gens, T, a, Cx, Cy):
+        """nizk/mod.rs:527-583"""
+        a = oc.to_ints(a) if isinstance(a, np.ndarray) else list(a)
+        assert gens.n == n and len(a) == n
+        T.append_protocol_name(b"dot product proof (log)")
+        T.append_point(b"Cx", Cx)
+        T.append_point(b"Cy", Cy)
+        T.append_scalars(b"a", a)
+        r = T.challenge_scalar(b"r")
+        gens_1_scaled = gens.gens_1.scale(r)
+        Gamma = _unpack(Cx) + _unpack(Cy) * r
+        g_hat, Gamma_hat, a_hat = self.bullet_reduction_proof.verify(n, a, T, Gamma, gens.gens_n.G)
+        T.append_point(b"delta", self.delta)
+        T.append_point(b"beta", self.beta)
+        c = T.challenge_scalar(b"c")
+        lhs = ((Gamma_hat * c + _unpack(self.beta)) * a_hat + _unpack(self.delta)).compress()
+        rhs = ((g_hat + gens_1_scaled.g(0) * a_hat) * self.z1 + gens_1_scaled.h * self.z2).compress()
+        if lhs != rhs:
+            raise ProofVerifyError("DotProductProofLog")
+
+
+# ----------------------------------------------------------------------------- dense_mlpoly.rs commitment / eval proof
+def factored_lens(ell):
+    """EqPolynomial::compute_factored_lens (dense_mlpoly.rs:86-88)"""
+    return ell // 2, ell - ell // 2
+
+
+class PolyCommitmentGens:
+    """dense_mlpoly.rs:24-36"""
+
+    def __init__(self, num_vars, label):
+        _, right = factored_lens(num_vars)
+        self.gens = DotProductProofGens(1 << right, label)
+
+
+@dataclass
+class PolyCommitment:
+    C: List[bytes]
+
+    def append_to_transcript(self, label, T):
+        """dense_mlpoly.rs:292-300"""
+        T.append_message(label, b"poly_commitment_begin")
+        for c in self.C:
+            T.append_point(b"poly_commitment_share", c)
+        T.append_message(label, b"poly_commitment_end")
+
+
+def poly_commit(Z, gens, tape=None):
+    """DensePolynomial::commit (dense_mlpoly.rs:179-204) -> (PolyCommitment, blinds)"""
+    n = len(Z)
+    ell = oc.log_2(n)
+    assert n == 1 << ell
+    lv, rv = factored_lens(ell)
+    L_size, R_size = 1 << lv, 1 << rv
+    blinds = tape.random_vector(b"poly_blinds", L_size) if tape is not None else [0] * L_size
+    return PolyCommitment(oc.commit_rows(Z, L_size, R_size, blinds, gens.gens.gens_n)), blinds
+
+
+@dataclass
+class PolyEvalProof:
+    proof: DotProductProofLog
+
+    @staticmethod
+    def prove(Z, blinds_opt, r, Zr, blind_Zr_opt, gens, T, tape):
+        """dense_mlpoly.rs:312-365"""
+        T.append_protocol_name(b"polynomial evaluation proof")
+        assert len(Z) == 1 << len(r)
+        lv, rv = factored_lens(len(r))
+        L_size, R_size = 1 << lv, 1 << rv
+        blinds = blinds_opt if blinds_opt is not None else [0] * L_size
+        assert len(blinds) == L_size
+        blind_Zr = blind_Zr_opt if blind_Zr_opt is not None else 0
+        Lv = oc.eq_evals(r[:lv])  # compute_factored_evals, dense_mlpoly.rs:90-98
+        Rv = oc.eq_evals(r[lv:])
+        LZ = oc.bound_rows(Z, Lv, L_size, R_size)
+        LZ_blind = sum(b * l for b, l in zip(blinds, oc.to_ints(Lv))) % Q
+        proof, _C_LR, C_Zr_prime = DotProductProofLog.prove(gens.gens, T, tape, LZ, LZ_blind, Rv, Zr, blind_Zr)
+        return PolyEvalProof(proof), C_Zr_prime
+
+    def verify(self, gens, T, r, C_Zr, comm):
+        """dense_mlpoly.rs:367-389"""
+        T.append_protocol_name(b"polynomial evaluation proof")
+        lv, _ = factored_lens(len(r))
+        Lv = oc.eq_evals(r[:lv])
+        Rv = oc.eq_evals(r[lv:])
+        C_dec = oc.points_array([_unpack(c) for c in comm.C])
+        C_LZ = oc.msm(Lv, C_dec).compress()
+        self.proof.verify(len(Rv), gens.gens, T, Rv, C_LZ, C_Zr)
+
+    def verify_plain(self, gens, T, r, Zr, comm):
+        """dense_mlpoly.rs:391-404"""
+        C_Zr = oc.commit_scalar(Zr, 0, gens.gens.gens_1).compress()
+        self.verify(gens, T, r, C_Zr, comm)
+
+
+# ----------------------------------------------------------------------------- sumcheck.rs
+@dataclass
+class SumcheckInstanceProof:
+    compressed_polys: List[CompressedUniPoly]
+
+    def verify(self, claim, num_rounds, degree_bound, T):
+        """sumcheck.rs:27-62"""
+        e, r = claim, []
+        assert len(self.compressed_polys) == num_rounds
+        for cp in self.compressed_polys:
+            poly = cp.decompress(e)
+            assert poly.degree() == degree_bound
+            assert (poly.eval_at_zero() + poly.eval_at_one()) % Q == e % Q
+            poly.append_to_transcript(b"poly", T)
+            r_i = T.challenge_scalar(b"challenge_nextround")
+            r.append(r_i)
+            e = poly.evaluate(r_i)
+        return e, r
+
+
+def prove_cubic_batched(claim, num_rounds, par, seq, coeffs, T):
+    """SumcheckInstanceProof::prove_cubic_batched (sumcheck.rs:254-424), comb = A*B*C (product_tree.rs:283-286).
+    par = (list A, list B, C_par) sharing C_par; seq = (list A, list B, list C).  Arrays are folded; the folded
+    arrays are returned through the lists (Python arrays are views, so we rebind)."""
+    A_par, B_par, C_par = par
+    A_seq, B_seq, C_seq = seq
+    e, r, polys = claim, [], []
+    for _ in range(num_rounds):
+        evals = []
+        for A, B in zip(A_par, B_par):
+            evals.append(oc.sc_eval_cubic(A, B, C_par))
+        for A, B, Cc in zip(A_seq, B_seq, C_seq):
+            evals.append(oc.sc_eval_cubic(A, B, Cc))
+        e0 = sum(ev[0] * c for ev, c in zip(evals, coeffs)) % Q
+        e2 = sum(ev[1] * c for ev, c in zip(evals, coeffs)) % Q
+        e3 = sum(ev[2] * c for ev, c in zip(evals, coeffs)) % Q
+        poly = UniPoly.from_evals([e0, (e - e0) % Q, e2, e3])
+        poly.append_to_transcript(b"poly", T)
+        r_j = T.challenge_scalar(b"challenge_nextround")
+        r.append(r_j)
+        for i in range(len(A_par)):
+            A_par[i] = oc.bound_top(A_par[i], r_j)
+            B_par[i] = oc.bound_top(B_par[i], r_j)
+        C_par = oc.bound_top(C_par, r_j)
+        for i in range(len(A_seq)):
+            A_seq[i] = oc.bound_top(A_seq[i], r_j)
+            B_seq[i] = oc.bound_top(B_seq[i], r_j)
+            C_seq[i] = oc.bound_top(C_seq[i], r_j)
+        e = poly.evaluate(r_j)
+        polys.append(poly.compress())
+    claims_prod = ([oc.arr_get(a, 0) for a in A_par], [oc.arr_get(b, 0) for b in B_par], oc.arr_get(C_par, 0))
+    claims_dotp = ([oc.arr_get(a, 0) for a in A_seq], [oc.arr_get(b, 0) for b in B_seq], [oc.arr_get(c, 0) for c in C_seq])
+    return SumcheckInstanceProof(polys), r, claims_prod, claims_dotp
+
+
+@dataclass
+class ZKSumcheckInstanceProof:
+    comm_polys: List[bytes]
+    comm_evals: List[bytes]
+    proofs: List[DotProductProof]
+
+    @staticmethod
+    def _prove(claim, blind_claim, num_rounds, polys, degree, gens_1, gens_n, T, tape):
+        """prove_quad (sumcheck.rs:428-586, degree 2, comb A*B) and prove_cubic_with_additive_term
+        (sumcheck.rs:588-776, degree 3, comb A*(B*C-D)); identical schedule apart from the eval loop."""
+        blinds_poly = tape.random_vector(b"blinds_poly", num_rounds)
+        blinds_evals = tape.random_vector(b"blinds_evals", num_rounds)
+        claim_per_round = claim
+        comm_claim_per_round = oc.commit_scalar(claim_per_round, blind_claim, gens_1).compress()
+        r, comm_polys, comm_evals, proofs = [], [], [], []
+        for j in range(num_rounds):
+            if degree == 2:
+                e0, e2 = oc.sc_eval_quad(polys[0], polys[1])
+                evals = [e0, (claim_per_round - e0) % Q, e2]
+            else:
+                e0, e2, e3 = oc.sc_eval_cubic(polys[0], polys[1], polys[2], polys[3])
+                evals = [e0, (claim_per_round - e0) % Q, e2, e3]
+            poly = UniPoly.from_evals(evals)
+            comm_poly = oc.commit_vec(poly.coeffs, blinds_poly[j], gens_n).compress()
+            T.append_point(b"comm_poly", comm_poly)
+            comm_polys.append(comm_poly)
+            r_j = T.challenge_scalar(b"challenge_nextround")
+            polys = [oc.bound_top(p, r_j) for p in polys]
+            ev = poly.evaluate(r_j)
+            comm_eval = oc.commit_scalar(ev, blinds_evals[j], gens_1).compress()
+            T.append_point(b"comm_claim_per_round", comm_claim_per_round)
+            T.append_point(b"comm_eval", comm_eval)
+            w = T.challenge_vector(b"combine_two_claims_to_one", 2)
+            target = (w[0] * claim_per_round + w[1] * ev) % Q
+            comm_target = oc.msm(w, oc.points_array([_unpack(comm_claim_per_round), _unpack(comm_eval)])).compress()
+            blind_sc = blind_claim if j == 0 else blinds_evals[j - 1]
+            blind = (w[0] * blind_sc + w[1] * blinds_evals[j]) % Q
+            assert oc.commit_scalar(target, blind, gens_1).compress() == comm_target  # sumcheck.rs:531 / :722
+            a_sc = [2] + [1] * degree
+            a_eval = [1]
+            for _ in range(degree):
+                a_eval.append(a_eval[-1] * r_j % Q)
+            a = [(w[0] * a_sc[i] + w[1] * a_eval[i]) % Q for i in range(degree + 1)]
+            proof, _, _ = DotProductProof.prove(gens_1, gens_n, T, tape, poly.coeffs, blinds_poly[j], a, target, blind)
+            claim_per_round = ev
+            comm_claim_per_round = comm_eval
+            proofs.append(proof)
+            r.append(r_j)
+            comm_evals.append(comm_claim_per_round)
+        finals = [oc.arr_get(p, 0) for p in polys]
+        return ZKSumcheckInstanceProof(comm_polys, comm_evals, proofs), r, finals, blinds_evals[num_rounds - 1]
+
+    @staticmethod
+    def prove_quad(claim, blind_claim, num_rounds, A, B, gens_1, gens_n, T, tape):
+        return ZKSumcheckInstanceProof._prove(claim, blind_claim, num_rounds, [A, B], 2, gens_1, gens_n, T, tape)
+
+    @staticmethod
+    def prove_cubic_with_additive_term(claim, blind_claim, num_rounds, A, B, Cc, D, gens_1, gens_n, T, tape):
+        return ZKSumcheckInstanceProof._prove(claim, blind_claim, num_rounds, [A, B, Cc, D], 3, gens_1, gens_n, T, tape)
+
+    def verify(self, comm_claim, num_rounds, degree_bound, gens_1, gens_n, T):
+        """sumcheck.rs:84-179"""
+        assert gens_n.n == degree_bound + 1
+        assert len(self.comm_polys) == num_rounds and len(self.comm_evals) == num_rounds
+        r = []
+        for i in range(num_rounds):
+            T.append_point(b"comm_poly", self.comm_polys[i])
+            r_i = T.challenge_scalar(b"challenge_nextround")
+            comm_claim_per_round = comm_claim if i == 0 else self.comm_evals[i - 1]
+            comm_eval = self.comm_evals[i]
+            T.append_point(b"comm_claim_per_round", comm_claim_per_round)
+            T.append_point(b"comm_eval", comm_eval)
+            w = T.challenge_vector(b"combine_two_claims_to_one", 2)
+            comm_target = oc.msm(w, oc.points_array([_unpack(comm_claim_per_round), _unpack(comm_eval)])).compress()
+            a_sc = [2] + [1] * degree_bound
+            a_eval = [1]
+            for _ in range(degree_bound):
+                a_eval.append(a_eval[-1] * r_i % Q)
+            a = [(w[0] * a_sc[k] + w[1] * a_eval[k]) % Q for k in range(degree_bound + 1)]
+            try:
+                self.proofs[i].verify(gens_1, gens_n, T, a, self.comm_polys[i], comm_target)
+            except ProofVerifyError:
+                raise ProofVerifyError("ZKSumcheck round %d" % i)
+            r.append(r_i)
+        return self.comm_evals[-1], r
+
+
+# ----------------------------------------------------------------------------- r1csproof.rs
+class R1CSSumcheckGens:
+    """r1csproof.rs:39-59"""
+
+    def __init__(self, label, gens_1_ref):
+        self.gens_1 = gens_1_ref
+        self.gens_3 = oc.MultiCommitGens.new(3, label)
+        self.gens_4 = oc.MultiCommitGens.new(4, label)
+
+
+class R1CSGens:
+    """r1csproof.rs:61-74"""
+
+    def __init__(self, label, _num_cons, num_vars):
+        self.gens_pc = PolyCommitmentGens(oc.log_2(num_vars), label)
+        self.gens_sc = R1CSSumcheckGens(label, self.gens_pc.gens.gens_1)
+
+
+@dataclass
+class R1CSProof:
+    comm_vars: PolyCommitment
+    sc_proof_phase1: ZKSumcheckInstanceProof
+    claims_phase2: Tuple[bytes, bytes, bytes, bytes]
+    pok_claims_phase2: Tuple[KnowledgeProof, ProductProof]
+    proof_eq_sc_phase1: EqualityProof
+    sc_proof_phase2: ZKSumcheckInstanceProof
+    comm_vars_at_ry: bytes
+    proof_eval_vars_at_ry: PolyEvalProof
+    proof_eq_sc_phase2: EqualityProof
+
+    @staticmethod
+    def prove(inst, vars_arr, input_ints, gens, T, tape):
+        """r1csproof.rs:144-349.  inst: r1cs.R1CSShape; vars_arr: (num_vars,4) Montgomery array"""
+        T.append_protocol_name(b"R1CS proof")
+        num_vars = len(vars_arr)
+        assert len(input_ints) < num_vars
+        T.append_scalars(b"input", input_ints)
+        # polycommit
+        comm_vars, blinds_vars = poly_commit(vars_arr, gens.gens_pc, tape)
+        comm_vars.append_to_transcript(b"poly_commitment", T)
+        # z = vars || 1 || input || 0...
+        z = np.concatenate([vars_arr, oc.to_arr([1] + list(input_ints)), oc.zeros(num_vars - len(input_ints) - 1)])
+        num_rounds_x, num_rounds_y = oc.log_2(inst.num_cons), oc.log_2(len(z))
+        tau = T.challenge_vector(b"challenge_tau", num_rounds_x)
+        poly_tau = oc.eq_evals(tau)
+        poly_Az, poly_Bz, poly_Cz = inst.multiply_vec(inst.num_cons, len(z), z)
+        sc1, rx, claims1, blind_claim_postsc1 = ZKSumcheckInstanceProof.prove_cubic_with_additive_term(
+            0, 0, num_rounds_x, poly_tau, poly_Az, poly_Bz, poly_Cz, gens.gens_sc.gens_1, gens.gens_sc.gens_4, T, tape)
+        tau_claim, Az_claim, Bz_claim, Cz_claim = claims1
+        Az_blind, Bz_blind, Cz_blind, prod_Az_Bz_blind = (tape.random_scalar(l) for l in (b"Az_blind", b"Bz_blind", b"Cz_blind", b"prod_Az_Bz_blind"))
+        pok_Cz_claim, comm_Cz_claim = KnowledgeProof.prove(gens.gens_sc.gens_1, T, tape, Cz_claim, Cz_blind)
+        prod = Az_claim * Bz_claim % Q
+        proof_prod, comm_Az_claim, comm_Bz_claim, comm_prod = ProductProof.prove(
+            gens.gens_sc.gens_1, T, tape, Az_claim, Az_blind, Bz_claim, Bz_blind, prod, prod_Az_Bz_blind)
+        T.append_point(b"comm_Az_claim", comm_Az_claim)
+        T.append_point(b"comm_Bz_claim", comm_Bz_claim)
+        T.append_point(b"comm_Cz_claim", comm_Cz_claim)
+        T.append_point(b"comm_prod_Az_Bz_claims", comm_prod)
+        blind_expected_claim_postsc1 = tau_claim * (prod_Az_Bz_blind - Cz_blind) % Q
+        claim_post_phase1 = (Az_claim * Bz_claim - Cz_claim) * tau_claim % Q
+        proof_eq_sc_phase1, _, _ = EqualityProof.prove(gens.gens_sc.gens_1, T, tape, claim_post_phase1, blind_expected_claim_postsc1,
+                                                       claim_post_phase1, blind_claim_postsc1)
+        r_A = T.challenge_scalar(b"challenge_Az")
+        r_B = T.challenge_scalar(b"challenge_Bz")
+        r_C = T.challenge_scalar(b"challenge_Cz")
+        claim_phase2 = (r_A * Az_claim + r_B * Bz_claim + r_C * Cz_claim) % Q
+        blind_claim_phase2 = (r_A * Az_blind + r_B * Bz_blind + r_C * Cz_blind) % Q
+        evals_rx = oc.eq_evals(rx)
+        eA, eB, eC = inst.compute_eval_table_sparse(inst.num_cons, len(z), evals_rx)
+        evals_ABC = oc.lincomb3(eA, eB, eC, r_A, r_B, r_C)
+        sc2, ry, claims2, blind_claim_postsc2 = ZKSumcheckInstanceProof.prove_quad(
+            claim_phase2, blind_claim_phase2, num_rounds_y, z.copy(), evals_ABC, gens.gens_sc.gens_1, gens.gens_sc.gens_3, T, tape)
+        eval_vars_at_ry = oc.evaluate(vars_arr, ry[1:])
+        blind_eval = tape.random_scalar(b"blind_eval")
+        proof_eval_vars_at_ry, comm_vars_at_ry = PolyEvalProof.prove(vars_arr, blinds_vars, ry[1:], eval_vars_at_ry, blind_eval, gens.gens_pc, T, tape)
+        blind_eval_Z_at_ry = (1 - ry[0]) * blind_eval % Q
+        blind_expected_claim_postsc2 = claims2[1] * blind_eval_Z_at_ry % Q
+        claim_post_phase2 = claims2[0] * claims2[1] % Q
+        proof_eq_sc_phase2, _, _ = EqualityProof.prove(gens.gens_pc.gens.gens_1, T, tape, claim_post_phase2, blind_expected_claim_postsc2,
+                                                       claim_post_phase2, blind_claim_postsc2)
+        return (R1CSProof(comm_vars, sc1, (comm_Az_claim, comm_Bz_claim, comm_Cz_claim, comm_prod), (pok_Cz_claim, proof_prod),
+                          proof_eq_sc_phase1, sc2, comm_vars_at_ry, proof_eval_vars_at_ry, proof_eq_sc_phase2), rx, ry)
+
+    def verify(self, num_vars, num_cons, input_ints, evals, T, gens):
+        """r1csproof.rs:351-489"""
+        T.append_protocol_name(b"R1CS proof")
+        T.append_scalars(b"input", input_ints)
+        n = num_vars
+        self.comm_vars.append_to_transcript(b"poly_commitment", T)
+        num_rounds_x, num_rounds_y = oc.log_2(num_cons), oc.log_2(2 * num_vars)
+        tau = T.challenge_vector(b"challenge_tau", num_rounds_x)
+        claim_phase1 = oc.commit_scalar(0, 0, gens.gens_sc.gens_1).compress()
+        comm_claim_post_phase1, rx = self.sc_proof_phase1.verify(claim_phase1, num_rounds_x, 3, gens.gens_sc.gens_1, gens.gens_sc.gens_4, T)
+        comm_Az, comm_Bz, comm_Cz, comm_prod = self.claims_phase2
+        pok_Cz, proof_prod = self.pok_claims_phase2
+        pok_Cz.verify(gens.gens_sc.gens_1, T, comm_Cz)
+        proof_prod.verify(gens.gens_sc.gens_1, T, comm_Az, comm_Bz, comm_prod)
+        T.append_point(b"comm_Az_claim", comm_Az)
+        T.append_point(b"comm_Bz_claim", comm_Bz)
+        T.append_point(b"comm_Cz_claim", comm_Cz)
+        T.append_point(b"comm_prod_Az_Bz_claims", comm_prod)
+        taus_bound_rx = 1
+        for a, b in zip(rx, tau):
+            taus_bound_rx = taus_bound_rx * (a * b + (1 - a) * (1 - b)) % Q
+        expected_claim_post_phase1 = ((_unpack(comm_prod) - _unpack(comm_Cz)) * taus_bound_rx).compress()
+        self.proof_eq_sc_phase1.verify(gens.gens_sc.gens_1, T, expected_claim_post_phase1, comm_claim_post_phase1)
+        r_A = T.challenge_scalar(b"challenge_Az")
+        r_B = T.challenge_scalar(b"challenge_Bz")
+        r_C = T.challenge_scalar(b"challenge_Cz")
+        comm_claim_phase2 = oc.msm([r_A, r_B, r_C], oc.points_array([_unpack(comm_Az), _unpack(comm_Bz), _unpack(comm_Cz)])).compress()
+        comm_claim_post_phase2, ry = self.sc_proof_phase2.verify(comm_claim_phase2, num_rounds_y, 2, gens.gens_sc.gens_1, gens.gens_sc.gens_3, T)
+        self.proof_eval_vars_at_ry.verify(gens.gens_pc, T, ry[1:], self.comm_vars_at_ry, self.comm_vars)
+        # SparsePolynomial::evaluate over (0,1),(i+1,input[i])  (r1csproof.rs:454-464, sparse_mlpoly.rs:1577-1593)
+        nb = oc.log_2(n)
+        entries = [(0, 1)] + [(i + 1, v) for i, v in enumerate(input_ints)]
+        poly_input_eval = 0
+        for idx, val in entries:
+            chi = 1
+            for k in range(nb):
+                bit = (idx >> (nb - k - 1)) & 1
+                chi = chi * (ry[1 + k] if bit else (1 - ry[1 + k])) % Q
+            poly_input_eval = (poly_input_eval + chi * val) % Q
+        comm_eval_Z_at_ry = oc.msm([(1 - ry[0]) % Q, ry[0]], oc.points_array(
+            [_unpack(self.comm_vars_at_ry), oc.commit_scalar(poly_input_eval, 0, gens.gens_pc.gens.gens_1)]))
+        eA, eB, eC = evals
+        expected_claim_post_phase2 = (comm_eval_Z_at_ry * ((r_A * eA + r_B * eB + r_C * eC) % Q)).compress()
+        self.proof_eq_sc_phase2.verify(gens.gens_sc.gens_1, T, expected_claim_post_phase2, comm_claim_post_phase2)
+        return rx, ry
