@@ -1,0 +1,488 @@
+// spartan_b200 — extern "C" boundary (include/spartan_b200.h).  Catches every exception and maps it to a status code.
+#include "../../include/spartan_b200.h"
+#include <stdlib.h>
+#include <algorithm>
+#include <sstream>
+#include "prover.hpp"
+#include "snark.hpp"
+
+using namespace sp;
+
+struct sp_ctx { Ctx c; explicit sp_ctx(int d) : c(d) {} };
+struct sp_poly { Ctx* ctx; DevBuf<u256> d; size_t len; };
+struct sp_gens { std::unique_ptr<GenSet> set; size_t n; };
+struct sp_instance { Instance inst; };
+struct sp_nizk_gens { std::unique_ptr<R1CSGens> g; };
+struct sp_snark_gens { std::unique_ptr<SnarkGens> g; };
+struct sp_snark_encoding { std::unique_ptr<SnarkEncoding> e; };
+
+static std::string g_create_error;
+
+#define SP_TRY(ctxp) try {
+#define SP_CATCH(ctxp)                                                                           \
+  }                                                                                              \
+  catch (const SpError& e) { if (ctxp) (ctxp)->c.last_error = e.what(); return e.code; }        \
+  catch (const std::exception& e) {                                                              \
+    if (ctxp) (ctxp)->c.last_error = e.what();                                                   \
+    return std::string(e.what()).find("CUDA") != std::string::npos ? SP_ERR_CUDA : SP_ERR_INTERNAL; \
+  }                                                                                              \
+  catch (...) { if (ctxp) (ctxp)->c.last_error = "unknown error"; return SP_ERR_INTERNAL; }      \
+  return SP_OK;
+
+static Fq fq_in(const uint64_t l[4]) { Fq f; memcpy(&f.m, l, 32); return f; }
+static void fq_out(uint64_t l[4], const Fq& f) { memcpy(l, &f.m, 32); }
+static std::vector<Fq> fq_vec(const uint64_t* l, size_t n) { std::vector<Fq> v(n); if (n) memcpy(v.data(), l, 32 * n); return v; }
+static uint8_t* dup_bytes(const std::vector<uint8_t>& v) { uint8_t* p = (uint8_t*)malloc(v.size() ? v.size() : 1); memcpy(p, v.data(), v.size()); return p; }
+
+extern "C" {
+
+int sp_device_count(void) { return dev::device_count(); }
+int sp_ctx_create(int device, sp_ctx** out) {
+  try {
+    if (dev::device_count() <= device) { g_create_error = "no CUDA device (spartan_b200 has no CPU fallback)"; return SP_ERR_NO_DEVICE; }
+    *out = new sp_ctx(device);
+    return SP_OK;
+  } catch (const std::exception& e) { g_create_error = e.what(); return SP_ERR_CUDA; }
+}
+void sp_ctx_destroy(sp_ctx* ctx) { delete ctx; }
+const char* sp_last_error(const sp_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : g_create_error.c_str(); }
+unsigned long long sp_kernel_launches(void) { return dev::launch_count(); }
+int sp_timings(sp_ctx* ctx, char* buf, size_t buflen) {
+  std::ostringstream os;
+  for (auto& t : ctx->c.timings) os << t.first << "=" << t.second << ";";
+  std::string s = os.str();
+  if (s.size() + 1 > buflen) return SP_ERR_INVALID_ARG;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return SP_OK;
+}
+
+// ---- scalars
+int sp_scalar_from_bytes(const uint8_t b[32], uint64_t out[4]) {
+  Fq f(fq_to_mont(bytes_to_u256(b)));
+  fq_out(out, f);
+  return fq_bytes_canonical(b) ? SP_OK : SP_ERR_INVALID_SCALAR;
+}
+void sp_scalar_to_bytes(const uint64_t m[4], uint8_t out[32]) { fq_in(m).to_bytes(out); }
+void sp_scalar_from_bytes_wide(const uint8_t w[64], uint64_t out[4]) { fq_out(out, Fq::from_bytes_wide(w)); }
+void sp_scalar_mul(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) { fq_out(out, fq_in(a) * fq_in(b)); }
+void sp_scalar_add(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) { fq_out(out, fq_in(a) + fq_in(b)); }
+void sp_scalar_sub(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) { fq_out(out, fq_in(a) - fq_in(b)); }
+int sp_scalar_invert(const uint64_t a[4], uint64_t out[4]) {
+  Fq x = fq_in(a);
+  fq_out(out, x.inv());
+  return x.is_zero() ? SP_ERR_INVALID_SCALAR : SP_OK;
+}
+
+// ---- polys
+int sp_poly_upload(sp_ctx* ctx, const uint64_t* limbs, size_t len, sp_poly** out) {
+  SP_TRY(ctx)
+  sp_poly* p = new sp_poly{&ctx->c, DevBuf<u256>(len), len};
+  dev::h2d(p->d.p, limbs, len * 32, ctx->c.stream);
+  ctx->c.sync();
+  *out = p;
+  SP_CATCH(ctx)
+}
+int sp_poly_download(sp_ctx* ctx, const sp_poly* p, uint64_t* limbs, size_t len) {
+  SP_TRY(ctx)
+  if (len > p->d.n) throw SpError(SP_ERR_INVALID_ARG, "download length exceeds allocation");
+  dev::d2h(limbs, p->d.p, len * 32, ctx->c.stream);
+  ctx->c.sync();
+  SP_CATCH(ctx)
+}
+size_t sp_poly_len(const sp_poly* p) { return p->len; }
+void sp_poly_free(sp_poly* p) { delete p; }
+
+static void check_same_len(sp_poly* const* polys, int k) {
+  for (int i = 1; i < k; i++) if (polys[i]->len != polys[0]->len) throw SpError(SP_ERR_INVALID_ARG, "polynomials differ in length");
+  if (polys[0]->len < 2 || (polys[0]->len & (polys[0]->len - 1))) throw SpError(SP_ERR_INVALID_ARG, "length must be a power of two >= 2");
+}
+int sp_fold_top(sp_ctx* ctx, sp_poly* const* polys, int k, const uint64_t r[4]) {
+  SP_TRY(ctx)
+  check_same_len(polys, k);
+  Fq rr = fq_in(r);
+  ctx->c.put_small(8, &rr, 1);
+  std::vector<u256*> t(k);
+  for (int i = 0; i < k; i++) t[i] = polys[i]->d.p;
+  dev::fold_top(t.data(), k, polys[0]->len, ctx->c.small.p + 8, ctx->c.stream);
+  ctx->c.sync();
+  for (int i = 0; i < k; i++) polys[i]->len /= 2;
+  SP_CATCH(ctx)
+}
+static int kind_tables(int kind) { return kind == 0 ? 2 : kind == 1 ? 3 : 4; }
+static dev::ScInst make_inst(sp_poly* const* polys, int nt) {
+  dev::ScInst in;
+  for (int t = 0; t < 4; t++) in.t[t] = t < nt ? polys[t]->d.p : nullptr;
+  in.c_out = in.t[2];
+  in.write_c = 1;
+  return in;
+}
+int sp_sumcheck_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, uint64_t out[3][4]) {
+  SP_TRY(ctx)
+  if (kind < 0 || kind > 2) throw SpError(SP_ERR_INVALID_ARG, "bad sumcheck kind");
+  int nt = kind_tables(kind);
+  check_same_len(polys, nt);
+  dev::ScInst in = make_inst(polys, nt);
+  dev::sc_eval((dev::ScKind)kind, &in, 1, polys[0]->len, ctx->c.small.p, ctx->c.scratch.p, ctx->c.stream);
+  Fq e[3];
+  ctx->c.get_small(0, e, 3);
+  memcpy(out, e, 96);
+  SP_CATCH(ctx)
+}
+int sp_sumcheck_fold_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, const uint64_t r[4], uint64_t out[3][4]) {
+  SP_TRY(ctx)
+  if (kind < 0 || kind > 2) throw SpError(SP_ERR_INVALID_ARG, "bad sumcheck kind");
+  int nt = kind_tables(kind);
+  check_same_len(polys, nt);
+  if (polys[0]->len < 4) throw SpError(SP_ERR_INVALID_ARG, "fold_eval needs length >= 4");
+  Fq rr = fq_in(r);
+  ctx->c.put_small(8, &rr, 1);
+  dev::ScInst in = make_inst(polys, nt);
+  dev::sc_fold_eval((dev::ScKind)kind, &in, 1, polys[0]->len, ctx->c.small.p + 8, ctx->c.small.p, ctx->c.scratch.p, ctx->c.stream);
+  Fq e[3];
+  ctx->c.get_small(0, e, 3);
+  memcpy(out, e, 96);
+  for (int i = 0; i < nt; i++) polys[i]->len /= 2;
+  SP_CATCH(ctx)
+}
+int sp_eq_evals(sp_ctx* ctx, const uint64_t* r, size_t ell, sp_poly** out) {
+  SP_TRY(ctx)
+  size_t n = (size_t)1 << ell;
+  sp_poly* p = new sp_poly{&ctx->c, DevBuf<u256>(n), n};
+  DevBuf<u256> d_r(ell + 1), small(2 * ((size_t)1 << ((ell + 1) / 2)) + 8);
+  dev::h2d(d_r.p, r, ell * 32, ctx->c.stream);
+  dev::eq_evals(p->d.p, d_r.p, (int)ell, small.p, ctx->c.stream);
+  ctx->c.sync();
+  *out = p;
+  SP_CATCH(ctx)
+}
+int sp_poly_evaluate(sp_ctx* ctx, const sp_poly* p, const uint64_t* r, size_t ell, uint64_t out[4]) {
+  SP_TRY(ctx)
+  if (p->len != (size_t)1 << ell) throw SpError(SP_ERR_INVALID_ARG, "evaluate: |r| != num_vars");
+  DevBuf<u256> d_r(ell + 1), small(2 * ((size_t)1 << ((ell + 1) / 2)) + 8), eq(p->len);
+  dev::h2d(d_r.p, r, ell * 32, ctx->c.stream);
+  dev::eq_evals(eq.p, d_r.p, (int)ell, small.p, ctx->c.stream);
+  dev::dot(ctx->c.small.p + 32, p->d.p, eq.p, p->len, ctx->c.scratch.p, ctx->c.stream);
+  Fq v;
+  ctx->c.get_small(32, &v, 1);
+  fq_out(out, v);
+  SP_CATCH(ctx)
+}
+int sp_poly_bound_rows(sp_ctx* ctx, const sp_poly* p, const uint64_t* Lm, size_t L_size, sp_poly** out) {
+  SP_TRY(ctx)
+  if (L_size == 0 || p->len % L_size) throw SpError(SP_ERR_INVALID_ARG, "bound: L does not divide the length");
+  size_t R_size = p->len / L_size;
+  sp_poly* o = new sp_poly{&ctx->c, DevBuf<u256>(R_size), R_size};
+  DevBuf<u256> d_L(L_size), tmp(64 * R_size);
+  dev::h2d(d_L.p, Lm, L_size * 32, ctx->c.stream);
+  dev::bound_rows(o->d.p, p->d.p, d_L.p, L_size, R_size, tmp.p, ctx->c.stream);
+  ctx->c.sync();
+  *out = o;
+  SP_CATCH(ctx)
+}
+int sp_dot(sp_ctx* ctx, const sp_poly* a, const sp_poly* b, uint64_t out[4]) {
+  SP_TRY(ctx)
+  if (a->len != b->len) throw SpError(SP_ERR_INVALID_ARG, "dot: length mismatch");
+  dev::dot(ctx->c.small.p + 32, a->d.p, b->d.p, a->len, ctx->c.scratch.p, ctx->c.stream);
+  Fq v;
+  ctx->c.get_small(32, &v, 1);
+  fq_out(out, v);
+  SP_CATCH(ctx)
+}
+
+// ---- gens / commitments
+int sp_gens_create(sp_ctx* ctx, const uint8_t* label, size_t label_len, size_t n, sp_gens** out) {
+  SP_TRY(ctx)
+  sp_gens* g = new sp_gens;
+  g->n = n;
+  g->set.reset(new GenSet(&ctx->c, std::string((const char*)label, label_len), n + 1, {}));
+  *out = g;
+  SP_CATCH(ctx)
+}
+void sp_gens_free(sp_gens* g) { delete g; }
+int sp_gens_export(sp_ctx* ctx, const sp_gens* g, uint8_t* out32) {
+  SP_TRY(ctx)
+  DevBuf<uint8_t> comp(32 * (g->n + 1));
+  dev::compress_batch(comp.p, g->set->G.p, g->n + 1, ctx->c.stream);
+  dev::d2h(out32, comp.p, 32 * (g->n + 1), ctx->c.stream);
+  ctx->c.sync();
+  SP_CATCH(ctx)
+}
+int sp_msm(sp_ctx* ctx, const sp_gens* g, const uint64_t* scalars, size_t n, uint8_t out32[32]) {
+  SP_TRY(ctx)
+  if (n > g->n) throw SpError(SP_ERR_INVALID_ARG, "msm: more scalars than generators");
+  DevBuf<u256> d(n ? n : 1);
+  dev::h2d(d.p, scalars, n * 32, ctx->c.stream);
+  CommitKey key{g->set.get(), 0, g->n, g->n};
+  std::vector<Cp> out;
+  commit_rows_and_compress(ctx->c, key, d.p, n, 1, n, nullptr, out);
+  memcpy(out32, out[0].b, 32);
+  SP_CATCH(ctx)
+}
+int sp_commit_rows(sp_ctx* ctx, const sp_gens* g, const sp_poly* p, size_t L, size_t R, const uint64_t* blinds, uint8_t* out32) {
+  SP_TRY(ctx)
+  if (L * R != p->len || R > g->n) throw SpError(SP_ERR_INVALID_ARG, "commit_rows: shape mismatch");
+  CommitKey key{g->set.get(), 0, g->n, g->n};
+  std::vector<Fq> bl;
+  if (blinds) bl = fq_vec(blinds, L);
+  std::vector<Cp> out;
+  commit_rows_and_compress(ctx->c, key, p->d.p, R, L, R, blinds ? bl.data() : nullptr, out);
+  memcpy(out32, out.data(), 32 * L);
+  SP_CATCH(ctx)
+}
+int sp_point_decompress_check(sp_ctx* ctx, const uint8_t* in32, size_t n, int* ok) {
+  SP_TRY(ctx)
+  DevBuf<uint8_t> d_in(32 * n);
+  DevBuf<ge> pts(n);
+  DevBuf<int> d_ok(n);
+  dev::h2d(d_in.p, in32, 32 * n, ctx->c.stream);
+  dev::decompress_batch(pts.p, d_ok.p, d_in.p, n, ctx->c.stream);
+  dev::d2h(ok, d_ok.p, sizeof(int) * n, ctx->c.stream);
+  ctx->c.sync();
+  SP_CATCH(ctx)
+}
+int sp_point_roundtrip(sp_ctx* ctx, const uint8_t* in32, size_t n, uint8_t* out32) {
+  SP_TRY(ctx)
+  DevBuf<uint8_t> d_in(32 * n), d_out(32 * n);
+  DevBuf<ge> pts(n);
+  dev::h2d(d_in.p, in32, 32 * n, ctx->c.stream);
+  dev::decompress_batch(pts.p, nullptr, d_in.p, n, ctx->c.stream);
+  dev::compress_batch(d_out.p, pts.p, n, ctx->c.stream);
+  dev::d2h(out32, d_out.p, 32 * n, ctx->c.stream);
+  ctx->c.sync();
+  SP_CATCH(ctx)
+}
+
+// ---- instances
+static size_t next_pow2(size_t x) { size_t p = 1; while (p < x) p <<= 1; return p; }
+
+int sp_instance_create(sp_ctx* ctx, size_t num_cons, size_t num_vars, size_t num_inputs, const uint64_t* A_row, const uint64_t* A_col, const uint8_t* A_val,
+                       size_t nA, const uint64_t* B_row, const uint64_t* B_col, const uint8_t* B_val, size_t nB, const uint64_t* C_row, const uint64_t* C_col,
+                       const uint8_t* C_val, size_t nC, sp_instance** out) {
+  SP_TRY(ctx)
+  // Instance::new padding rules (lib.rs:129-198)
+  size_t num_vars_padded = next_pow2(std::max(num_vars, num_inputs + 1));
+  size_t num_cons_padded = num_cons;
+  if (num_cons_padded == 0 || num_cons_padded == 1) num_cons_padded = 2;
+  if (next_pow2(num_cons) != num_cons) num_cons_padded = next_pow2(num_cons);
+  std::unique_ptr<sp_instance> I(new sp_instance);
+  I->inst.num_cons = num_cons_padded; I->inst.num_vars = num_vars_padded; I->inst.num_inputs = num_inputs;
+  const uint64_t* rows[3] = {A_row, B_row, C_row};
+  const uint64_t* cols[3] = {A_col, B_col, C_col};
+  const uint8_t* vals[3] = {A_val, B_val, C_val};
+  size_t nn[3] = {nA, nB, nC};
+  for (int m = 0; m < 3; m++) {
+    SparseMatDev& M = I->inst.M[m];
+    for (size_t k = 0; k < nn[m]; k++) {
+      size_t row = rows[m][k], col = cols[m][k];
+      if (row >= num_cons) throw SpError(SP_ERR_INVALID_INDEX, "R1CSError::InvalidIndex (row)");
+      if (col >= num_vars + 1 + num_inputs) throw SpError(SP_ERR_INVALID_INDEX, "R1CSError::InvalidIndex (col)");
+      const uint8_t* vb = vals[m] + 32 * k;
+      if (!fq_bytes_canonical(vb)) throw SpError(SP_ERR_INVALID_SCALAR, "R1CSError::InvalidScalar");
+      M.row.push_back((uint32_t)row);
+      M.col.push_back((uint32_t)(col >= num_vars ? col + num_vars_padded - num_vars : col));
+      M.val.push_back(Fq(fq_to_mont(bytes_to_u256(vb))));
+    }
+    if (num_cons == 0 || num_cons == 1)
+      for (size_t i = nn[m]; i < num_cons_padded; i++) { M.row.push_back((uint32_t)i); M.col.push_back((uint32_t)num_vars); M.val.push_back(Fq::zero()); }
+  }
+  I->inst.finalize(&ctx->c);
+  *out = I.release();
+  SP_CATCH(ctx)
+}
+
+static std::vector<Fq> prg_scalars(const std::string& tag, size_t n, uint64_t seed) {
+  // DESIGN.md "deterministic inputs": SHAKE256("spartan-b200/v1/" || tag || LE64(seed)), 64 bytes per scalar -> from_bytes_wide
+  std::string s = "spartan-b200/v1/" + tag;
+  std::vector<uint8_t> in(s.begin(), s.end());
+  for (int i = 0; i < 8; i++) in.push_back((uint8_t)(seed >> (8 * i)));
+  std::vector<uint8_t> raw(64 * n);
+  shake256(raw.data(), raw.size(), in.data(), in.size());
+  std::vector<Fq> out(n);
+  for (size_t i = 0; i < n; i++) out[i] = Fq::from_bytes_wide(raw.data() + 64 * i);
+  return out;
+}
+
+int sp_instance_synthetic(sp_ctx* ctx, size_t num_cons, size_t num_vars, size_t num_inputs, uint64_t seed, sp_instance** out, uint64_t* vars_out,
+                          uint64_t* inputs_out) {
+  SP_TRY(ctx)
+  // R1CSShape::produce_synthetic_r1cs (r1cs.rs:160-238)
+  if (next_pow2(num_cons) != num_cons || next_pow2(num_vars) != num_vars || !(num_inputs < num_vars)) throw SpError(SP_ERR_INVALID_ARG, "synthetic: sizes");
+  size_t size_z = num_vars + num_inputs + 1;
+  std::vector<Fq> Z = prg_scalars("Z", size_z, seed);
+  Z[num_vars] = Fq::one();
+  std::unique_ptr<sp_instance> I(new sp_instance);
+  I->inst.num_cons = num_cons; I->inst.num_vars = num_vars; I->inst.num_inputs = num_inputs;
+  SparseMatDev &A = I->inst.M[0], &B = I->inst.M[1], &Cm = I->inst.M[2];
+  // batch inversion of the Z values used as C_val denominators
+  std::vector<Fq> zinv(size_z), pref(size_z);
+  Fq acc = Fq::one();
+  for (size_t i = 0; i < size_z; i++) { pref[i] = acc; if (!Z[i].is_zero()) acc *= Z[i]; }
+  Fq ainv = acc.inv();
+  for (size_t i = size_z; i-- > 0;) { if (Z[i].is_zero()) { zinv[i] = Fq::zero(); continue; } zinv[i] = ainv * pref[i]; ainv *= Z[i]; }
+  for (size_t i = 0; i < num_cons; i++) {
+    size_t a = i % size_z, b = (i + 2) % size_z, c = (i + 3) % size_z;
+    A.row.push_back((uint32_t)i); A.col.push_back((uint32_t)a); A.val.push_back(Fq::one());
+    B.row.push_back((uint32_t)i); B.col.push_back((uint32_t)b); B.val.push_back(Fq::one());
+    Fq ab = Z[a] * Z[b];
+    Cm.row.push_back((uint32_t)i);
+    if (Z[c].is_zero()) { Cm.col.push_back((uint32_t)num_vars); Cm.val.push_back(ab); }
+    else { Cm.col.push_back((uint32_t)c); Cm.val.push_back(ab * zinv[c]); }
+  }
+  // the COO column index space is [vars | 1 | inputs] padded to 2*num_vars: columns >= num_vars need no shift here because
+  // produce_synthetic_r1cs requires num_vars to be a power of two already (r1cs.rs:172-176)
+  I->inst.finalize(&ctx->c);
+  memcpy(vars_out, Z.data(), 32 * num_vars);
+  memcpy(inputs_out, Z.data() + num_vars + 1, 32 * num_inputs);
+  *out = I.release();
+  SP_CATCH(ctx)
+}
+void sp_instance_free(sp_instance* inst) { delete inst; }
+int sp_instance_dims(const sp_instance* inst, size_t* nc, size_t* nv, size_t* ni) {
+  *nc = inst->inst.num_cons; *nv = inst->inst.num_vars; *ni = inst->inst.num_inputs;
+  return SP_OK;
+}
+int sp_instance_set_digest(sp_instance* inst, const uint8_t* digest, size_t len) { inst->inst.digest.assign(digest, digest + len); return SP_OK; }
+int sp_instance_bincode(const sp_instance* inst, uint8_t** out, size_t* len) {
+  // bincode(R1CSShape{num_cons,num_vars,num_inputs,A,B,C}), SparseMatPolynomial{num_vars_x,num_vars_y,M:Vec<{row,col,val}>} (r1cs.rs:19-26, sparse_mlpoly.rs:19-37)
+  Writer w;
+  const Instance& I = inst->inst;
+  w.u64(I.num_cons); w.u64(I.num_vars); w.u64(I.num_inputs);
+  size_t nx = 0, ny = 0;
+  while (((size_t)1 << nx) < I.num_cons) nx++;
+  while (((size_t)1 << ny) < 2 * I.num_vars) ny++;
+  for (int m = 0; m < 3; m++) {
+    w.u64(nx); w.u64(ny); w.u64(I.M[m].row.size());
+    for (size_t k = 0; k < I.M[m].row.size(); k++) { w.u64(I.M[m].row[k]); w.u64(I.M[m].col[k]); w.scalar(I.M[m].val[k]); }
+  }
+  *out = dup_bytes(w.out); *len = w.out.size();
+  return SP_OK;
+}
+int sp_instance_nnz(const sp_instance* inst, int m, size_t* nnz) { if (m < 0 || m > 2) return SP_ERR_INVALID_ARG; *nnz = inst->inst.M[m].row.size(); return SP_OK; }
+int sp_instance_export(const sp_instance* inst, int m, uint64_t* row, uint64_t* col, uint64_t* val) {
+  if (m < 0 || m > 2) return SP_ERR_INVALID_ARG;
+  const SparseMatDev& M = inst->inst.M[m];
+  for (size_t k = 0; k < M.row.size(); k++) { row[k] = M.row[k]; col[k] = M.col[k]; }
+  memcpy(val, M.val.data(), 32 * M.val.size());
+  return SP_OK;
+}
+
+static DevBuf<u256> upload_padded_vars(Ctx& c, const Instance& I, const uint64_t* vars, size_t nvars) {
+  if (nvars > I.num_vars) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs (vars)");
+  DevBuf<u256> d(I.num_vars);
+  dev::h2d(d.p, vars, nvars * 32, c.stream);
+  if (nvars < I.num_vars) dev::dzero(d.p + nvars, (I.num_vars - nvars) * 32, c.stream);  // Assignment::pad (lib.rs:91-104)
+  return d;
+}
+
+int sp_instance_is_sat(sp_ctx* ctx, const sp_instance* inst, const uint64_t* vars, size_t nvars, const uint64_t* inputs, size_t ninputs, int* sat) {
+  SP_TRY(ctx)
+  const Instance& I = inst->inst;
+  if (ninputs != I.num_inputs) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs");
+  Ctx& c = ctx->c;
+  DevBuf<u256> d_vars = upload_padded_vars(c, I, vars, nvars);
+  DevBuf<u256> z(2 * I.num_vars), Az(I.num_cons), Bz(I.num_cons), Cz(I.num_cons);
+  dev::d2d(z.p, d_vars.p, I.num_vars * 32, c.stream);
+  std::vector<Fq> tail(1 + ninputs);
+  tail[0] = Fq::one();
+  if (ninputs) memcpy(&tail[1], inputs, 32 * ninputs);
+  dev::h2d(z.p + I.num_vars, tail.data(), tail.size() * 32, c.stream);
+  dev::dzero(z.p + I.num_vars + tail.size(), (I.num_vars - tail.size()) * 32, c.stream);
+  u256* outs[3] = {Az.p, Bz.p, Cz.p};
+  for (int m = 0; m < 3; m++) dev::spmv(outs[m], I.num_cons, I.M[m].csr_ptr.p, I.M[m].csr_idx.p, I.M[m].csr_val.p, z.p, c.stream);
+  DevBuf<u256> prod(I.num_cons);
+  dev::hadamard(prod.p, Az.p, Bz.p, I.num_cons, c.stream);
+  std::vector<Fq> p = c.download(prod.p, I.num_cons), cz = c.download(Cz.p, I.num_cons);
+  *sat = 1;
+  for (size_t i = 0; i < I.num_cons; i++) if (!(p[i] == cz[i])) { *sat = 0; break; }   // r1cs.rs:265
+  SP_CATCH(ctx)
+}
+
+// ---- NIZK
+int sp_nizk_gens_create(sp_ctx* ctx, size_t num_cons, size_t num_vars, size_t num_inputs, sp_nizk_gens** out) {
+  SP_TRY(ctx)
+  (void)num_cons;
+  size_t num_vars_padded = next_pow2(std::max(num_vars, num_inputs + 1));  // lib.rs:475-481
+  sp_nizk_gens* g = new sp_nizk_gens;
+  g->g.reset(new R1CSGens(&ctx->c, "gens_r1cs_sat", num_vars_padded));
+  *out = g;
+  SP_CATCH(ctx)
+}
+void sp_nizk_gens_free(sp_nizk_gens* g) { delete g; }
+
+static int nizk_prove_common(sp_ctx* ctx, const sp_instance* inst, const u256* d_vars, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens,
+                             const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+  SP_TRY(ctx)
+  if (ninputs != inst->inst.num_inputs) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs");
+  Transcript T(std::string((const char*)label, label_len));
+  NizkProof P;
+  nizk_prove(ctx->c, inst->inst, d_vars, fq_vec(inputs, ninputs), *gens->g, T, fq_in(seed), P);
+  Writer w;
+  P.ser(w);
+  *proof = dup_bytes(w.out); *proof_len = w.out.size();
+  SP_CATCH(ctx)
+}
+int sp_nizk_prove(sp_ctx* ctx, const sp_instance* inst, const uint64_t* vars, size_t nvars, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens,
+                  const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+  DevBuf<u256> d_vars;
+  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
+  catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
+  return nizk_prove_common(ctx, inst, d_vars.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
+}
+int sp_nizk_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_poly* vars, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens,
+                           const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+  if (vars->len != inst->inst.num_vars) { ctx->c.last_error = "resident vars must already be padded to num_vars"; return SP_ERR_INVALID_INPUTS; }
+  return nizk_prove_common(ctx, inst, vars->d.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
+}
+
+// ---- SNARK
+int sp_snark_gens_create(sp_ctx* ctx, size_t num_cons, size_t num_vars, size_t num_inputs, size_t num_nz_entries, sp_snark_gens** out) {
+  SP_TRY(ctx)
+  sp_snark_gens* g = new sp_snark_gens;
+  g->g.reset(new SnarkGens(&ctx->c, num_cons, num_vars, num_inputs, num_nz_entries));
+  *out = g;
+  SP_CATCH(ctx)
+}
+void sp_snark_gens_free(sp_snark_gens* g) { delete g; }
+int sp_snark_encode(sp_ctx* ctx, const sp_instance* inst, const sp_snark_gens* gens, sp_snark_encoding** out) {
+  SP_TRY(ctx)
+  sp_snark_encoding* e = new sp_snark_encoding;
+  e->e.reset(new SnarkEncoding());
+  snark_encode(ctx->c, inst->inst, *gens->g, *e->e);
+  *out = e;
+  SP_CATCH(ctx)
+}
+void sp_snark_encoding_free(sp_snark_encoding* e) { delete e; }
+int sp_snark_commitment_bytes(const sp_snark_encoding* e, uint8_t** out, size_t* len) {
+  Writer w;
+  e->e->ser_commitment(w);
+  *out = dup_bytes(w.out); *len = w.out.size();
+  return SP_OK;
+}
+static int snark_prove_common(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const u256* d_vars, const uint64_t* inputs, size_t ninputs,
+                              const sp_snark_gens* gens, const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+  SP_TRY(ctx)
+  if (ninputs != inst->inst.num_inputs) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs");
+  Transcript T(std::string((const char*)label, label_len));
+  Writer w;
+  snark_prove(ctx->c, inst->inst, *enc->e, d_vars, fq_vec(inputs, ninputs), *gens->g, T, fq_in(seed), w);
+  *proof = dup_bytes(w.out); *proof_len = w.out.size();
+  SP_CATCH(ctx)
+}
+int sp_snark_prove(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const uint64_t* vars, size_t nvars, const uint64_t* inputs, size_t ninputs,
+                   const sp_snark_gens* gens, const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+  DevBuf<u256> d_vars;
+  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
+  catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
+  return snark_prove_common(ctx, inst, enc, d_vars.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
+}
+int sp_snark_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const sp_poly* vars, const uint64_t* inputs, size_t ninputs,
+                            const sp_snark_gens* gens, const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+  if (vars->len != inst->inst.num_vars) { ctx->c.last_error = "resident vars must already be padded to num_vars"; return SP_ERR_INVALID_INPUTS; }
+  return snark_prove_common(ctx, inst, enc, vars->d.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
+}
+
+void sp_free(void* p) { free(p); }
+
+}  // extern "C"

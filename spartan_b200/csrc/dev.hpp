@@ -1,0 +1,95 @@
+// spartan_b200 — launch wrappers around the sm_100a kernels (kernels.cu).  Plain C++ signatures so the host
+// prover (prover.cpp, compiled by g++) never sees CUDA syntax.  All pointers are DEVICE pointers unless named h_*.
+// Every wrapper enqueues on `stream` and returns immediately; errors surface through sp::dev::check().
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "field.cuh"
+#include "curve.cuh"
+
+struct CUstream_st;
+typedef CUstream_st* cudaStream_t;
+
+namespace sp {
+namespace dev {
+
+// ---- runtime plumbing
+void check(const char* what);  // throws std::runtime_error on a pending CUDA error
+int device_count();
+void set_device(int dev);
+cudaStream_t stream_create();
+void stream_destroy(cudaStream_t s);
+void stream_sync(cudaStream_t s);
+void* dmalloc(size_t bytes);
+void dfree(void* p);
+void* hmalloc_pinned(size_t bytes);
+void hfree_pinned(void* p);
+void h2d(void* d, const void* h, size_t bytes, cudaStream_t s);
+void d2h(void* h, const void* d, size_t bytes, cudaStream_t s);
+void d2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
+void dzero(void* d, size_t bytes, cudaStream_t s);
+int sm_count();
+// event timing of the kernels launched through these wrappers (bench.py roofline leg)
+void* event_create();
+void event_record(void* ev, cudaStream_t s);
+float event_elapsed_ms(void* a, void* b);
+void event_destroy(void* ev);
+unsigned long long launch_count();  // kernels launched by this library since load
+
+// ---- sumcheck rounds (K1/K2 of SURVEY.md §2b)
+enum ScKind { SC_QUAD = 0 /*A*B*/, SC_CUBIC3 = 1 /*A*B*C*/, SC_CUBIC4 = 2 /*A*(B*C-D)*/ };
+struct ScInst {        // one sumcheck instance: up to four tables of the same current length
+  u256* t[4];          // A, B, C, D (unused entries null)
+  u256* c_out;         // where the folded C goes (== t[2] for private C; a ping-pong buffer when C is shared)
+  int write_c;         // 1: this instance stores the folded C
+};
+// scratch: >= sc_scratch_bytes(); out: ninst*3 scalars [e0,e2,e3] (e3 = 0 for SC_QUAD), device memory
+size_t sc_scratch_bytes(int ninst);
+void sc_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s);
+// fold every table of every instance by r (len -> len/2, in place) and evaluate the next round on the result
+void sc_fold_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, const u256* d_r, u256* out, void* scratch, cudaStream_t s);
+// fold only (bound_poly_var_top, dense_mlpoly.rs:215-223): tables[k][i] += r*(tables[k][i+len/2]-tables[k][i])
+void fold_top(u256* const* d_tables, int ntables, size_t len, const u256* d_r, cudaStream_t s);
+void fold_top_single(u256* table, size_t len, const u256* d_r, cudaStream_t s);
+
+// ---- dense polynomial helpers (K7)
+void eq_evals(u256* out, const u256* d_r, int ell, u256* scratch_small /* >= 2*2^ceil(ell/2) */, cudaStream_t s);
+void dot(u256* out, const u256* a, const u256* b, size_t n, void* scratch, cudaStream_t s);
+void dot3(u256* out, const u256* a, const u256* b, const u256* c, size_t n, void* scratch, cudaStream_t s);
+void bound_rows(u256* out, const u256* Z, const u256* L, size_t L_size, size_t R_size, u256* scratch /* >= 64*R_size */, cudaStream_t s);
+void lincomb3(u256* out, const u256* A, const u256* B, const u256* C, const u256* d_rabc /*3*/, size_t n, cudaStream_t s);
+void hadamard(u256* out, const u256* a, const u256* b, size_t n, cudaStream_t s);
+void from_u64(u256* out, const uint64_t* v, size_t n, cudaStream_t s);
+void from_bytes_wide(u256* out, const uint8_t* in64, size_t n, cudaStream_t s);
+void batch_invert_elems(u256* inout, size_t n, cudaStream_t s);
+void gather(u256* out, const u256* mem, const uint32_t* idx, size_t n, cudaStream_t s);
+// hash layer of the SPARK memory check: out = ts*r^2 + val*r + addr - g  (sparse_mlpoly.rs:545-600)
+// addr == null: addr = index i;  ts == null: ts = 0;  ts_plus_one adds one.   d_rg = [r_hash, r_multiset]
+void spark_hash(u256* out, size_t n, const u256* addr, const u256* val, const u256* ts, int ts_plus_one, const u256* d_rg, cudaStream_t s);
+// IPA vector folds (bullet.rs:105-107): a[i] = a[i]*u + uinv*a[i+n];  b[i] = b[i]*uinv + u*b[i+n]   d_u = [u, uinv]
+void ipa_fold_ab(u256* a, u256* b, size_t n, const u256* d_u, cudaStream_t s);
+// scalars for the L / R commitments against the UNFOLDED generators: see DESIGN.md "IPA without folding G"
+void ipa_lr_scalars(u256* outL, u256* outR, const u256* a, const u256* svec, size_t n_cur, size_t n_full, cudaStream_t s);
+void ipa_update_s(u256* svec, size_t n_cur_half, size_t n_full, const u256* d_u, cudaStream_t s);
+void fill_one(u256* out, size_t n, cudaStream_t s);
+
+// ---- sparse matrix-vector products on CSR (row-major) / CSC (column-major) copies of the COO triples
+void spmv(u256* out, size_t nrows, const uint32_t* ptr, const uint32_t* idx, const u256* val, const u256* x, cudaStream_t s);
+// sum_k trx[row_k]*try[col_k]*val_k
+void sparse_eval3(u256* out, const uint32_t* row, const uint32_t* col, const u256* val, size_t nnz, const u256* trx, const u256* try_, void* scratch, cudaStream_t s);
+
+// ---- group: generators, fixed-base window tables, multi-row MSM, compression (K3/K4/K6)
+void gens_from_uniform(ge* out, const uint8_t* d_uniform64, size_t n, cudaStream_t s);
+void decompress_batch(ge* out, int* ok, const uint8_t* in32, size_t n, cudaStream_t s);
+void compress_batch(uint8_t* out32, const ge* in, size_t n, cudaStream_t s);
+// table[(j*32 + w)*128 + (d-1)] = d * 2^(8w) * G_j in affine-niels form
+size_t table_entries(size_t nbases);
+void build_tables(ge_niels* table, const ge* G, size_t nbases, cudaStream_t s);
+// out[row] = sum_{j<R} scalars[row*stride + j] * G_j  (+ blinds[row] * G_{blind_base} when blinds != null)
+// scalars are Montgomery-form; partial: scratch >= msm_scratch_bytes(L, R)
+size_t msm_scratch_bytes(size_t L, size_t R);
+void msm_rows(ge* out, const ge_niels* table, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
+              void* scratch, cudaStream_t s);
+
+}  // namespace dev
+}  // namespace sp

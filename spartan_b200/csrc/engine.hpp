@@ -1,0 +1,85 @@
+// spartan_b200 — device context, buffers and generator sets shared by the host prover.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+#include "dev.hpp"
+#include "host.hpp"
+
+namespace sp {
+
+void shake256(uint8_t* out, size_t outlen, const uint8_t* in, size_t inlen);
+
+struct SpError : std::runtime_error {  // carries a C-ABI status code (include/spartan_b200.h)
+  int code;
+  SpError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+template <class T>
+struct DevBuf {  // owning device allocation
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  ~DevBuf() { release(); }
+  void alloc(size_t count) { release(); p = (T*)dev::dmalloc(count * sizeof(T)); n = count; }
+  void release() { if (p) dev::dfree(p); p = nullptr; n = 0; }
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint8_t* pinned = nullptr;       // staging for small host<->device exchanges
+  size_t pinned_bytes = 0;
+  DevBuf<uint8_t> scratch;         // reduction partials / MSM partials
+  DevBuf<u256> small;              // challenges, results (device side)
+  std::string last_error;
+  // per-phase timers (profile feature of the reference, src/timer.rs): label -> milliseconds of the last prove
+  std::vector<std::pair<std::string, double>> timings;
+
+  explicit Ctx(int dev);
+  ~Ctx();
+  void sync() { dev::stream_sync(stream); }
+  void ensure_scratch(size_t bytes) { if (scratch.n < bytes) { sync(); scratch.alloc(bytes); } }
+  // upload k scalars to small[slot..]
+  void put_small(size_t slot, const Fq* v, size_t k);
+  void get_small(size_t slot, Fq* v, size_t k);  // synchronises
+  void upload(u256* d, const Fq* h, size_t n);
+  std::vector<Fq> download(const u256* d, size_t n);
+};
+
+// One SHAKE256 generator stream (a `label` of MultiCommitGens::new, commitments.rs:15-33) expanded to `nbases` points,
+// with the fixed-base window table on the device and host copies of the tables of a few named bases.
+struct GenSet {
+  Ctx* ctx;
+  std::string label;
+  size_t nbases;
+  DevBuf<ge> G;
+  DevBuf<ge_niels> table;
+  std::map<size_t, HostBaseTable> host_tab;
+  std::vector<Cp> compressed;  // lazily filled export
+  GenSet(Ctx* c, const std::string& label, size_t nbases, const std::vector<size_t>& host_bases);
+  const HostBaseTable& tab(size_t base) const {
+    auto it = host_tab.find(base);
+    if (it == host_tab.end()) throw std::runtime_error("spartan_b200: no host table for generator " + std::to_string(base));
+    return it->second;
+  }
+  ge host_point(size_t base) const;  // 1 * G_base from the host table
+};
+
+// A MultiCommitGens view (commitments.rs:8-12): G = set.G[off .. off+n), h = set.G[h]
+struct CommitKey {
+  const GenSet* set = nullptr;
+  size_t off = 0, n = 0, h = 0;
+};
+
+struct Term { size_t base; Fq k; };
+// sum of k_i * G_{base_i} over host tables
+ge host_commit(const GenSet& gs, const Term* terms, size_t nterms);
+inline Cp host_commit_c(const GenSet& gs, const std::vector<Term>& t) { return compress(host_commit(gs, t.data(), t.size())); }
+
+}  // namespace sp

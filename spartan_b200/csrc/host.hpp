@@ -1,0 +1,203 @@
+// spartan_b200 — host side of the prover: scalar wrapper, Merlin transcript, RandomTape, small fixed-base commitments.
+//
+// This is the part of the reference that stays on the CPU in a B200 deployment: the Fiat-Shamir transcript is a strict serial
+// dependency between kernel launches (/root/reference/src/transcript.rs, src/random.rs), and the constant-size sigma protocols
+// (src/nizk/mod.rs:27-405) commit to at most five scalars at a time.  The data-parallel work lives in kernels.cu.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "curve.cuh"
+#include "field.cuh"
+
+namespace sp {
+
+// ------------------------------------------------------------------------------------------------ scalars
+struct Fq {  // Montgomery-form element, same bytes as the reference's Scalar([u64;4])
+  u256 m;
+  Fq() : m(fq_zero()) {}
+  explicit Fq(const u256& x) : m(x) {}
+  static Fq zero() { return Fq(); }
+  static Fq one() { return Fq(fq_one()); }
+  static Fq from_u64(uint64_t x) { return Fq(fq_from_u64(x)); }
+  static Fq from_bytes_wide(const uint8_t b[64]) { return Fq(fq_from_wide(bytes_to_u256(b), bytes_to_u256(b + 32))); }  // transcript.rs:26-30
+  void to_bytes(uint8_t out[32]) const { u256_to_bytes(out, fq_from_mont(m)); }  // canonical LE (ristretto255.rs:419)
+  u256 canonical() const { return fq_from_mont(m); }
+  Fq operator+(const Fq& o) const { return Fq(fq_add(m, o.m)); }
+  Fq operator-(const Fq& o) const { return Fq(fq_sub(m, o.m)); }
+  Fq operator*(const Fq& o) const { return Fq(fq_mul(m, o.m)); }
+  Fq operator-() const { return Fq(fq_neg(m)); }
+  Fq& operator+=(const Fq& o) { m = fq_add(m, o.m); return *this; }
+  Fq& operator*=(const Fq& o) { m = fq_mul(m, o.m); return *this; }
+  bool operator==(const Fq& o) const { return fq_eq(m, o.m); }
+  bool is_zero() const { return fq_is_zero(m); }
+  Fq inv() const { return Fq(fq_inv(m)); }
+  Fq sqr() const { return Fq(fq_sqr(m)); }
+};
+// Scalar::from_bytes acceptance test (ristretto255.rs:400-409): the little-endian integer must be < q
+inline bool fq_bytes_canonical(const uint8_t b[32]) {
+  static const uint8_t qb[32] = {0xed, 0xd3, 0xf5, 0x5c, 0x1a, 0x63, 0x12, 0x58, 0xd6, 0x9c, 0xf7, 0xa2, 0xde, 0xf9, 0xde, 0x14,
+                                 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x10};
+  for (int i = 31; i >= 0; i--) {
+    if (b[i] < qb[i]) return true;
+    if (b[i] > qb[i]) return false;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------ Keccak-f[1600] / STROBE-128 / Merlin
+// merlin ^3.0.0 is a third-party crate (Cargo.toml:19); construction per the Merlin v1.0 / STROBE v1.0.2 specifications.
+class Keccak {
+ public:
+  static void f1600(uint64_t A[25]) {
+    static const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
+                                    0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
+                                    0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
+                                    0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+                                    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    static const int RHO[5][5] = {{0, 36, 3, 41, 18}, {1, 44, 10, 45, 2}, {62, 6, 43, 15, 61}, {28, 55, 25, 21, 56}, {27, 20, 39, 8, 14}};  // [x][y]
+    for (int rnd = 0; rnd < 24; rnd++) {
+      uint64_t Cx[5], D[5], B[25];
+      for (int x = 0; x < 5; x++) Cx[x] = A[x] ^ A[x + 5] ^ A[x + 10] ^ A[x + 15] ^ A[x + 20];
+      for (int x = 0; x < 5; x++) D[x] = Cx[(x + 4) % 5] ^ rotl(Cx[(x + 1) % 5], 1);
+      for (int x = 0; x < 5; x++)
+        for (int y = 0; y < 5; y++) {
+          uint64_t v = A[x + 5 * y] ^ D[x];
+          // pi: B[y, 2x+3y] = rot(A[x,y], rho[x][y])
+          B[y + 5 * ((2 * x + 3 * y) % 5)] = rotl(v, RHO[x][y]);
+        }
+      for (int y = 0; y < 5; y++)
+        for (int x = 0; x < 5; x++) A[x + 5 * y] = B[x + 5 * y] ^ (~B[(x + 1) % 5 + 5 * y] & B[(x + 2) % 5 + 5 * y]);
+      A[0] ^= RC[rnd];
+    }
+  }
+
+ private:
+  static uint64_t rotl(uint64_t v, int n) { return n ? (v << n) | (v >> (64 - n)) : v; }
+};
+
+class Transcript {  // merlin::Transcript + ProofTranscript (transcript.rs:5-37)
+ public:
+  explicit Transcript(const std::string& label) {
+    memset(st_, 0, sizeof st_);
+    uint8_t* b = bytes();
+    const uint8_t hdr[6] = {1, R + 2, 1, 0, 1, 96};
+    memcpy(b, hdr, 6);
+    memcpy(b + 6, "STROBEv1.0.2", 12);
+    Keccak::f1600(st_);
+    pos_ = 0; pos_begin_ = 0;
+    meta_ad((const uint8_t*)"Merlin v1.0", 11, false);
+    append_message("dom-sep", (const uint8_t*)label.data(), label.size());
+  }
+  void append_message(const char* label, const uint8_t* msg, size_t len) {
+    uint8_t l4[4] = {(uint8_t)len, (uint8_t)(len >> 8), (uint8_t)(len >> 16), (uint8_t)(len >> 24)};
+    meta_ad((const uint8_t*)label, strlen(label), false);
+    meta_ad(l4, 4, true);
+    ad(msg, len);
+  }
+  void append_message(const char* label, const char* msg) { append_message(label, (const uint8_t*)msg, strlen(msg)); }
+  void append_u64(const char* label, uint64_t x) {
+    uint8_t b[8];
+    for (int i = 0; i < 8; i++) b[i] = (uint8_t)(x >> (8 * i));
+    append_message(label, b, 8);
+  }
+  void challenge_bytes(const char* label, uint8_t* out, size_t n) {
+    uint8_t l4[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+    meta_ad((const uint8_t*)label, strlen(label), false);
+    meta_ad(l4, 4, true);
+    begin_op(FLAG_I | FLAG_A | FLAG_C, false);
+    uint8_t* b = bytes();
+    for (size_t i = 0; i < n; i++) { out[i] = b[pos_]; b[pos_] = 0; if (++pos_ == R) run_f(); }
+  }
+  // ProofTranscript
+  void append_protocol_name(const char* name) { append_message("protocol-name", name); }
+  void append_scalar(const char* label, const Fq& s) { uint8_t b[32]; s.to_bytes(b); append_message(label, b, 32); }
+  void append_point(const char* label, const uint8_t p[32]) { append_message(label, p, 32); }
+  Fq challenge_scalar(const char* label) { uint8_t b[64]; challenge_bytes(label, b, 64); return Fq::from_bytes_wide(b); }
+  std::vector<Fq> challenge_vector(const char* label, size_t n) {
+    std::vector<Fq> v(n);
+    for (size_t i = 0; i < n; i++) v[i] = challenge_scalar(label);
+    return v;
+  }
+  void append_scalars(const char* label, const Fq* v, size_t n) {  // AppendToTranscript for [Scalar], transcript.rs:49-57
+    append_message(label, "begin_append_vector");
+    for (size_t i = 0; i < n; i++) append_scalar(label, v[i]);
+    append_message(label, "end_append_vector");
+  }
+  void append_scalars(const char* label, const std::vector<Fq>& v) { append_scalars(label, v.data(), v.size()); }
+  // canonical 32-byte scalars already serialised (device-side to_bytes), same framing
+  void append_scalar_bytes(const char* label, const uint8_t* canon32, size_t n) {
+    append_message(label, "begin_append_vector");
+    for (size_t i = 0; i < n; i++) append_message(label, canon32 + 32 * i, 32);
+    append_message(label, "end_append_vector");
+  }
+
+ private:
+  static const uint8_t R = 166, FLAG_I = 1, FLAG_A = 2, FLAG_C = 4, FLAG_M = 16, FLAG_K = 32;
+  uint64_t st_[25];
+  uint8_t pos_, pos_begin_;
+  uint8_t* bytes() { return reinterpret_cast<uint8_t*>(st_); }
+  void run_f() {
+    uint8_t* b = bytes();
+    b[pos_] ^= pos_begin_;
+    b[pos_ + 1] ^= 0x04;
+    b[R + 1] ^= 0x80;
+    Keccak::f1600(st_);
+    pos_ = 0; pos_begin_ = 0;
+  }
+  void absorb(const uint8_t* d, size_t n) {
+    uint8_t* b = bytes();
+    for (size_t i = 0; i < n; i++) { b[pos_] ^= d[i]; if (++pos_ == R) run_f(); }
+  }
+  void begin_op(uint8_t flags, bool more) {
+    if (more) return;
+    uint8_t old_begin = pos_begin_;
+    pos_begin_ = pos_ + 1;
+    uint8_t hdr[2] = {old_begin, flags};
+    absorb(hdr, 2);
+    if ((flags & (FLAG_C | FLAG_K)) && pos_ != 0) run_f();
+  }
+  void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(FLAG_M | FLAG_A, more); absorb(d, n); }
+  void ad(const uint8_t* d, size_t n) { begin_op(FLAG_A, false); absorb(d, n); }
+};
+
+class RandomTape {  // random.rs:6-28; the OsRng seed scalar is an explicit input here
+ public:
+  RandomTape(const std::string& name, const Fq& seed) : tape_(name) { tape_.append_scalar("init_randomness", seed); }
+  Fq random_scalar(const char* label) { return tape_.challenge_scalar(label); }
+  std::vector<Fq> random_vector(const char* label, size_t n) { return tape_.challenge_vector(label, n); }
+
+ private:
+  Transcript tape_;
+};
+
+// ------------------------------------------------------------------------------------------------ small host commitments
+typedef uint8_t CompressedPoint[32];
+struct Cp {  // CompressedGroup (group.rs:7)
+  uint8_t b[32];
+  bool operator==(const Cp& o) const { return memcmp(b, o.b, 32) == 0; }
+};
+inline Cp compress(const ge& p) { Cp c; u256_to_bytes(c.b, ristretto_encode(p)); return c; }
+
+// 8-bit signed fixed-base windows for one generator: 32 windows x 128 affine-niels entries (copied from the device table)
+struct HostBaseTable {
+  std::vector<ge_niels> e;  // [w*128 + d-1]
+};
+inline void host_fixed_mul_acc(ge& acc, const HostBaseTable& tb, const Fq& k) {
+  if (k.is_zero()) return;
+  u256 c = k.canonical();
+  uint32_t carry = 0;
+  for (int w = 0; w < 32; w++) {
+    uint32_t v = ((c.v[w >> 2] >> ((w & 3) * 8)) & 0xffu) + carry;
+    int d;
+    if (v > 128u) { d = (int)v - 256; carry = 1; } else { d = (int)v; carry = 0; }
+    if (d == 0) continue;
+    int ad = d < 0 ? -d : d;
+    acc = ge_madd(acc, tb.e[(size_t)w * 128 + ad - 1], d < 0);
+  }
+}
+
+}  // namespace sp

@@ -1,0 +1,108 @@
+// spartan_b200 — CPU-only test hooks.  Compiled with -DSP_FORCE_PORTABLE so the *device* formulation of the field / curve
+// arithmetic (32-bit limbs, the code the kernels run) executes on the host and can be checked against the oracle without a GPU.
+// Not linked into libspartan_b200.so.
+#include "host.hpp"
+#include "engine.hpp"
+using namespace sp;
+
+namespace sp { void shake256(uint8_t* out, size_t outlen, const uint8_t* in, size_t inlen); }
+
+static u256 in256(const uint8_t* b) { u256 r; memcpy(&r, b, 32); return r; }
+static void out256(uint8_t* b, const u256& x) { memcpy(b, &x, 32); }
+
+extern "C" {
+int spt_portable(void) {
+#if SP_HOST_FAST
+  return 0;
+#else
+  return 1;
+#endif
+}
+void spt_fq_mul(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fq_mul(in256(a), in256(b))); }
+void spt_fq_add(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fq_add(in256(a), in256(b))); }
+void spt_fq_sub(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fq_sub(in256(a), in256(b))); }
+void spt_fq_inv(const uint8_t* a, uint8_t* r) { out256(r, fq_inv(in256(a))); }
+void spt_fq_from_wide(const uint8_t* w, uint8_t* r) { out256(r, fq_from_wide(in256(w), in256(w + 32))); }
+void spt_fq_from_mont(const uint8_t* a, uint8_t* r) { out256(r, fq_from_mont(in256(a))); }
+void spt_fq_from_u64(uint64_t x, uint8_t* r) { out256(r, fq_from_u64(x)); }
+// Fp: inputs / outputs as canonical little-endian integers
+void spt_fp_mul(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fp_canon(fp_mul(in256(a), in256(b)))); }
+void spt_fp_add(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fp_canon(fp_add(in256(a), in256(b)))); }
+void spt_fp_sub(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fp_canon(fp_sub(in256(a), in256(b)))); }
+void spt_fp_inv(const uint8_t* a, uint8_t* r) { out256(r, fp_canon(fp_inv(in256(a)))); }
+void spt_fp_canon(const uint8_t* a, uint8_t* r) { out256(r, fp_canon(in256(a))); }
+// group
+int spt_decode_encode(const uint8_t* in32, uint8_t* out32) {
+  ge g;
+  if (!ristretto_decode(g, in256(in32))) return 0;
+  out256(out32, ristretto_encode(g));
+  return 1;
+}
+void spt_from_uniform(const uint8_t* in64, uint8_t* out32) { out256(out32, ristretto_encode(ristretto_from_uniform(in256(in64), in256(in64 + 32)))); }
+int spt_add(const uint8_t* a32, const uint8_t* b32, uint8_t* out32) {
+  ge a, b;
+  if (!ristretto_decode(a, in256(a32)) || !ristretto_decode(b, in256(b32))) return 0;
+  out256(out32, ristretto_encode(ge_add(a, b)));
+  return 1;
+}
+int spt_dbl(const uint8_t* a32, uint8_t* out32) {
+  ge a;
+  if (!ristretto_decode(a, in256(a32))) return 0;
+  out256(out32, ristretto_encode(ge_dbl(a)));
+  return 1;
+}
+int spt_scalarmul(const uint8_t* k_canonical, const uint8_t* a32, uint8_t* out32) {
+  ge a;
+  if (!ristretto_decode(a, in256(a32))) return 0;
+  out256(out32, ristretto_encode(ge_scalarmul(in256(k_canonical), a)));
+  return 1;
+}
+// the fixed-base window path used by msm_rows / host_commit: build the 32x128 niels table of a point and multiply through it
+int spt_fixed_base_mul(const uint8_t* k_mont, const uint8_t* a32, uint8_t* out32) {
+  ge P;
+  if (!ristretto_decode(P, in256(a32))) return 0;
+  HostBaseTable tb;
+  tb.e.resize(32 * 128);
+  for (int w = 0; w < 32; w++) {
+    ge acc = P;
+    for (int d = 0; d < 128; d++) { tb.e[(size_t)w * 128 + d] = ge_to_niels(acc); acc = ge_add(acc, P); }
+    for (int k = 0; k < 8; k++) P = ge_dbl(P);
+  }
+  ge acc = ge_identity();
+  Fq k; memcpy(&k.m, k_mont, 32);
+  host_fixed_mul_acc(acc, tb, k);
+  out256(out32, ristretto_encode(acc));
+  return 1;
+}
+// transcript
+void spt_transcript_kat(uint8_t* out32) {
+  Transcript t("test protocol");
+  t.append_message("some label", (const uint8_t*)"some data", 9);
+  t.challenge_bytes("challenge", out32, 32);
+}
+void spt_transcript_run(const uint8_t* label, size_t llen, const uint8_t* msgs, const size_t* lens, size_t nmsgs, uint8_t* out64) {
+  Transcript t(std::string((const char*)label, llen));
+  size_t off = 0;
+  for (size_t i = 0; i < nmsgs; i++) { t.append_message("m", msgs + off, lens[i]); off += lens[i]; }
+  t.challenge_bytes("c", out64, 64);
+}
+void spt_shake256(uint8_t* out, size_t outlen, const uint8_t* in, size_t inlen) { sp::shake256(out, outlen, in, inlen); }
+}
+
+namespace sp {
+void shake256(uint8_t* out, size_t outlen, const uint8_t* in, size_t inlen) {
+  uint64_t st[25];
+  memset(st, 0, sizeof st);
+  uint8_t* sb = reinterpret_cast<uint8_t*>(st);
+  const size_t rate = 136;
+  while (inlen >= rate) { for (size_t i = 0; i < rate; i++) sb[i] ^= in[i]; Keccak::f1600(st); in += rate; inlen -= rate; }
+  for (size_t i = 0; i < inlen; i++) sb[i] ^= in[i];
+  sb[inlen] ^= 0x1f; sb[rate - 1] ^= 0x80;
+  Keccak::f1600(st);
+  while (outlen) {
+    size_t n = outlen < rate ? outlen : rate;
+    memcpy(out, sb, n); out += n; outlen -= n;
+    if (outlen) Keccak::f1600(st);
+  }
+}
+}

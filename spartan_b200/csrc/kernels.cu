@@ -1,0 +1,680 @@
+// spartan_b200 — hand-written sm_100a kernels for the Spartan prover hot path.
+//
+// Kernel families:
+//   K1/K2  sc_eval / sc_fold_eval / fold_top : dense-multilinear sumcheck rounds
+//          (reference loops: /root/reference/src/sumcheck.rs:460-469, :204-228, :296-355, :625-652 and
+//           src/dense_mlpoly.rs:215-223).  Streaming scans: 128-bit coalesced loads, per-thread field accumulators,
+//           warp-shuffle + shared-memory segmented reduction, last-block finalisation (no second launch).
+//   K3/K4  msm_rows : Pedersen commitments sum_j s_j*G_j (+ blind*h) for L rows sharing one generator set
+//          (reference: dalek vartime_multiscalar_mul behind src/group.rs:98-117, called from src/commitments.rs:80-92 and
+//           src/dense_mlpoly.rs:165-177).  Generators are fixed per `Gens`, so the kernel is a fixed-base comb: 8-bit signed
+//           windows, 128-entry affine-niels tables per (generator, window) resident in HBM, 7M mixed additions.
+//   K6     compress_batch / decompress_batch / gens_from_uniform (RFC 9496).
+//   K7     eq_evals, dot, bound_rows, lincomb3, hadamard, spmv, SPARK hash layer, IPA helpers.
+// All arithmetic is exact 256-bit integer work on the INT32 pipe; no tensor-core formulation exists.
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+#include <atomic>
+#include "dev.hpp"
+
+namespace sp {
+namespace dev {
+
+static std::atomic<unsigned long long> g_launches{0};
+#define SP_LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+unsigned long long launch_count() { return g_launches.load(); }
+
+void check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("spartan_b200 CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+static void ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string("spartan_b200 CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+void set_device(int d) { ck(cudaSetDevice(d), "cudaSetDevice"); }
+cudaStream_t stream_create() { cudaStream_t s; ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate"); return s; }
+void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
+void stream_sync(cudaStream_t s) { ck(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+void* dmalloc(size_t b) { void* p = nullptr; ck(cudaMalloc(&p, b ? b : 16), "cudaMalloc"); return p; }
+void dfree(void* p) { if (p) cudaFree(p); }
+void* hmalloc_pinned(size_t b) { void* p = nullptr; ck(cudaMallocHost(&p, b ? b : 16), "cudaMallocHost"); return p; }
+void hfree_pinned(void* p) { if (p) cudaFreeHost(p); }
+void h2d(void* d, const void* h, size_t b, cudaStream_t s) { if (b) ck(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s), "h2d"); }
+void d2h(void* h, const void* d, size_t b, cudaStream_t s) { if (b) ck(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s), "d2h"); }
+void d2d(void* dst, const void* src, size_t b, cudaStream_t s) { if (b) ck(cudaMemcpyAsync(dst, src, b, cudaMemcpyDeviceToDevice, s), "d2d"); }
+void dzero(void* d, size_t b, cudaStream_t s) { if (b) ck(cudaMemsetAsync(d, 0, b, s), "memset"); }
+int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+void* event_create() { cudaEvent_t e; ck(cudaEventCreate(&e), "cudaEventCreate"); return (void*)e; }
+void event_record(void* ev, cudaStream_t s) { ck(cudaEventRecord((cudaEvent_t)ev, s), "cudaEventRecord"); }
+float event_elapsed_ms(void* a, void* b) {
+  float ms = 0;
+  ck(cudaEventSynchronize((cudaEvent_t)b), "cudaEventSynchronize");
+  ck(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b), "cudaEventElapsedTime");
+  return ms;
+}
+void event_destroy(void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
+
+// =============================================================================================== helpers
+__device__ __forceinline__ u256 ld256(const u256* p) {  // two 128-bit loads
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  u256 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ u256 ld256_ro(const u256* p) {  // read-only path for data never written by the kernel
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  u256 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ u256 ld256_cg(const u256* p) {  // L2-coherent loads for cross-block partial sums
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldcg(q), b = __ldcg(q + 1);
+  u256 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st256(u256* p, const u256& x) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ u256 shfl_down_256(const u256& x, int delta) {
+  u256 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], delta);
+  return r;
+}
+__device__ __forceinline__ u256 warp_sum_fq(u256 x) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) x = fq_add(x, shfl_down_256(x, d));
+  return x;
+}
+
+// Block-wide sum of NV field values per thread, then cross-block finalisation by the last block to arrive.
+// partials: [gridDim.y][gridDim.x][NV]; counters: [gridDim.y] zero-initialised, self-resetting.
+template <int NV>
+__device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* partials, unsigned int* counters, u256* out, int out_stride) {
+  __shared__ u256 sm[32][NV];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    u256 s = warp_sum_fq(acc[k]);
+    if (lane == 0) sm[warp][k] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      u256 s = lane < nwarps ? sm[lane][k] : fq_zero();
+      s = warp_sum_fq(s);
+      if (lane == 0) st256(&partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NV + k], s);
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int ticket = atomicAdd(&counters[blockIdx.y], 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        u256 s = fq_zero();
+        for (unsigned int b = lane; b < gridDim.x; b += 32) s = fq_add(s, ld256_cg(&partials[((size_t)blockIdx.y * gridDim.x + b) * NV + k]));
+        s = warp_sum_fq(s);
+        if (lane == 0) st256(&out[(size_t)blockIdx.y * out_stride + k], s);
+      }
+      if (lane == 0) counters[blockIdx.y] = 0;
+    }
+  }
+}
+
+// =============================================================================================== sumcheck rounds
+#define SC_MAX_INST 24
+struct ScBatch {
+  ScInst inst[SC_MAX_INST];
+};
+
+template <int KIND>
+__device__ __forceinline__ u256 sc_comb(const u256& a, const u256& b, const u256& c, const u256& d) {
+  if (KIND == SC_QUAD) return fq_mul(a, b);                        // r1csproof.rs:122-123
+  if (KIND == SC_CUBIC3) return fq_mul(fq_mul(a, b), c);           // product_tree.rs:283-286
+  return fq_mul(a, fq_sub(fq_mul(b, c), d));                       // r1csproof.rs:87-91
+}
+
+template <int KIND>
+__device__ __forceinline__ void sc_accumulate(u256 (&acc)[3], const u256 (&lo)[4], const u256 (&hi)[4]) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  u256 x[4], dl[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) { x[t] = fq_zero(); dl[t] = fq_zero(); }
+  // t = 0 : low halves                                             (sumcheck.rs:463 / :627)
+  acc[0] = fq_add(acc[0], sc_comb<KIND>(lo[0], lo[1], lo[2], lo[3]));
+  // t = 2 : 2*hi - lo = hi + (hi - lo)                              (sumcheck.rs:466-468 / :630-639)
+#pragma unroll
+  for (int t = 0; t < NT; t++) { dl[t] = fq_sub(hi[t], lo[t]); x[t] = fq_add(hi[t], dl[t]); }
+  acc[1] = fq_add(acc[1], sc_comb<KIND>(x[0], x[1], x[2], x[3]));
+  if (KIND != SC_QUAD) {
+    // t = 3 : previous point + (hi - lo)                            (sumcheck.rs:642-651)
+#pragma unroll
+    for (int t = 0; t < NT; t++) x[t] = fq_add(x[t], dl[t]);
+    acc[2] = fq_add(acc[2], sc_comb<KIND>(x[0], x[1], x[2], x[3]));
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_sc_eval(ScBatch batch, size_t len, u256* partials, unsigned int* counters, u256* out) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1;
+  u256 acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    u256 lo[4], hi[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { lo[t] = fq_zero(); hi[t] = fq_zero(); }
+#pragma unroll
+    for (int t = 0; t < NT; t++) { lo[t] = ld256(in.t[t] + i); hi[t] = ld256(in.t[t] + i + half); }
+    sc_accumulate<KIND>(acc, lo, hi);
+  }
+  block_reduce_finish<3>(acc, partials, counters, out, 3);
+}
+
+// Fused: bind the top variable with r (len -> len/2) and evaluate the next round's polynomial on the folded table.
+// Thread i owns elements {i, i+len/4, i+len/2, i+3len/4} of every table: in-place update is race-free.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_sc_fold_eval(ScBatch batch, size_t len, const u256* __restrict__ rp, u256* partials,
+                                                       unsigned int* counters, u256* out) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1, quarter = len >> 2;
+  const u256 r = ld256_ro(rp);
+  u256 acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quarter; i += (size_t)gridDim.x * blockDim.x) {
+    u256 lo[4], hi[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { lo[t] = fq_zero(); hi[t] = fq_zero(); }
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      u256 a0 = ld256(in.t[t] + i), a1 = ld256(in.t[t] + i + half);
+      u256 b0 = ld256(in.t[t] + i + quarter), b1 = ld256(in.t[t] + i + quarter + half);
+      lo[t] = fq_add(a0, fq_mul(r, fq_sub(a1, a0)));   // dense_mlpoly.rs:218
+      hi[t] = fq_add(b0, fq_mul(r, fq_sub(b1, b0)));
+      if (t == 2) {
+        if (in.write_c) { st256(in.c_out + i, lo[t]); st256(in.c_out + i + quarter, hi[t]); }
+      } else {
+        st256(in.t[t] + i, lo[t]); st256(in.t[t] + i + quarter, hi[t]);
+      }
+    }
+    sc_accumulate<KIND>(acc, lo, hi);
+  }
+  block_reduce_finish<3>(acc, partials, counters, out, 3);
+}
+
+struct FoldBatch {
+  u256* t[64];
+};
+__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const u256* __restrict__ rp) {
+  const size_t half = len >> 1;
+  u256* T = tabs.t[blockIdx.y];
+  const u256 r = ld256_ro(rp);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    u256 a0 = ld256(T + i), a1 = ld256(T + i + half);
+    st256(T + i, fq_add(a0, fq_mul(r, fq_sub(a1, a0))));
+  }
+}
+
+static unsigned int grid_for(size_t work, int threads, int per_sm) {
+  size_t blocks = (work + threads - 1) / threads;
+  size_t cap = (size_t)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned int)blocks;
+}
+
+// scratch layout: [counters: 64 x u32][partials]
+static const size_t SC_MAX_BLOCKS = 148 * 4 + 64;
+size_t sc_scratch_bytes(int ninst) { return 256 + (size_t)ninst * SC_MAX_BLOCKS * 3 * sizeof(u256); }
+
+static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
+  if (ninst > SC_MAX_INST) throw std::runtime_error("spartan_b200: too many sumcheck instances in one batch");
+  for (int i = 0; i < ninst; i++) b.inst[i] = insts[i];
+}
+
+void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s) {
+  ScBatch b; fill_batch(b, insts, ninst);
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(len / 2, 256, 2), ninst);
+  if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
+  switch (kind) {
+    case SC_QUAD: k_sc_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
+    case SC_CUBIC3: k_sc_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
+    default: k_sc_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
+  }
+  SP_LAUNCHED(); check("sc_eval");
+}
+void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256* d_r, u256* out, void* scratch, cudaStream_t s) {
+  ScBatch b; fill_batch(b, insts, ninst);
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(len / 4, 256, 2), ninst);
+  if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
+  switch (kind) {
+    case SC_QUAD: k_sc_fold_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
+    case SC_CUBIC3: k_sc_fold_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
+    default: k_sc_fold_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
+  }
+  SP_LAUNCHED(); check("sc_fold_eval");
+}
+void fold_top(u256* const* tables, int ntables, size_t len, const u256* d_r, cudaStream_t s) {
+  for (int base = 0; base < ntables; base += 64) {
+    FoldBatch fb; int n = ntables - base < 64 ? ntables - base : 64;
+    for (int i = 0; i < n; i++) fb.t[i] = tables[base + i];
+    dim3 grid(grid_for(len / 2, 256, 4), n);
+    k_fold_top<<<grid, 256, 0, s>>>(fb, len, d_r);
+    SP_LAUNCHED();
+  }
+  check("fold_top");
+}
+void fold_top_single(u256* table, size_t len, const u256* d_r, cudaStream_t s) { u256* t[1] = {table}; fold_top(t, 1, len, d_r, s); }
+
+// =============================================================================================== dense helpers
+// eq(r, .) table (dense_mlpoly.rs:68-84): out[i] = prod_j (bit_j(i) ? r_j : 1 - r_j), bit 0 of r = most significant bit of i.
+// Two-level: small tables for the high / low halves of the variables, then one product per output element.
+__global__ void k_eq_small(u256* out, const u256* __restrict__ r, int nv) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((size_t)1 << nv)) return;
+  u256 acc = fq_one();
+  for (int j = 0; j < nv; j++) {
+    u256 rj = ld256_ro(r + j);
+    bool bit = (i >> (nv - 1 - j)) & 1;
+    acc = fq_mul(acc, bit ? rj : fq_sub(fq_one(), rj));
+  }
+  st256(out + i, acc);
+}
+__global__ void k_eq_combine(u256* out, const u256* __restrict__ hi, const u256* __restrict__ lo, int nlo, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st256(out + i, fq_mul(ld256_ro(hi + (i >> nlo)), ld256_ro(lo + (i & (((size_t)1 << nlo) - 1)))));
+}
+void eq_evals(u256* out, const u256* d_r, int ell, u256* small, cudaStream_t s) {
+  if (ell <= 10) {
+    size_t n = (size_t)1 << ell;
+    k_eq_small<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(out, d_r, ell);
+    SP_LAUNCHED(); check("eq_small");
+    return;
+  }
+  int nhi = ell / 2, nlo = ell - nhi;
+  u256* thi = small; u256* tlo = small + ((size_t)1 << nhi);
+  k_eq_small<<<(unsigned)((((size_t)1 << nhi) + 127) / 128), 128, 0, s>>>(thi, d_r, nhi);
+  k_eq_small<<<(unsigned)((((size_t)1 << nlo) + 127) / 128), 128, 0, s>>>(tlo, d_r + nhi, nlo);
+  size_t n = (size_t)1 << ell;
+  k_eq_combine<<<grid_for(n, 256, 8), 256, 0, s>>>(out, thi, tlo, nlo, n);
+  SP_LAUNCHED(); SP_LAUNCHED(); SP_LAUNCHED(); check("eq_evals");
+}
+
+__global__ void __launch_bounds__(256) k_dot(const u256* __restrict__ a, const u256* __restrict__ b, const u256* __restrict__ c, size_t n,
+                                            u256* partials, unsigned int* counters, u256* out) {
+  u256 acc[1] = {fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    u256 m = fq_mul(ld256_ro(a + i), ld256_ro(b + i));
+    if (c) m = fq_mul(m, ld256_ro(c + i));
+    acc[0] = fq_add(acc[0], m);
+  }
+  block_reduce_finish<1>(acc, partials, counters, out, 1);
+}
+void dot3(u256* out, const u256* a, const u256* b, const u256* c, size_t n, void* scratch, cudaStream_t s) {
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(n, 256, 2), 1);
+  k_dot<<<grid, 256, 0, s>>>(a, b, c, n, partials, counters, out);
+  SP_LAUNCHED(); check("dot");
+}
+void dot(u256* out, const u256* a, const u256* b, size_t n, void* scratch, cudaStream_t s) { dot3(out, a, b, nullptr, n, scratch, s); }
+
+// DensePolynomial::bound (dense_mlpoly.rs:206-213): out[i] = sum_j L[j]*Z[j*R+i].  Column-per-thread (coalesced over i),
+// rows split into gridDim.y slabs whose partial sums land in scratch and are combined by a second tiny kernel.
+__global__ void __launch_bounds__(128) k_bound_rows_partial(u256* part, const u256* __restrict__ Z, const u256* __restrict__ L, size_t L_size,
+                                                           size_t R_size, size_t rows_per_slab) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R_size) return;
+  size_t j0 = (size_t)blockIdx.y * rows_per_slab, j1 = j0 + rows_per_slab;
+  if (j1 > L_size) j1 = L_size;
+  u256 acc = fq_zero();
+  for (size_t j = j0; j < j1; j++) acc = fq_add(acc, fq_mul(ld256_ro(L + j), ld256_ro(Z + j * R_size + i)));
+  st256(part + (size_t)blockIdx.y * R_size + i, acc);
+}
+__global__ void k_sum_slabs(u256* out, const u256* __restrict__ part, size_t R_size, int nslabs) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R_size) return;
+  u256 acc = fq_zero();
+  for (int k = 0; k < nslabs; k++) acc = fq_add(acc, ld256_ro(part + (size_t)k * R_size + i));
+  st256(out + i, acc);
+}
+void bound_rows(u256* out, const u256* Z, const u256* L, size_t L_size, size_t R_size, u256* scratch, cudaStream_t s) {
+  int nslabs = 64;
+  while (nslabs > 1 && (size_t)nslabs > L_size) nslabs >>= 1;
+  size_t rows_per_slab = (L_size + nslabs - 1) / nslabs;
+  dim3 grid((unsigned)((R_size + 127) / 128), nslabs);
+  k_bound_rows_partial<<<grid, 128, 0, s>>>(scratch, Z, L, L_size, R_size, rows_per_slab);
+  k_sum_slabs<<<(unsigned)((R_size + 127) / 128), 128, 0, s>>>(out, scratch, R_size, nslabs);
+  SP_LAUNCHED(); SP_LAUNCHED(); check("bound_rows");
+}
+
+__global__ void k_lincomb3(u256* out, const u256* __restrict__ A, const u256* __restrict__ B, const u256* __restrict__ C,
+                           const u256* __restrict__ rabc, size_t n) {
+  u256 ra = ld256_ro(rabc), rb = ld256_ro(rabc + 1), rc = ld256_ro(rabc + 2);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st256(out + i, fq_add(fq_add(fq_mul(ra, ld256_ro(A + i)), fq_mul(rb, ld256_ro(B + i))), fq_mul(rc, ld256_ro(C + i))));
+}
+void lincomb3(u256* out, const u256* A, const u256* B, const u256* C, const u256* d_rabc, size_t n, cudaStream_t s) {
+  k_lincomb3<<<grid_for(n, 256, 4), 256, 0, s>>>(out, A, B, C, d_rabc, n);
+  SP_LAUNCHED(); check("lincomb3");
+}
+__global__ void k_hadamard(u256* out, const u256* a, const u256* b, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st256(out + i, fq_mul(ld256(a + i), ld256(b + i)));
+}
+void hadamard(u256* out, const u256* a, const u256* b, size_t n, cudaStream_t s) {
+  k_hadamard<<<grid_for(n, 256, 8), 256, 0, s>>>(out, a, b, n);
+  SP_LAUNCHED(); check("hadamard");
+}
+__global__ void k_from_u64(u256* out, const uint64_t* __restrict__ v, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st256(out + i, fq_from_u64(v[i]));
+}
+void from_u64(u256* out, const uint64_t* v, size_t n, cudaStream_t s) {
+  k_from_u64<<<grid_for(n, 256, 8), 256, 0, s>>>(out, v, n);
+  SP_LAUNCHED(); check("from_u64");
+}
+__global__ void k_from_wide(u256* out, const uint8_t* __restrict__ in, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u256* p = reinterpret_cast<const u256*>(in + 64 * i);
+    st256(out + i, fq_from_wide(ld256_ro(p), ld256_ro(p + 1)));
+  }
+}
+void from_bytes_wide(u256* out, const uint8_t* in64, size_t n, cudaStream_t s) {
+  k_from_wide<<<grid_for(n, 256, 8), 256, 0, s>>>(out, in64, n);
+  SP_LAUNCHED(); check("from_bytes_wide");
+}
+__global__ void k_invert(u256* x, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st256(x + i, fq_inv(ld256(x + i)));
+}
+void batch_invert_elems(u256* x, size_t n, cudaStream_t s) {
+  k_invert<<<grid_for(n, 128, 16), 128, 0, s>>>(x, n);
+  SP_LAUNCHED(); check("invert");
+}
+__global__ void k_gather(u256* out, const u256* __restrict__ mem, const uint32_t* __restrict__ idx, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st256(out + i, ld256_ro(mem + idx[i]));
+}
+void gather(u256* out, const u256* mem, const uint32_t* idx, size_t n, cudaStream_t s) {
+  k_gather<<<grid_for(n, 256, 8), 256, 0, s>>>(out, mem, idx, n);
+  SP_LAUNCHED(); check("gather");
+}
+__global__ void k_spark_hash(u256* out, size_t n, const u256* __restrict__ addr, const u256* __restrict__ val, const u256* __restrict__ ts,
+                             int ts_plus_one, const u256* __restrict__ rg) {
+  u256 r = ld256_ro(rg), g = ld256_ro(rg + 1), r2 = fq_sqr(r);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    u256 a = addr ? ld256_ro(addr + i) : fq_from_u64((uint64_t)i);
+    u256 t = ts ? ld256_ro(ts + i) : fq_zero();
+    if (ts_plus_one) t = fq_add(t, fq_one());
+    u256 h = fq_add(fq_add(fq_mul(t, r2), fq_mul(ld256_ro(val + i), r)), a);
+    st256(out + i, fq_sub(h, g));
+  }
+}
+void spark_hash(u256* out, size_t n, const u256* addr, const u256* val, const u256* ts, int ts_plus_one, const u256* d_rg, cudaStream_t s) {
+  k_spark_hash<<<grid_for(n, 256, 4), 256, 0, s>>>(out, n, addr, val, ts, ts_plus_one, d_rg);
+  SP_LAUNCHED(); check("spark_hash");
+}
+__global__ void k_fill_one(u256* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st256(out + i, fq_one());
+}
+void fill_one(u256* out, size_t n, cudaStream_t s) {
+  k_fill_one<<<grid_for(n, 256, 8), 256, 0, s>>>(out, n);
+  SP_LAUNCHED(); check("fill_one");
+}
+
+// ---- IPA helpers (nizk/bullet.rs:72-119)
+__global__ void k_ipa_fold_ab(u256* a, u256* b, size_t n, const u256* __restrict__ up) {
+  u256 u = ld256_ro(up), ui = ld256_ro(up + 1);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    u256 aL = ld256(a + i), aR = ld256(a + i + n), bL = ld256(b + i), bR = ld256(b + i + n);
+    st256(a + i, fq_add(fq_mul(aL, u), fq_mul(ui, aR)));   // bullet.rs:106
+    st256(b + i, fq_add(fq_mul(bL, ui), fq_mul(u, bR)));   // bullet.rs:107
+  }
+}
+void ipa_fold_ab(u256* a, u256* b, size_t n, const u256* d_u, cudaStream_t s) {
+  k_ipa_fold_ab<<<grid_for(n, 128, 8), 128, 0, s>>>(a, b, n, d_u);
+  SP_LAUNCHED(); check("ipa_fold_ab");
+}
+// G is never folded on the device: after k rounds G_k[i] = sum_{j = i mod n_k} s[j]*G[j], so the round's
+// L = <a_L, G_R> and R = <a_R, G_L> are full-length fixed-base MSMs with scalars a[.]*s[j] (zero on the other half).
+__global__ void k_ipa_lr(u256* outL, u256* outR, const u256* __restrict__ a, const u256* __restrict__ sv, size_t n_cur, size_t n_full) {
+  size_t half = n_cur >> 1;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_full; j += (size_t)gridDim.x * blockDim.x) {
+    size_t ip = j & (n_cur - 1);
+    u256 sj = ld256_ro(sv + j);
+    if (ip >= half) { st256(outL + j, fq_mul(ld256_ro(a + ip - half), sj)); st256(outR + j, fq_zero()); }
+    else { st256(outL + j, fq_zero()); st256(outR + j, fq_mul(ld256_ro(a + ip + half), sj)); }
+  }
+}
+void ipa_lr_scalars(u256* outL, u256* outR, const u256* a, const u256* svec, size_t n_cur, size_t n_full, cudaStream_t s) {
+  k_ipa_lr<<<grid_for(n_full, 128, 8), 128, 0, s>>>(outL, outR, a, svec, n_cur, n_full);
+  SP_LAUNCHED(); check("ipa_lr");
+}
+__global__ void k_ipa_update_s(u256* sv, size_t half, size_t n_full, const u256* __restrict__ up) {
+  u256 u = ld256_ro(up), ui = ld256_ro(up + 1);
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_full; j += (size_t)gridDim.x * blockDim.x) {
+    bool right = (j & (2 * half - 1)) >= half;
+    st256(sv + j, fq_mul(ld256(sv + j), right ? u : ui));   // G_L[i] <- u^-1 G_L[i] + u G_R[i], bullet.rs:108
+  }
+}
+void ipa_update_s(u256* svec, size_t half, size_t n_full, const u256* d_u, cudaStream_t s) {
+  k_ipa_update_s<<<grid_for(n_full, 128, 8), 128, 0, s>>>(svec, half, n_full, d_u);
+  SP_LAUNCHED(); check("ipa_update_s");
+}
+
+// ---- sparse
+__global__ void k_spmv(u256* out, size_t nrows, const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, const u256* __restrict__ val,
+                       const u256* __restrict__ x) {
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (size_t)gridDim.x * blockDim.x) {
+    u256 acc = fq_zero();
+    for (uint32_t k = ptr[r]; k < ptr[r + 1]; k++) acc = fq_add(acc, fq_mul(ld256_ro(val + k), ld256_ro(x + idx[k])));
+    st256(out + r, acc);
+  }
+}
+void spmv(u256* out, size_t nrows, const uint32_t* ptr, const uint32_t* idx, const u256* val, const u256* x, cudaStream_t s) {
+  k_spmv<<<grid_for(nrows, 128, 8), 128, 0, s>>>(out, nrows, ptr, idx, val, x);
+  SP_LAUNCHED(); check("spmv");
+}
+__global__ void __launch_bounds__(256) k_sparse_eval3(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col, const u256* __restrict__ val,
+                                                     size_t nnz, const u256* __restrict__ trx, const u256* __restrict__ try_, u256* partials,
+                                                     unsigned int* counters, u256* out) {
+  u256 acc[1] = {fq_zero()};
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (size_t)gridDim.x * blockDim.x)
+    acc[0] = fq_add(acc[0], fq_mul(fq_mul(ld256_ro(trx + row[k]), ld256_ro(try_ + col[k])), ld256_ro(val + k)));
+  block_reduce_finish<1>(acc, partials, counters, out, 1);
+}
+void sparse_eval3(u256* out, const uint32_t* row, const uint32_t* col, const u256* val, size_t nnz, const u256* trx, const u256* try_,
+                  void* scratch, cudaStream_t s) {
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(nnz, 256, 2), 1);
+  k_sparse_eval3<<<grid, 256, 0, s>>>(row, col, val, nnz, trx, try_, partials, counters, out);
+  SP_LAUNCHED(); check("sparse_eval3");
+}
+
+// =============================================================================================== group kernels
+__device__ __forceinline__ ge ld_ge(const ge* p) {
+  ge r;
+  r.X = ld256(&p->X); r.Y = ld256(&p->Y); r.Z = ld256(&p->Z); r.T = ld256(&p->T);
+  return r;
+}
+__device__ __forceinline__ void st_ge(ge* p, const ge& g) { st256(&p->X, g.X); st256(&p->Y, g.Y); st256(&p->Z, g.Z); st256(&p->T, g.T); }
+
+__global__ void k_gens_from_uniform(ge* out, const uint8_t* __restrict__ uni, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u256* p = reinterpret_cast<const u256*>(uni + 64 * i);
+  st_ge(out + i, ristretto_from_uniform(ld256_ro(p), ld256_ro(p + 1)));
+}
+void gens_from_uniform(ge* out, const uint8_t* d_uniform64, size_t n, cudaStream_t s) {
+  k_gens_from_uniform<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(out, d_uniform64, n);
+  SP_LAUNCHED(); check("gens_from_uniform");
+}
+__global__ void k_decompress(ge* out, int* ok, const uint8_t* __restrict__ in, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ge g = ge_identity();
+  bool good = ristretto_decode(g, ld256_ro(reinterpret_cast<const u256*>(in + 32 * i)));
+  st_ge(out + i, g);
+  if (ok) ok[i] = good ? 1 : 0;
+}
+void decompress_batch(ge* out, int* ok, const uint8_t* in32, size_t n, cudaStream_t s) {
+  k_decompress<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(out, ok, in32, n);
+  SP_LAUNCHED(); check("decompress");
+}
+__global__ void k_compress(uint8_t* out, const ge* __restrict__ in, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st256(reinterpret_cast<u256*>(out + 32 * i), ristretto_encode(ld_ge(in + i)));
+}
+void compress_batch(uint8_t* out32, const ge* in, size_t n, cudaStream_t s) {
+  k_compress<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(out32, in, n);
+  SP_LAUNCHED(); check("compress");
+}
+
+// ---- fixed-base window tables: entry (j, w, d-1) = d * 2^(8w) * G_j, affine niels
+#define MSM_WINDOWS 32
+#define MSM_TABLE_D 128
+size_t table_entries(size_t nbases) { return nbases * MSM_WINDOWS * MSM_TABLE_D; }
+__global__ void __launch_bounds__(64) k_build_tables(ge_niels* table, const ge* __restrict__ G, size_t nbases) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbases * MSM_WINDOWS) return;
+  size_t j = t / MSM_WINDOWS;
+  int w = (int)(t % MSM_WINDOWS);
+  ge P = ld_ge(G + j);
+  for (int k = 0; k < 8 * w; k++) P = ge_dbl(P);
+  ge acc = P;
+  ge_niels* dst = table + t * MSM_TABLE_D;
+  for (int d = 0; d < MSM_TABLE_D; d++) {
+    ge_niels nl = ge_to_niels(acc);  // the a=-1 addition law is complete: Z never vanishes
+    st256(&dst[d].ypx, nl.ypx); st256(&dst[d].ymx, nl.ymx); st256(&dst[d].t2d, nl.t2d);
+    acc = ge_add(acc, P);
+  }
+}
+void build_tables(ge_niels* table, const ge* G, size_t nbases, cudaStream_t s) {
+  size_t threads = nbases * MSM_WINDOWS;
+  k_build_tables<<<(unsigned)((threads + 63) / 64), 64, 0, s>>>(table, G, nbases);
+  SP_LAUNCHED(); check("build_tables");
+}
+
+// ---- multi-row fixed-base MSM
+// grid = (chunks, L); block = 128 threads; a block covers COLS = 128*WPT/32 columns of one row.  Thread t handles column
+// t / (32/WPT) of the chunk and WPT consecutive 8-bit windows.  Signed digits in [-127,128]; zero digits are skipped
+// (vartime, like the reference's vartime_multiscalar_mul).  Partial sums are tree-reduced through shared memory.
+template <int WPT>
+__global__ void __launch_bounds__(128) k_msm_rows(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ scalars, size_t stride,
+                                                  size_t R, const u256* __restrict__ blinds, size_t blind_base) {
+  constexpr int GROUPS = MSM_WINDOWS / WPT;      // threads per column
+  constexpr int COLS = 128 / GROUPS;             // columns per block
+  const size_t row = blockIdx.y;
+  const size_t ncols = R + (blinds ? 1 : 0);
+  const size_t col = (size_t)blockIdx.x * COLS + threadIdx.x / GROUPS;
+  const int g = threadIdx.x % GROUPS;
+  ge acc = ge_identity();
+  if (col < ncols) {
+    u256 k;
+    size_t base;
+    if (col < R) { k = ld256_ro(scalars + row * stride + col); base = col; }
+    else { k = ld256_ro(blinds + row); base = blind_base; }
+    if (!fq_is_zero(k)) {
+      k = fq_from_mont(k);  // group.rs:110-113: scalars leave Montgomery form before the MSM
+      // carry into window g*WPT from the signed recoding of the lower bytes
+      uint32_t carry = 0;
+      for (int w = 0; w < g * WPT; w++) {
+        uint32_t v = ((k.v[w >> 2] >> ((w & 3) * 8)) & 0xffu) + carry;
+        carry = v > 128u ? 1u : 0u;
+      }
+      const ge_niels* tb = table + (base * MSM_WINDOWS + (size_t)g * WPT) * MSM_TABLE_D;
+#pragma unroll 1
+      for (int w = g * WPT; w < (g + 1) * WPT; w++, tb += MSM_TABLE_D) {
+        uint32_t v = ((k.v[w >> 2] >> ((w & 3) * 8)) & 0xffu) + carry;
+        int d;
+        if (v > 128u) { d = (int)v - 256; carry = 1; } else { d = (int)v; carry = 0; }
+        if (d == 0) continue;
+        int ad = d < 0 ? -d : d;
+        const ge_niels* e = tb + (ad - 1);
+        ge_niels nl;
+        nl.ypx = ld256_ro(&e->ypx); nl.ymx = ld256_ro(&e->ymx); nl.t2d = ld256_ro(&e->t2d);
+        acc = ge_madd(acc, nl, d < 0);
+      }
+    }
+  }
+  __shared__ ge sm[64];
+  for (int s = 64; s > 0; s >>= 1) {
+    if (threadIdx.x >= s && threadIdx.x < 2 * s) sm[threadIdx.x - s] = acc;
+    __syncthreads();
+    if (threadIdx.x < s) acc = ge_add(acc, sm[threadIdx.x]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_ge(partial + row * gridDim.x + blockIdx.x, acc);
+}
+__global__ void __launch_bounds__(32) k_msm_reduce(ge* out, const ge* __restrict__ partial, int chunks) {
+  const size_t row = blockIdx.x;
+  ge acc = ge_identity();
+  for (int c = threadIdx.x; c < chunks; c += 32) acc = ge_add(acc, ld_ge(partial + row * chunks + c));
+  __shared__ ge sm[16];
+  for (int s = 16; s > 0; s >>= 1) {
+    if (threadIdx.x >= s && threadIdx.x < 2 * s) sm[threadIdx.x - s] = acc;
+    __syncwarp();
+    if (threadIdx.x < s) acc = ge_add(acc, sm[threadIdx.x]);
+    __syncwarp();
+  }
+  if (threadIdx.x == 0) st_ge(out + row, acc);
+}
+static int msm_pick_wpt(size_t L, size_t R) {
+  // enough threads to fill the chip: prefer many windows per thread (less reduction) once L*R is large
+  size_t cols = L * (R + 1);
+  size_t target = (size_t)sm_count() * 1024;
+  if (cols * 1 >= target) return 32;
+  if (cols * 4 >= target) return 8;
+  return 4;
+}
+static size_t msm_chunks(size_t R1, int wpt) { size_t cols = 128 / (MSM_WINDOWS / wpt); return (R1 + cols - 1) / cols; }
+size_t msm_scratch_bytes(size_t L, size_t R) {
+  size_t worst = msm_chunks(R + 1, 4);
+  return L * worst * sizeof(ge);
+}
+void msm_rows(ge* out, const ge_niels* table, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
+              void* scratch, cudaStream_t s) {
+  int wpt = msm_pick_wpt(L, R);
+  size_t chunks = msm_chunks(R + (blinds ? 1 : 0), wpt);
+  ge* partial = (ge*)scratch;
+  for (size_t row0 = 0; row0 < L; row0 += 32768) {   // gridDim.y limit 65535
+    size_t rows = L - row0 < 32768 ? L - row0 : 32768;
+    dim3 grid((unsigned)chunks, (unsigned)rows);
+    const u256* sc = scalars + row0 * stride;
+    const u256* bl = blinds ? blinds + row0 : nullptr;
+    ge* pp = partial + row0 * chunks;
+    if (wpt == 32) k_msm_rows<32><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
+    else if (wpt == 8) k_msm_rows<8><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
+    else k_msm_rows<4><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
+    SP_LAUNCHED();
+  }
+  k_msm_reduce<<<(unsigned)L, 32, 0, s>>>(out, partial, (int)chunks);
+  SP_LAUNCHED(); check("msm_rows");
+}
+
+}  // namespace dev
+}  // namespace sp

@@ -1,0 +1,595 @@
+// spartan_b200 — host prover for the R1CS satisfiability proof (NIZK path), driving the sm_100a kernels.
+// Follows the exact Fiat-Shamir schedule of /root/reference/src/r1csproof.rs:144-349 so that the
+// proof bytes equal the reference's for identical instance, assignment, transcript label and RandomTape seed.
+#include "prover.hpp"
+#include <chrono>
+
+namespace sp {
+
+// ================================================================================================ plumbing
+void shake256(uint8_t* out, size_t outlen, const uint8_t* in, size_t inlen) {
+  uint64_t st[25];
+  memset(st, 0, sizeof st);
+  uint8_t* sb = reinterpret_cast<uint8_t*>(st);
+  const size_t rate = 136;
+  while (inlen >= rate) { for (size_t i = 0; i < rate; i++) sb[i] ^= in[i]; Keccak::f1600(st); in += rate; inlen -= rate; }
+  for (size_t i = 0; i < inlen; i++) sb[i] ^= in[i];
+  sb[inlen] ^= 0x1f; sb[rate - 1] ^= 0x80;
+  Keccak::f1600(st);
+  while (outlen) {
+    size_t n = outlen < rate ? outlen : rate;
+    memcpy(out, sb, n); out += n; outlen -= n;
+    if (outlen) Keccak::f1600(st);
+  }
+}
+
+Ctx::Ctx(int dev_) : device(dev_) {
+  if (dev::device_count() <= dev_) throw std::runtime_error("spartan_b200: no CUDA device " + std::to_string(dev_) + " (the prover has no CPU fallback)");
+  dev::set_device(dev_);
+  stream = dev::stream_create();
+  pinned_bytes = 1 << 20;
+  pinned = (uint8_t*)dev::hmalloc_pinned(pinned_bytes);
+  small.alloc(4096);
+  scratch.alloc(dev::sc_scratch_bytes(24) + (1 << 20));
+  dev::dzero(scratch.p, scratch.n, stream);
+  sync();
+}
+Ctx::~Ctx() {
+  try { sync(); } catch (...) {}
+  scratch.release(); small.release();
+  dev::hfree_pinned(pinned);
+  dev::stream_destroy(stream);
+}
+void Ctx::put_small(size_t slot, const Fq* v, size_t k) {
+  // staged through pageable memory on purpose: cudaMemcpyAsync from pageable memory snapshots the source before returning
+  dev::h2d(small.p + slot, v, k * sizeof(u256), stream);
+}
+void Ctx::get_small(size_t slot, Fq* v, size_t k) {
+  dev::d2h(pinned, small.p + slot, k * sizeof(u256), stream);
+  sync();
+  memcpy(v, pinned, k * sizeof(u256));
+}
+void Ctx::upload(u256* d, const Fq* h, size_t n) { dev::h2d(d, h, n * sizeof(u256), stream); sync(); }
+std::vector<Fq> Ctx::download(const u256* d, size_t n) {
+  std::vector<Fq> v(n);
+  dev::d2h(v.data(), d, n * sizeof(u256), stream);
+  sync();
+  return v;
+}
+
+GenSet::GenSet(Ctx* c, const std::string& label_, size_t nbases_, const std::vector<size_t>& host_bases) : ctx(c), label(label_), nbases(nbases_) {
+  // MultiCommitGens::new (commitments.rs:15-33): SHAKE256(label || basepoint), 64 bytes per generator
+  static const uint8_t basepoint[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+                                        0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
+  std::vector<uint8_t> seed(label.begin(), label.end());
+  seed.insert(seed.end(), basepoint, basepoint + 32);
+  std::vector<uint8_t> uni(64 * nbases);
+  shake256(uni.data(), uni.size(), seed.data(), seed.size());
+  DevBuf<uint8_t> d_uni(uni.size());
+  dev::h2d(d_uni.p, uni.data(), uni.size(), ctx->stream);
+  G.alloc(nbases);
+  dev::gens_from_uniform(G.p, d_uni.p, nbases, ctx->stream);
+  table.alloc(dev::table_entries(nbases));
+  dev::build_tables(table.p, G.p, nbases, ctx->stream);
+  ctx->sync();
+  for (size_t b : host_bases) {
+    if (b >= nbases) continue;
+    HostBaseTable t;
+    t.e.resize(32 * 128);
+    dev::d2h(t.e.data(), table.p + b * 32 * 128, sizeof(ge_niels) * 32 * 128, ctx->stream);
+    ctx->sync();
+    host_tab[b] = std::move(t);
+  }
+}
+ge GenSet::host_point(size_t base) const {
+  ge acc = ge_identity();
+  return ge_madd(acc, tab(base).e[0], false);
+}
+ge host_commit(const GenSet& gs, const Term* terms, size_t nterms) {
+  ge acc = ge_identity();
+  for (size_t i = 0; i < nterms; i++) host_fixed_mul_acc(acc, gs.tab(terms[i].base), terms[i].k);
+  return acc;
+}
+
+R1CSGens::R1CSGens(Ctx* ctx, const std::string& label, size_t num_vars) {
+  // R1CSGens::new (r1csproof.rs:68-73) -> PolyCommitmentGens::new(log2 num_vars) (dense_mlpoly.rs:31-35) ->
+  // DotProductProofGens::new(2^ceil(ell/2)) = MultiCommitGens::new(n+1).split_at(n) (nizk/mod.rs:414-418)
+  size_t ell = 0;
+  while (((size_t)1 << ell) < num_vars) ell++;
+  size_t n = (size_t)1 << (ell - ell / 2);
+  set.reset(new GenSet(ctx, label, n + 2, {0, 1, 2, 3, 4, n, n + 1}));
+  gens_pc.n = n;
+  gens_pc.gens_n = CommitKey{set.get(), 0, n, n + 1};
+  gens_pc.gens_1 = CommitKey{set.get(), n, 1, n + 1};
+  gens_1 = gens_pc.gens_1;                       // R1CSSumcheckGens::new clones gens_pc.gens.gens_1 (r1csproof.rs:48-58)
+  gens_3 = CommitKey{set.get(), 0, 3, 3};        // MultiCommitGens::new(3, label): same SHAKE prefix, h = 4th point
+  gens_4 = CommitKey{set.get(), 0, 4, 4};
+}
+
+// ================================================================================================ small host protocol pieces
+static Cp commit1(const CommitKey& k, const Fq& x, const Fq& blind) {  // impl Commitments for Scalar (commitments.rs:73-78)
+  Term t[2] = {{k.off, x}, {k.h, blind}};
+  return compress(host_commit(*k.set, t, 2));
+}
+static Cp commitv(const CommitKey& k, const std::vector<Fq>& x, const Fq& blind) {  // impl Commitments for [Scalar] (:80-92), small n only
+  std::vector<Term> t;
+  for (size_t i = 0; i < x.size(); i++) t.push_back({k.off + i, x[i]});
+  t.push_back({k.h, blind});
+  return compress(host_commit(*k.set, t.data(), t.size()));
+}
+
+struct UniPoly {  // unipoly.rs
+  std::vector<Fq> coeffs;
+  static UniPoly from_evals(const std::vector<Fq>& e) {  // unipoly.rs:23-54
+    static const Fq two_inv = Fq::from_u64(2).inv(), six_inv = Fq::from_u64(6).inv();
+    UniPoly p;
+    if (e.size() == 3) {
+      Fq c = e[0];
+      Fq a = two_inv * (e[2] - e[1] - e[1] + c);
+      Fq b = e[1] - c - a;
+      p.coeffs = {c, b, a};
+    } else {
+      Fq d = e[0];
+      Fq a = six_inv * (e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0]);
+      Fq b = two_inv * (e[0] + e[0] - e[1] - e[1] - e[1] - e[1] - e[1] + e[2] + e[2] + e[2] + e[2] - e[3]);
+      Fq c = e[1] - d - a - b;
+      p.coeffs = {d, c, b, a};
+    }
+    return p;
+  }
+  Fq evaluate(const Fq& r) const {  // unipoly.rs:72-80
+    Fq ev = coeffs[0], power = r;
+    for (size_t i = 1; i < coeffs.size(); i++) { ev += power * coeffs[i]; power *= r; }
+    return ev;
+  }
+  CompressedUniPoly compress() const {  // unipoly.rs:82-88
+    CompressedUniPoly c;
+    c.coeffs_except_linear_term.push_back(coeffs[0]);
+    for (size_t i = 2; i < coeffs.size(); i++) c.coeffs_except_linear_term.push_back(coeffs[i]);
+    return c;
+  }
+  void append_to_transcript(const char* label, Transcript& T) const {  // unipoly.rs:112-120
+    T.append_message(label, "UniPoly_begin");
+    for (auto& c : coeffs) T.append_scalar("coeff", c);
+    T.append_message(label, "UniPoly_end");
+  }
+};
+
+static KnowledgeProof knowledge_prove(const CommitKey& g, Transcript& T, RandomTape& tape, const Fq& x, const Fq& r, Cp& C_out) {  // nizk/mod.rs:27-52
+  T.append_protocol_name("knowledge proof");
+  Fq t1 = tape.random_scalar("t1"), t2 = tape.random_scalar("t2");
+  C_out = commit1(g, x, r);
+  T.append_point("C", C_out.b);
+  KnowledgeProof p;
+  p.alpha = commit1(g, t1, t2);
+  T.append_point("alpha", p.alpha.b);
+  Fq c = T.challenge_scalar("c");
+  p.z1 = x * c + t1;
+  p.z2 = r * c + t2;
+  return p;
+}
+static EqualityProof equality_prove(const CommitKey& g, Transcript& T, RandomTape& tape, const Fq& v1, const Fq& s1, const Fq& v2, const Fq& s2) {  // :88-116
+  T.append_protocol_name("equality proof");
+  Fq r = tape.random_scalar("r");
+  Cp C1 = commit1(g, v1, s1); T.append_point("C1", C1.b);
+  Cp C2 = commit1(g, v2, s2); T.append_point("C2", C2.b);
+  EqualityProof p;
+  Term t[1] = {{g.h, r}};
+  p.alpha = compress(host_commit(*g.set, t, 1));  // r * h
+  T.append_point("alpha", p.alpha.b);
+  Fq c = T.challenge_scalar("c");
+  p.z = c * (s1 - s2) + r;
+  return p;
+}
+static ProductProof product_prove(const CommitKey& g, Transcript& T, RandomTape& tape, const Fq& x, const Fq& rX, const Fq& y, const Fq& rY, const Fq& z,
+                                  const Fq& rZ, Cp& X, Cp& Y, Cp& Z) {  // nizk/mod.rs:159-229
+  T.append_protocol_name("product proof");
+  Fq b1 = tape.random_scalar("b1"), b2 = tape.random_scalar("b2"), b3 = tape.random_scalar("b3"), b4 = tape.random_scalar("b4"), b5 = tape.random_scalar("b5");
+  X = commit1(g, x, rX); T.append_point("X", X.b);
+  Y = commit1(g, y, rY); T.append_point("Y", Y.b);
+  Z = commit1(g, z, rZ); T.append_point("Z", Z.b);
+  ProductProof p;
+  p.alpha = commit1(g, b1, b2); T.append_point("alpha", p.alpha.b);
+  p.beta = commit1(g, b3, b4); T.append_point("beta", p.beta.b);
+  // delta = b3*X + b5*h with X = x*G + rX*h (nizk/mod.rs:199-206): same group element as (b3*x)*G + (b3*rX + b5)*h
+  p.delta = commit1(g, b3 * x, b3 * rX + b5);
+  T.append_point("delta", p.delta.b);
+  Fq c = T.challenge_scalar("c");
+  p.z = {b1 + c * x, b2 + c * rX, b3 + c * y, b4 + c * rY, b5 + c * (rZ - rX * y)};
+  return p;
+}
+// DotProductProof::prove (nizk/mod.rs:311-370); Cx is passed in when the caller already holds commit(x_vec; blind_x)
+static DotProductProof dotproduct_prove(const CommitKey& g1, const CommitKey& gn, Transcript& T, RandomTape& tape, const std::vector<Fq>& x_vec,
+                                        const Fq& blind_x, const std::vector<Fq>& a_vec, const Fq& y, const Fq& blind_y, const Cp* Cx_known) {
+  T.append_protocol_name("dot product proof");
+  size_t n = x_vec.size();
+  std::vector<Fq> d_vec = tape.random_vector("d_vec", n);
+  Fq r_delta = tape.random_scalar("r_delta"), r_beta = tape.random_scalar("r_beta");
+  Cp Cx = Cx_known ? *Cx_known : commitv(gn, x_vec, blind_x);
+  T.append_point("Cx", Cx.b);
+  Cp Cy = commit1(g1, y, blind_y);
+  T.append_point("Cy", Cy.b);
+  T.append_scalars("a", a_vec);
+  DotProductProof p;
+  p.delta = commitv(gn, d_vec, r_delta);
+  T.append_point("delta", p.delta.b);
+  Fq dot = Fq::zero();
+  for (size_t i = 0; i < n; i++) dot += a_vec[i] * d_vec[i];
+  p.beta = commit1(g1, dot, r_beta);
+  T.append_point("beta", p.beta.b);
+  Fq c = T.challenge_scalar("c");
+  p.z.resize(n);
+  for (size_t i = 0; i < n; i++) p.z[i] = c * x_vec[i] + d_vec[i];
+  p.z_delta = c * blind_x + r_delta;
+  p.z_beta = c * blind_y + r_beta;
+  return p;
+}
+
+std::vector<Fq> host_eq_evals(const std::vector<Fq>& r) {  // EqPolynomial::evals (dense_mlpoly.rs:68-84)
+  size_t ell = r.size();
+  std::vector<Fq> ev((size_t)1 << ell, Fq::one());
+  size_t size = 1;
+  for (size_t j = 0; j < ell; j++) {
+    size *= 2;
+    for (size_t i = size - 1;; i -= 2) {
+      Fq s = ev[i / 2];
+      ev[i] = s * r[j];
+      ev[i - 1] = s - ev[i];
+      if (i == 1) break;
+    }
+  }
+  return ev;
+}
+
+// ================================================================================================ ZK sumcheck on the device
+// prove_quad (sumcheck.rs:428-586) and prove_cubic_with_additive_term (sumcheck.rs:588-776).
+// tables: NT device arrays of length 2^num_rounds, folded in place (their first element holds the final evaluation).
+static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const Fq& blind_claim, size_t num_rounds, u256* const* tables, int nt,
+                              const CommitKey& g1, const CommitKey& gn, Transcript& T, RandomTape& tape, ZKSumcheckInstanceProof& proof,
+                              std::vector<Fq>& r, std::vector<Fq>& finals, Fq& blind_post) {
+  const int degree = kind == dev::SC_QUAD ? 2 : 3;
+  std::vector<Fq> blinds_poly = tape.random_vector("blinds_poly", num_rounds);
+  std::vector<Fq> blinds_evals = tape.random_vector("blinds_evals", num_rounds);
+  Fq claim_per_round = claim;
+  Cp comm_claim_per_round = commit1(g1, claim_per_round, blind_claim);
+  dev::ScInst inst;
+  for (int t = 0; t < 4; t++) inst.t[t] = t < nt ? tables[t] : nullptr;
+  inst.c_out = inst.t[2];
+  inst.write_c = 1;
+  u256* d_out = ctx.small.p + 0;     // 3 result scalars
+  u256* d_r = ctx.small.p + 8;       // round challenge
+  size_t len = (size_t)1 << num_rounds;
+  dev::sc_eval(kind, &inst, 1, len, d_out, ctx.scratch.p, ctx.stream);
+  for (size_t j = 0; j < num_rounds; j++) {
+    Fq e[3];
+    ctx.get_small(0, e, 3);
+    std::vector<Fq> evals = {e[0], claim_per_round - e[0], e[1]};
+    if (degree == 3) evals.push_back(e[2]);
+    UniPoly poly = UniPoly::from_evals(evals);
+    Cp comm_poly = commitv(gn, poly.coeffs, blinds_poly[j]);
+    T.append_point("comm_poly", comm_poly.b);
+    proof.comm_polys.push_back(comm_poly);
+    Fq r_j = T.challenge_scalar("challenge_nextround");
+    // bind the tables to r_j on the device right away (fused with the next round's evaluation); the host continues with the
+    // sigma protocol of this round while the kernel runs
+    ctx.put_small(8, &r_j, 1);
+    if (j + 1 < num_rounds) dev::sc_fold_eval(kind, &inst, 1, len, d_r, d_out, ctx.scratch.p, ctx.stream);
+    else dev::fold_top(tables, nt, len, d_r, ctx.stream);
+    len >>= 1;
+
+    Fq eval = poly.evaluate(r_j);
+    Cp comm_eval = commit1(g1, eval, blinds_evals[j]);
+    T.append_point("comm_claim_per_round", comm_claim_per_round.b);
+    T.append_point("comm_eval", comm_eval.b);
+    std::vector<Fq> w = T.challenge_vector("combine_two_claims_to_one", 2);
+    Fq target = w[0] * claim_per_round + w[1] * eval;
+    const Fq& blind_sc = j == 0 ? blind_claim : blinds_evals[j - 1];
+    Fq blind = w[0] * blind_sc + w[1] * blinds_evals[j];
+    // (the reference also recomputes comm_target from the two decompressed commitments and asserts equality, sumcheck.rs:531/:722;
+    //  it is a self-check with no effect on the transcript)
+    std::vector<Fq> a(degree + 1);
+    Fq rpow = Fq::one();
+    for (int i = 0; i <= degree; i++) {
+      Fq a_sc = i == 0 ? Fq::from_u64(2) : Fq::one();
+      a[i] = w[0] * a_sc + w[1] * rpow;
+      rpow *= r_j;
+    }
+    proof.proofs.push_back(dotproduct_prove(g1, gn, T, tape, poly.coeffs, blinds_poly[j], a, target, blind, &comm_poly));
+    claim_per_round = eval;
+    comm_claim_per_round = comm_eval;
+    r.push_back(r_j);
+    proof.comm_evals.push_back(comm_claim_per_round);
+  }
+  finals.resize(nt);
+  for (int t = 0; t < nt; t++) dev::d2h(ctx.pinned + 32 * t, tables[t], 32, ctx.stream);
+  ctx.sync();
+  memcpy(finals.data(), ctx.pinned, 32 * nt);
+  blind_post = blinds_evals[num_rounds - 1];
+}
+
+// ================================================================================================ polynomial commitment / evaluation proof
+Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalars, size_t stride, size_t L, size_t R, const Fq* blinds,
+                            std::vector<Cp>& out) {
+  // DensePolynomial::commit_inner (dense_mlpoly.rs:148-177): C_i = (MSM(Z[iR..(i+1)R], G) + blinds[i]*h).compress()
+  if (key.off != 0 || R > key.n) throw std::runtime_error("spartan_b200: commit_rows key mismatch");
+  ctx.ensure_scratch(dev::msm_scratch_bytes(L, R) + 64);
+  DevBuf<ge> rows(L);
+  DevBuf<u256> d_bl;
+  if (blinds) { d_bl.alloc(L); dev::h2d(d_bl.p, blinds, L * sizeof(u256), ctx.stream); }
+  dev::msm_rows(rows.p, key.set->table.p, d_scalars, stride, L, R, blinds ? d_bl.p : nullptr, key.h, ctx.scratch.p, ctx.stream);
+  DevBuf<uint8_t> comp(32 * L);
+  dev::compress_batch(comp.p, rows.p, L, ctx.stream);
+  out.resize(L);
+  dev::d2h(out.data(), comp.p, 32 * L, ctx.stream);
+  ctx.sync();
+  return out.empty() ? Cp() : out[0];
+}
+
+static void append_poly_commitment(Transcript& T, const char* label, const PolyCommitment& c) {  // dense_mlpoly.rs:292-300
+  T.append_message(label, "poly_commitment_begin");
+  for (auto& p : c.C) T.append_point("poly_commitment_share", p.b);
+  T.append_message(label, "poly_commitment_end");
+}
+
+// BulletReductionProof::prove (nizk/bullet.rs:32-132) with Q = r*G1 and H = h folded into host fixed-base terms, and the
+// generator vector left unfolded (see k_ipa_lr in kernels.cu).  d_a / d_b are consumed (folded in place).
+static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens, const Fq& r_scale, u256* d_a, u256* d_b, size_t n, const Fq& blind,
+                         const std::vector<std::pair<Fq, Fq>>& blinds_vec, BulletReductionProof& proof, Fq& a_hat, Fq& b_hat, ge& g_hat, Fq& blind_final) {
+  const GenSet& gs = *gens.gens_n.set;
+  DevBuf<u256> svec(n), lr(2 * n);
+  DevBuf<ge> pts(2);
+  dev::fill_one(svec.p, n, ctx.stream);
+  ctx.ensure_scratch(dev::msm_scratch_bytes(2, n) + 64);
+  u256* d_c = ctx.small.p + 16;  // c_L, c_R
+  u256* d_u = ctx.small.p + 24;  // u, u^-1
+  blind_final = blind;
+  size_t cur = n, k = 0;
+  while (cur != 1) {
+    size_t half = cur / 2;
+    dev::dot(d_c, d_a, d_b + half, half, ctx.scratch.p, ctx.stream);          // c_L = <a_L, b_R>   bullet.rs:78
+    dev::dot(d_c + 1, d_a + half, d_b, half, ctx.scratch.p, ctx.stream);      // c_R = <a_R, b_L>   bullet.rs:79
+    dev::ipa_lr_scalars(lr.p, lr.p + n, d_a, svec.p, cur, n, ctx.stream);
+    dev::msm_rows(pts.p, gs.table.p, lr.p, n, 2, n, nullptr, 0, ctx.scratch.p, ctx.stream);
+    dev::d2h(ctx.pinned, d_c, 64, ctx.stream);
+    dev::d2h(ctx.pinned + 64, pts.p, 2 * sizeof(ge), ctx.stream);
+    ctx.sync();
+    Fq c_L, c_R;
+    memcpy(&c_L, ctx.pinned, 32); memcpy(&c_R, ctx.pinned + 32, 32);
+    ge Lg, Rg;
+    memcpy(&Lg, ctx.pinned + 64, sizeof(ge)); memcpy(&Rg, ctx.pinned + 64 + sizeof(ge), sizeof(ge));
+    const Fq& blind_L = blinds_vec[k].first;
+    const Fq& blind_R = blinds_vec[k].second;
+    // + c_L*Q + blind_L*H with Q = r*G1 (nizk/mod.rs:479-480), H = gens_n.h   (bullet.rs:83-97)
+    Term tl[2] = {{gens.gens_1.off, c_L * r_scale}, {gens.gens_n.h, blind_L}};
+    Term tr[2] = {{gens.gens_1.off, c_R * r_scale}, {gens.gens_n.h, blind_R}};
+    Cp Lc = compress(ge_add(Lg, host_commit(gs, tl, 2)));
+    Cp Rc = compress(ge_add(Rg, host_commit(gs, tr, 2)));
+    T.append_point("L", Lc.b);
+    T.append_point("R", Rc.b);
+    Fq u = T.challenge_scalar("u");
+    Fq u_inv = u.inv();
+    Fq uu[2] = {u, u_inv};
+    ctx.put_small(24, uu, 2);
+    dev::ipa_fold_ab(d_a, d_b, half, d_u, ctx.stream);
+    dev::ipa_update_s(svec.p, half, n, d_u, ctx.stream);
+    blind_final = blind_final + blind_L * u * u + blind_R * u_inv * u_inv;  // bullet.rs:111
+    proof.L_vec.push_back(Lc);
+    proof.R_vec.push_back(Rc);
+    cur = half;
+    k++;
+  }
+  // g_hat = G_final[0] = <s, G>
+  dev::msm_rows(pts.p, gs.table.p, svec.p, n, 1, n, nullptr, 0, ctx.scratch.p, ctx.stream);
+  dev::d2h(ctx.pinned, d_a, 32, ctx.stream);
+  dev::d2h(ctx.pinned + 32, d_b, 32, ctx.stream);
+  dev::d2h(ctx.pinned + 64, pts.p, sizeof(ge), ctx.stream);
+  ctx.sync();
+  memcpy(&a_hat, ctx.pinned, 32); memcpy(&b_hat, ctx.pinned + 32, 32); memcpy(&g_hat, ctx.pinned + 64, sizeof(ge));
+}
+
+// DotProductProofLog::prove (nizk/mod.rs:440-525).  d_x: device x_vec (n, consumed); a_vec on the host (it is absorbed by the transcript).
+static void dotproduct_log_prove(Ctx& ctx, const PolyCommitmentGens& gens, Transcript& T, RandomTape& tape, u256* d_x, const Fq& blind_x,
+                                 const std::vector<Fq>& a_vec, const Fq& y, const Fq& blind_y, DotProductProofLog& proof, Cp& Cy_out) {
+  T.append_protocol_name("dot product proof (log)");
+  size_t n = a_vec.size();
+  if (gens.n != n) throw std::runtime_error("spartan_b200: DotProductProofLog size mismatch");
+  const GenSet& gs = *gens.gens_n.set;
+  Fq d = tape.random_scalar("d");
+  Fq r_delta = tape.random_scalar("r_delta");
+  Fq r_beta = tape.random_scalar("r_delta");  // sic: the reference reuses the label (nizk/mod.rs:459)
+  size_t lg_n = 0;
+  while (((size_t)1 << lg_n) < n) lg_n++;
+  std::vector<Fq> v1 = tape.random_vector("blinds_vec_1", lg_n), v2 = tape.random_vector("blinds_vec_2", lg_n);
+  std::vector<std::pair<Fq, Fq>> blinds_vec;
+  for (size_t i = 0; i < lg_n; i++) blinds_vec.push_back({v1[i], v2[i]});
+  std::vector<Cp> cx;
+  commit_rows_and_compress(ctx, gens.gens_n, d_x, n, 1, n, &blind_x, cx);
+  T.append_point("Cx", cx[0].b);
+  Cy_out = commit1(gens.gens_1, y, blind_y);
+  T.append_point("Cy", Cy_out.b);
+  T.append_scalars("a", a_vec);
+  Fq r = T.challenge_scalar("r");
+  Fq blind_Gamma = blind_x + r * blind_y;
+  DevBuf<u256> d_b(n);
+  dev::h2d(d_b.p, a_vec.data(), n * sizeof(u256), ctx.stream);
+  Fq x_hat, a_hat, rhat_Gamma;
+  ge g_hat;
+  bullet_prove(ctx, T, gens, r, d_x, d_b.p, n, blind_Gamma, blinds_vec, proof.bullet_reduction_proof, x_hat, a_hat, g_hat, rhat_Gamma);
+  Fq y_hat = x_hat * a_hat;
+  // delta = d*g_hat + r_delta*h (gens_hat, nizk/mod.rs:497-505)
+  Term th[1] = {{gens.gens_1.h, r_delta}};
+  proof.delta = compress(ge_add(ge_scalarmul(d.canonical(), g_hat), host_commit(gs, th, 1)));
+  T.append_point("delta", proof.delta.b);
+  // beta = d*(r*G1) + r_beta*h (gens_1_scaled, nizk/mod.rs:507)
+  proof.beta = commit1(gens.gens_1, d * r, r_beta);
+  T.append_point("beta", proof.beta.b);
+  Fq c = T.challenge_scalar("c");
+  proof.z1 = d + c * y_hat;
+  proof.z2 = a_hat * (c * rhat_Gamma + r_beta) + r_delta;
+}
+
+// PolyEvalProof::prove (dense_mlpoly.rs:312-365).  d_Z: device table of 2^|r| scalars (read-only).
+static void polyeval_prove(Ctx& ctx, const u256* d_Z, const std::vector<Fq>* blinds_opt, const std::vector<Fq>& r, const Fq& Zr, const Fq* blind_Zr_opt,
+                           const PolyCommitmentGens& gens, Transcript& T, RandomTape& tape, PolyEvalProof& proof, Cp& C_Zr) {
+  T.append_protocol_name("polynomial evaluation proof");
+  size_t ell = r.size(), lv = ell / 2;
+  size_t L_size = (size_t)1 << lv, R_size = (size_t)1 << (ell - lv);
+  std::vector<Fq> Lr(r.begin(), r.begin() + lv), Rr(r.begin() + lv, r.end());
+  std::vector<Fq> Lev = host_eq_evals(Lr), Rev = host_eq_evals(Rr);  // compute_factored_evals (dense_mlpoly.rs:90-98)
+  Fq LZ_blind = Fq::zero();
+  if (blinds_opt) for (size_t i = 0; i < L_size; i++) LZ_blind += (*blinds_opt)[i] * Lev[i];
+  Fq blind_Zr = blind_Zr_opt ? *blind_Zr_opt : Fq::zero();
+  DevBuf<u256> d_L(L_size), d_LZ(R_size), tmp(64 * R_size);
+  dev::h2d(d_L.p, Lev.data(), L_size * sizeof(u256), ctx.stream);
+  dev::bound_rows(d_LZ.p, d_Z, d_L.p, L_size, R_size, tmp.p, ctx.stream);  // DensePolynomial::bound (dense_mlpoly.rs:206-213)
+  dotproduct_log_prove(ctx, gens, T, tape, d_LZ.p, LZ_blind, Rev, Zr, blind_Zr, proof.proof, C_Zr);
+}
+
+// ================================================================================================ instance
+static void build_compressed(size_t nmajor, const std::vector<uint32_t>& major, const std::vector<uint32_t>& minor, const std::vector<Fq>& val,
+                             std::vector<uint32_t>& ptr, std::vector<uint32_t>& idx, std::vector<Fq>& v) {
+  size_t nnz = major.size();
+  ptr.assign(nmajor + 1, 0);
+  for (size_t k = 0; k < nnz; k++) ptr[major[k] + 1]++;
+  for (size_t i = 0; i < nmajor; i++) ptr[i + 1] += ptr[i];
+  std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);
+  idx.resize(nnz); v.resize(nnz);
+  for (size_t k = 0; k < nnz; k++) { uint32_t p = fill[major[k]]++; idx[p] = minor[k]; v[p] = val[k]; }
+}
+template <class T>
+static void up(Ctx* ctx, DevBuf<T>& d, const std::vector<T>& h) { d.alloc(h.size()); dev::h2d(d.p, h.data(), h.size() * sizeof(T), ctx->stream); }
+static void up(Ctx* ctx, DevBuf<u256>& d, const std::vector<Fq>& h) { d.alloc(h.size()); dev::h2d(d.p, h.data(), h.size() * sizeof(u256), ctx->stream); }
+
+void Instance::finalize(Ctx* ctx) {
+  size_t ncols = 2 * num_vars;
+  for (int m = 0; m < 3; m++) {
+    SparseMatDev& M_ = M[m];
+    std::vector<uint32_t> ptr, idx;
+    std::vector<Fq> v;
+    build_compressed(num_cons, M_.row, M_.col, M_.val, ptr, idx, v);
+    up(ctx, M_.csr_ptr, ptr); up(ctx, M_.csr_idx, idx); up(ctx, M_.csr_val, v);
+    build_compressed(ncols, M_.col, M_.row, M_.val, ptr, idx, v);
+    up(ctx, M_.csc_ptr, ptr); up(ctx, M_.csc_idx, idx); up(ctx, M_.csc_val, v);
+    up(ctx, M_.coo_row, M_.row); up(ctx, M_.coo_col, M_.col); up(ctx, M_.coo_val, M_.val);
+    ctx->sync();
+  }
+}
+
+// ================================================================================================ R1CSProof::prove
+struct PhaseTimer {
+  Ctx& ctx; const char* name; std::chrono::steady_clock::time_point t0;
+  PhaseTimer(Ctx& c, const char* n) : ctx(c), name(n), t0(std::chrono::steady_clock::now()) {}
+  ~PhaseTimer() { ctx.timings.push_back({name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()}); }
+};
+
+void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T,
+                RandomTape& tape, R1CSProof& proof, std::vector<Fq>& rx, std::vector<Fq>& ry) {
+  PhaseTimer t_all(ctx, "R1CSProof::prove");
+  T.append_protocol_name("R1CS proof");
+  const size_t num_vars = inst.num_vars, num_cons = inst.num_cons;
+  if (!(input.size() < num_vars)) throw std::runtime_error("spartan_b200: |input| + 1 must be at most the number of variables");  // r1csproof.rs:156
+  T.append_scalars("input", input);
+
+  size_t ell = 0;
+  while (((size_t)1 << ell) < num_vars) ell++;
+  const size_t L_size = (size_t)1 << (ell / 2), R_size = (size_t)1 << (ell - ell / 2);
+  std::vector<Fq> blinds_vars;
+  {
+    PhaseTimer t(ctx, "polycommit");
+    blinds_vars = tape.random_vector("poly_blinds", L_size);  // dense_mlpoly.rs:193-196
+    commit_rows_and_compress(ctx, gens.gens_pc.gens_n, d_vars, R_size, L_size, R_size, blinds_vars.data(), proof.comm_vars.C);
+    append_poly_commitment(T, "poly_commitment", proof.comm_vars);
+  }
+
+  // z = vars || 1 || input || 0...                                          (r1csproof.rs:177-185)
+  const size_t zlen = 2 * num_vars;
+  DevBuf<u256> d_z(zlen);
+  size_t num_rounds_x = 0, num_rounds_y = 0;
+  while (((size_t)1 << num_rounds_x) < num_cons) num_rounds_x++;
+  while (((size_t)1 << num_rounds_y) < zlen) num_rounds_y++;
+  DevBuf<u256> d_tau(num_cons), d_Az(num_cons), d_Bz(num_cons), d_Cz(num_cons), d_chal(64), eq_small(2 * ((size_t)1 << ((std::max(num_rounds_x, num_rounds_y) + 1) / 2)) + 8);
+  Fq blind_claim_postsc1;
+  std::vector<Fq> claims1;
+  {
+    PhaseTimer t(ctx, "prove_sc_phase_one");
+    dev::d2d(d_z.p, d_vars, num_vars * sizeof(u256), ctx.stream);
+    std::vector<Fq> tail(1 + input.size());
+    tail[0] = Fq::one();
+    for (size_t i = 0; i < input.size(); i++) tail[1 + i] = input[i];
+    dev::h2d(d_z.p + num_vars, tail.data(), tail.size() * sizeof(u256), ctx.stream);
+    dev::dzero(d_z.p + num_vars + tail.size(), (num_vars - tail.size()) * sizeof(u256), ctx.stream);
+    std::vector<Fq> tau = T.challenge_vector("challenge_tau", num_rounds_x);
+    dev::h2d(d_chal.p, tau.data(), tau.size() * sizeof(u256), ctx.stream);
+    dev::eq_evals(d_tau.p, d_chal.p, (int)num_rounds_x, eq_small.p, ctx.stream);
+    // inst.multiply_vec (r1cs.rs:268-282)
+    u256* outs[3] = {d_Az.p, d_Bz.p, d_Cz.p};
+    for (int m = 0; m < 3; m++) dev::spmv(outs[m], num_cons, inst.M[m].csr_ptr.p, inst.M[m].csr_idx.p, inst.M[m].csr_val.p, d_z.p, ctx.stream);
+    u256* tabs[4] = {d_tau.p, d_Az.p, d_Bz.p, d_Cz.p};
+    zk_sumcheck_prove(ctx, dev::SC_CUBIC4, Fq::zero(), Fq::zero(), num_rounds_x, tabs, 4, gens.gens_1, gens.gens_4, T, tape, proof.sc_proof_phase1, rx, claims1,
+                      blind_claim_postsc1);
+  }
+  const Fq tau_claim = claims1[0], Az_claim = claims1[1], Bz_claim = claims1[2], Cz_claim = claims1[3];
+  Fq Az_blind = tape.random_scalar("Az_blind"), Bz_blind = tape.random_scalar("Bz_blind"), Cz_blind = tape.random_scalar("Cz_blind"),
+     prod_Az_Bz_blind = tape.random_scalar("prod_Az_Bz_blind");
+  Cp comm_Cz_claim, comm_Az_claim, comm_Bz_claim, comm_prod;
+  proof.pok_Cz = knowledge_prove(gens.gens_1, T, tape, Cz_claim, Cz_blind, comm_Cz_claim);
+  Fq prod = Az_claim * Bz_claim;
+  proof.proof_prod = product_prove(gens.gens_1, T, tape, Az_claim, Az_blind, Bz_claim, Bz_blind, prod, prod_Az_Bz_blind, comm_Az_claim, comm_Bz_claim, comm_prod);
+  T.append_point("comm_Az_claim", comm_Az_claim.b);
+  T.append_point("comm_Bz_claim", comm_Bz_claim.b);
+  T.append_point("comm_Cz_claim", comm_Cz_claim.b);
+  T.append_point("comm_prod_Az_Bz_claims", comm_prod.b);
+  proof.claims_phase2 = {comm_Az_claim, comm_Bz_claim, comm_Cz_claim, comm_prod};
+  Fq blind_expected_claim_postsc1 = tau_claim * (prod_Az_Bz_blind - Cz_blind);
+  Fq claim_post_phase1 = (Az_claim * Bz_claim - Cz_claim) * tau_claim;
+  proof.proof_eq_sc_phase1 = equality_prove(gens.gens_1, T, tape, claim_post_phase1, blind_expected_claim_postsc1, claim_post_phase1, blind_claim_postsc1);
+
+  Fq blind_claim_postsc2;
+  std::vector<Fq> claims2;
+  {
+    PhaseTimer t(ctx, "prove_sc_phase_two");
+    Fq rabc[3] = {T.challenge_scalar("challenge_Az"), T.challenge_scalar("challenge_Bz"), T.challenge_scalar("challenge_Cz")};
+    Fq claim_phase2 = rabc[0] * Az_claim + rabc[1] * Bz_claim + rabc[2] * Cz_claim;
+    Fq blind_claim_phase2 = rabc[0] * Az_blind + rabc[1] * Bz_blind + rabc[2] * Cz_blind;
+    // evals_rx = eq(rx, .), then the three transposed SpMVs of compute_eval_table_sparse (r1cs.rs:284-298), then r_A*A + r_B*B + r_C*C
+    dev::h2d(d_chal.p, rx.data(), rx.size() * sizeof(u256), ctx.stream);
+    dev::eq_evals(d_tau.p, d_chal.p, (int)num_rounds_x, eq_small.p, ctx.stream);
+    DevBuf<u256> eA(zlen), eB(zlen), eC(zlen), d_ABC(zlen);
+    u256* outs[3] = {eA.p, eB.p, eC.p};
+    for (int m = 0; m < 3; m++) dev::spmv(outs[m], zlen, inst.M[m].csc_ptr.p, inst.M[m].csc_idx.p, inst.M[m].csc_val.p, d_tau.p, ctx.stream);
+    dev::h2d(d_chal.p + 32, rabc, 3 * sizeof(u256), ctx.stream);
+    dev::lincomb3(d_ABC.p, eA.p, eB.p, eC.p, d_chal.p + 32, zlen, ctx.stream);
+    u256* tabs[2] = {d_z.p, d_ABC.p};
+    zk_sumcheck_prove(ctx, dev::SC_QUAD, claim_phase2, blind_claim_phase2, num_rounds_y, tabs, 2, gens.gens_1, gens.gens_3, T, tape, proof.sc_proof_phase2, ry, claims2,
+                      blind_claim_postsc2);
+  }
+  {
+    PhaseTimer t(ctx, "polyeval");
+    // eval_vars_at_ry = poly_vars.evaluate(ry[1..]) (dense_mlpoly.rs:236-242)
+    std::vector<Fq> ry1(ry.begin() + 1, ry.end());
+    DevBuf<u256> d_eq(num_vars);
+    dev::h2d(d_chal.p, ry1.data(), ry1.size() * sizeof(u256), ctx.stream);
+    dev::eq_evals(d_eq.p, d_chal.p, (int)ry1.size(), eq_small.p, ctx.stream);
+    dev::dot(ctx.small.p + 32, d_vars, d_eq.p, num_vars, ctx.scratch.p, ctx.stream);
+    Fq eval_vars_at_ry;
+    ctx.get_small(32, &eval_vars_at_ry, 1);
+    Fq blind_eval = tape.random_scalar("blind_eval");
+    polyeval_prove(ctx, d_vars, &blinds_vars, ry1, eval_vars_at_ry, &blind_eval, gens.gens_pc, T, tape, proof.proof_eval_vars_at_ry, proof.comm_vars_at_ry);
+    Fq blind_eval_Z_at_ry = (Fq::one() - ry[0]) * blind_eval;
+    Fq blind_expected_claim_postsc2 = claims2[1] * blind_eval_Z_at_ry;
+    Fq claim_post_phase2 = claims2[0] * claims2[1];
+    proof.proof_eq_sc_phase2 = equality_prove(gens.gens_pc.gens_1, T, tape, claim_post_phase2, blind_expected_claim_postsc2, claim_post_phase2, blind_claim_postsc2);
+  }
+}
+
+void nizk_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T, const Fq& tape_seed,
+                NizkProof& out) {
+  ctx.timings.clear();
+  PhaseTimer t(ctx, "NIZK::prove");
+  RandomTape tape("proof", tape_seed);                                   // lib.rs:511
+  T.append_protocol_name("Spartan NIZK proof");                          // lib.rs:513
+  T.append_message("R1CSShapeDigest", inst.digest.data(), inst.digest.size());  // lib.rs:514
+  r1cs_prove(ctx, inst, d_vars, input, gens, T, tape, out.r1cs_sat_proof, out.rx, out.ry);
+}
+
+}  // namespace sp

@@ -1,0 +1,161 @@
+"""GPU parity (prover level): proof bytes of the B200 prover diffed against the oracle's restatement of NIZK::prove on identical
+synthetic instances, transcript labels and RandomTape seeds (BASELINE.json configs[0]), plus oracle-verifier acceptance at sizes the
+oracle prover is too slow for.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.spartan_ref import core as oc  # noqa: E402
+from oracle.spartan_ref import protocol as pr  # noqa: E402
+from oracle.spartan_ref import r1cs  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import spartan_b200 as m
+    m.default_context()
+    return m
+
+
+def oracle_nizk(num_cons, num_vars, num_inputs, seed, label=b"example"):
+    inst, vars_arr, inputs = r1cs.Instance.produce_synthetic_r1cs(num_cons, num_vars, num_inputs, seed)
+    gens = r1cs.NIZKGens(num_cons, num_vars, num_inputs)
+    proof = r1cs.NIZK.prove(inst, vars_arr, inputs, gens, oc.Transcript(label), r1cs.tape_seed(seed))
+    return inst, vars_arr, inputs, gens, proof
+
+
+@pytest.mark.parametrize("num_cons,num_vars,num_inputs", [(1024, 1024, 10), (16, 16, 3), (64, 256, 7), (512, 32, 5), (2, 2, 1), (4096, 2048, 10)])
+def test_synthetic_instance_matches_oracle(sb, num_cons, num_vars, num_inputs):
+    """Instance::produce_synthetic_r1cs (r1cs.rs:160-238) with the seeded generator: same COO triples, witness, digest input"""
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(num_cons, num_vars, num_inputs, seed=3)
+    oi, ovars, oinputs = r1cs.Instance.produce_synthetic_r1cs(num_cons, num_vars, num_inputs, 3)
+    assert np.array_equal(vars_.limbs, ovars)
+    assert oc.to_ints(inputs.limbs) == oinputs
+    for m, M in enumerate((oi.inst.A, oi.inst.B, oi.inst.C)):
+        row, col, val = inst.export(m)
+        assert np.array_equal(row, M.row) and np.array_equal(col, M.col) and np.array_equal(val, M.val)
+    assert inst.digest == oi.digest
+    assert inst.is_sat(vars_, inputs)
+    bad = sb.Assignment(vars_.limbs.copy())
+    bad.limbs[0] = oc.to_arr([12345])[0]
+    assert not inst.is_sat(bad, inputs)
+
+
+@pytest.mark.parametrize("num_cons,num_vars,num_inputs,seed", [(1024, 1024, 10, 0), (16, 16, 3, 1), (64, 256, 7, 2), (512, 32, 5, 3), (2, 2, 1, 4),
+                                                               (4096, 2048, 10, 5), (8192, 8192, 10, 6)])
+def test_nizk_proof_bytes_match_oracle(sb, num_cons, num_vars, num_inputs, seed):
+    """BASELINE.json configs[0] (1024/1024/10) and ragged shapes: bincode(NIZK) identical to the oracle's"""
+    oi, ovars, oinputs, ogens, oproof = oracle_nizk(num_cons, num_vars, num_inputs, seed)
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(num_cons, num_vars, num_inputs, seed=seed)
+    inst.set_digest(oi.digest)
+    gens = sb.NIZKGens(num_cons, num_vars, num_inputs)
+    proof = sb.NIZK.prove(inst, vars_, inputs, gens, b"example", sb.tape_seed(seed))
+    want = oproof.ser()
+    assert len(proof.bytes) == len(want)
+    if (num_cons, num_vars, num_inputs) == (1024, 1024, 10):
+        assert len(want) == 9408 and len(pr.ser(oproof.r1cs_sat_proof)) == 8720
+    assert proof.bytes == want
+    # resident-assignment entry point gives the same bytes
+    proof2 = sb.NIZK.prove(inst, sb.DensePolynomial(vars_.limbs), inputs, gens, b"example", sb.tape_seed(seed))
+    assert proof2.bytes == want
+    # a different tape seed or transcript label changes the proof
+    assert sb.NIZK.prove(inst, vars_, inputs, gens, b"example", sb.tape_seed(seed + 1)).bytes != want
+    assert sb.NIZK.prove(inst, vars_, inputs, gens, b"other", sb.tape_seed(seed)).bytes != want
+
+
+def test_nizk_user_instance_with_padding(sb):
+    """Instance::new padding rules (lib.rs:129-198): num_cons = 1, num_vars = 0 edge case of lib.rs:672-752 style, and a 3-constraint
+    instance (examples/cubic.rs shape: x^3 + x + 5 = y) proven and accepted by the oracle verifier, bytes equal to the oracle prover"""
+    one = (1).to_bytes(32, "little")
+    five = (5).to_bytes(32, "little")
+    # Z0*Z0 = Z1 ; Z1*Z0 = Z2 ; (Z2+Z0)*1 = Z3 ; (Z3+5)*1 = I0      (vars Z0..Z3, one input)
+    num_cons, num_vars, num_inputs = 4, 4, 1
+    A = [(0, 0, one), (1, 1, one), (2, 2, one), (2, 0, one), (3, 3, one), (3, num_vars, five)]
+    B = [(0, 0, one), (1, 0, one), (2, num_vars, one), (3, num_vars, one)]
+    Cm = [(0, 1, one), (1, 2, one), (2, 3, one), (3, num_vars + 1, one)]
+    x = 3
+    zs = [x, x * x, x * x * x, x * x * x + x]
+    y = zs[3] + 5
+    vars_ = sb.Assignment([v.to_bytes(32, "little") for v in zs])
+    inputs = sb.Assignment([y.to_bytes(32, "little")])
+    inst = sb.Instance.new(num_cons, num_vars, num_inputs, A, B, Cm)
+    assert inst.is_sat(vars_, inputs)
+    oi = r1cs.Instance.new(num_cons, num_vars, num_inputs, A, B, Cm)
+    assert inst.bincode() and inst.digest == oi.digest
+    gens = sb.NIZKGens(num_cons, num_vars, num_inputs)
+    proof = sb.NIZK.prove(inst, vars_, inputs, gens, b"nizk_example", sb.tape_seed(9))
+    ogens = r1cs.NIZKGens(num_cons, num_vars, num_inputs)
+    ovars = r1cs.assignment_from_bytes([v.to_bytes(32, "little") for v in zs])
+    oproof = r1cs.NIZK.prove(oi, ovars, [y], ogens, oc.Transcript(b"nizk_example"), r1cs.tape_seed(9))
+    assert proof.bytes == oproof.ser()
+    oproof.verify(oi, [y], oc.Transcript(b"nizk_example"), ogens)
+    # error behaviour of Instance::new (lib.rs:627-670)
+    with pytest.raises(sb.R1CSError):
+        sb.Instance.new(num_cons, num_vars, num_inputs, [(num_cons, 0, one)], B, Cm)
+    with pytest.raises(sb.R1CSError):
+        sb.Instance.new(num_cons, num_vars, num_inputs, [(0, num_vars + num_inputs + 1, one)], B, Cm)
+    with pytest.raises(sb.R1CSError):
+        sb.Instance.new(num_cons, num_vars, num_inputs, [(0, 0, b"\xff" * 32)], B, Cm)
+    with pytest.raises(sb.R1CSError):
+        sb.Assignment([b"\xff" * 32])
+
+
+@pytest.mark.parametrize("logn", [16, 20])
+def test_nizk_large_accepted_by_oracle_verifier(sb, logn):
+    """full-size run (2^20 = the size of the reference's published profile, README.md:394-413): the oracle's NIZK::verify accepts the
+    GPU proof; the sat-proof length is the reference's published 47,024 bytes at 2^20 (README.md:411)"""
+    import dataclasses
+    n = 1 << logn
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(n, n, 10, seed=1)
+    gens = sb.NIZKGens(n, n, 10)
+    proof = sb.NIZK.prove(inst, vars_, inputs, gens, b"example", sb.tape_seed(1))
+    if logn == 20:
+        assert len(proof.bytes) == 47024 + (8 + 20 * 32) + (8 + 21 * 32)
+    oi, ovars, oinputs = r1cs.Instance.produce_synthetic_r1cs(n, n, 10, 1)
+    oi.digest = inst.digest
+    ogens = r1cs.NIZKGens(n, n, 10)
+    parsed = parse_nizk(proof.bytes, logn, logn + 1)
+    parsed.verify(oi, oinputs, oc.Transcript(b"example"), ogens)
+
+
+def parse_nizk(b, rounds_x, rounds_y):
+    """inverse of bincode(NIZK) for the oracle verifier (layout: SURVEY Appendix B)"""
+    pos = [0]
+
+    def take(n):
+        v = b[pos[0]:pos[0] + n]
+        pos[0] += n
+        return v
+
+    def u64():
+        return int.from_bytes(take(8), "little")
+
+    def sc():
+        return oc.from_mont_bytes(take(32))
+
+    def pt():
+        return take(32)
+
+    def vec(f):
+        return [f() for _ in range(u64())]
+
+    def dpp():
+        return pr.DotProductProof(pt(), pt(), vec(sc), sc(), sc())
+
+    def zk():
+        return pr.ZKSumcheckInstanceProof(vec(pt), vec(pt), vec(dpp))
+    comm_vars = pr.PolyCommitment(vec(pt))
+    sc1 = zk()
+    claims = (pt(), pt(), pt(), pt())
+    pok = pr.KnowledgeProof(pt(), sc(), sc())
+    prod = pr.ProductProof(pt(), pt(), pt(), (sc(), sc(), sc(), sc(), sc()))
+    eq1 = pr.EqualityProof(pt(), sc())
+    sc2 = zk()
+    comm_at_ry = pt()
+    brp = pr.BulletReductionProof(vec(pt), vec(pt))
+    pe = pr.PolyEvalProof(pr.DotProductProofLog(brp, pt(), pt(), sc(), sc()))
+    eq2 = pr.EqualityProof(pt(), sc())
+    rx, ry = vec(sc), vec(sc)
+    assert pos[0] == len(b) and len(rx) == rounds_x and len(ry) == rounds_y
+    return r1cs.NIZK(pr.R1CSProof(comm_vars, sc1, claims, (pok, prod), eq1, sc2, comm_at_ry, pe, eq2), (rx, ry))
