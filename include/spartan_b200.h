@@ -47,6 +47,15 @@ const char* sp_last_error(const sp_ctx* ctx);  /* ctx may be NULL: message of th
 unsigned long long sp_kernel_launches(void);   /* kernels launched by this library since load */
 /* phase timings of the last prove call, the labels of the reference's `profile` feature (src/timer.rs; src/r1csproof.rs:152-298) */
 int sp_timings(sp_ctx* ctx, char* buf, size_t buflen);
+/* bytes moved host->device / device->host by this library since load (bench.py e2e leg) */
+void sp_io_bytes(unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
+/* CUDA-event timing of every kernel family on the launching stream (bench.py roofline leg).  sp_prof_enable(1) clears and starts;
+ * sp_prof_report writes "name:launches:total_ms:total_algorithmic_bytes;..." after synchronising the device */
+void sp_prof_enable(int on);
+int sp_prof_report(char* buf, size_t buflen);
+/* device-side stopwatch on the context's stream (CUDA events) */
+int sp_timer_start(sp_ctx* ctx);
+int sp_timer_stop_ms(sp_ctx* ctx, float* ms);
 
 /* ---- scalar field helpers (host side, for harnesses) */
 int sp_scalar_from_bytes(const uint8_t canonical[32], uint64_t out_mont[4]);        /* Scalar::from_bytes       ristretto255.rs:391 */

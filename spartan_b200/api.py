@@ -479,3 +479,38 @@ class SNARK:
             ctx.check(lib.sp_snark_prove(ctx.h, inst.h, comm.h, _p(vars.limbs), _sz(len(vars)), _p(inputs.limbs), _sz(len(inputs)), gens.h,
                                          C.c_char_p(transcript_label), _sz(len(transcript_label)), _p(seed), C.byref(out), C.byref(n)))
         return SNARK(_take_bytes(out, n))
+
+
+# ----------------------------------------------------------------------------- measurement helpers (bench.py)
+def io_bytes():
+    a, b = C.c_ulonglong(), C.c_ulonglong()
+    lib.sp_io_bytes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def prof_enable(on=True):
+    lib.sp_prof_enable(C.c_int(1 if on else 0))
+
+
+def prof_report():
+    """{kernel family: {"launches", "ms", "bytes"}} measured with CUDA events on the launching stream"""
+    buf = C.create_string_buffer(1 << 16)
+    lib.sp_prof_report(buf, _sz(1 << 16))
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            name, n, ms, by = item.split(":")
+            out[name] = {"launches": int(n), "ms": float(ms), "bytes": float(by)}
+    return out
+
+
+def timer_start(ctx=None):
+    ctx = ctx or default_context()
+    ctx.check(lib.sp_timer_start(ctx.h))
+
+
+def timer_stop_ms(ctx=None):
+    ctx = ctx or default_context()
+    ms = C.c_float()
+    ctx.check(lib.sp_timer_stop_ms(ctx.h, C.byref(ms)))
+    return float(ms.value)

@@ -56,6 +56,28 @@ int sp_timings(sp_ctx* ctx, char* buf, size_t buflen) {
   return SP_OK;
 }
 
+void sp_io_bytes(unsigned long long* h, unsigned long long* d) { dev::io_bytes(h, d); }
+void sp_prof_enable(int on) { dev::prof_enable(on != 0); }
+int sp_prof_report(char* buf, size_t buflen) {
+  std::string s = dev::prof_report();
+  if (s.size() + 1 > buflen) return SP_ERR_INVALID_ARG;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return SP_OK;
+}
+static void* g_ev_a = nullptr; static void* g_ev_b = nullptr;
+int sp_timer_start(sp_ctx* ctx) {
+  SP_TRY(ctx)
+  if (!g_ev_a) { g_ev_a = dev::event_create(); g_ev_b = dev::event_create(); }
+  dev::event_record(g_ev_a, ctx->c.stream);
+  SP_CATCH(ctx)
+}
+int sp_timer_stop_ms(sp_ctx* ctx, float* ms) {
+  SP_TRY(ctx)
+  dev::event_record(g_ev_b, ctx->c.stream);
+  *ms = dev::event_elapsed_ms(g_ev_a, g_ev_b);
+  SP_CATCH(ctx)
+}
+
 // ---- scalars
 int sp_scalar_from_bytes(const uint8_t b[32], uint64_t out[4]) {
   Fq f(fq_to_mont(bytes_to_u256(b)));
@@ -122,7 +144,7 @@ int sp_sumcheck_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, uint64_t out[
   int nt = kind_tables(kind);
   check_same_len(polys, nt);
   dev::ScInst in = make_inst(polys, nt);
-  dev::sc_eval((dev::ScKind)kind, &in, 1, polys[0]->len, ctx->c.small.p, ctx->c.scratch.p, ctx->c.stream);
+  dev::sc_eval((dev::ScKind)kind, &in, 1, polys[0]->len, ctx->c.small.p, ctx->c.red.p, ctx->c.stream);
   Fq e[3];
   ctx->c.get_small(0, e, 3);
   memcpy(out, e, 96);
@@ -137,7 +159,7 @@ int sp_sumcheck_fold_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, const ui
   Fq rr = fq_in(r);
   ctx->c.put_small(8, &rr, 1);
   dev::ScInst in = make_inst(polys, nt);
-  dev::sc_fold_eval((dev::ScKind)kind, &in, 1, polys[0]->len, ctx->c.small.p + 8, ctx->c.small.p, ctx->c.scratch.p, ctx->c.stream);
+  dev::sc_fold_eval((dev::ScKind)kind, &in, 1, polys[0]->len, ctx->c.small.p + 8, ctx->c.small.p, ctx->c.red.p, ctx->c.stream);
   Fq e[3];
   ctx->c.get_small(0, e, 3);
   memcpy(out, e, 96);
@@ -161,7 +183,7 @@ int sp_poly_evaluate(sp_ctx* ctx, const sp_poly* p, const uint64_t* r, size_t el
   DevBuf<u256> d_r(ell + 1), small(2 * ((size_t)1 << ((ell + 1) / 2)) + 8), eq(p->len);
   dev::h2d(d_r.p, r, ell * 32, ctx->c.stream);
   dev::eq_evals(eq.p, d_r.p, (int)ell, small.p, ctx->c.stream);
-  dev::dot(ctx->c.small.p + 32, p->d.p, eq.p, p->len, ctx->c.scratch.p, ctx->c.stream);
+  dev::dot(ctx->c.small.p + 32, p->d.p, eq.p, p->len, ctx->c.red.p, ctx->c.stream);
   Fq v;
   ctx->c.get_small(32, &v, 1);
   fq_out(out, v);
@@ -182,7 +204,7 @@ int sp_poly_bound_rows(sp_ctx* ctx, const sp_poly* p, const uint64_t* Lm, size_t
 int sp_dot(sp_ctx* ctx, const sp_poly* a, const sp_poly* b, uint64_t out[4]) {
   SP_TRY(ctx)
   if (a->len != b->len) throw SpError(SP_ERR_INVALID_ARG, "dot: length mismatch");
-  dev::dot(ctx->c.small.p + 32, a->d.p, b->d.p, a->len, ctx->c.scratch.p, ctx->c.stream);
+  dev::dot(ctx->c.small.p + 32, a->d.p, b->d.p, a->len, ctx->c.red.p, ctx->c.stream);
   Fq v;
   ctx->c.get_small(32, &v, 1);
   fq_out(out, v);

@@ -4,6 +4,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <string>
 #include "field.cuh"
 #include "curve.cuh"
 
@@ -35,6 +36,9 @@ void event_record(void* ev, cudaStream_t s);
 float event_elapsed_ms(void* a, void* b);
 void event_destroy(void* ev);
 unsigned long long launch_count();  // kernels launched by this library since load
+void io_bytes(unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);  // bytes moved through h2d()/d2h() since load
+void prof_enable(bool on);          // CUDA-event timing around every kernel family (clears previous records)
+std::string prof_report();          // "name:launches:total_ms:total_algorithmic_bytes;..."
 
 // ---- sumcheck rounds (K1/K2 of SURVEY.md §2b)
 enum ScKind { SC_QUAD = 0 /*A*B*/, SC_CUBIC3 = 1 /*A*B*C*/, SC_CUBIC4 = 2 /*A*(B*C-D)*/ };

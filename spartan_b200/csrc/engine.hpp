@@ -35,7 +35,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   uint8_t* pinned = nullptr;       // staging for small host<->device exchanges
   size_t pinned_bytes = 0;
-  DevBuf<uint8_t> scratch;         // reduction partials / MSM partials
+  DevBuf<uint8_t> scratch;         // MSM partial sums (growable)
+  DevBuf<uint8_t> red;             // reduction tickets + per-block partials (fixed size, tickets zeroed once and self-resetting)
   DevBuf<u256> small;              // challenges, results (device side)
   std::string last_error;
   // per-phase timers (profile feature of the reference, src/timer.rs): label -> milliseconds of the last prove

@@ -16,6 +16,7 @@
 #include <stdexcept>
 #include <string>
 #include <atomic>
+#include <vector>
 #include "dev.hpp"
 
 namespace sp {
@@ -24,6 +25,51 @@ namespace dev {
 static std::atomic<unsigned long long> g_launches{0};
 #define SP_LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 unsigned long long launch_count() { return g_launches.load(); }
+static std::atomic<unsigned long long> g_h2d{0}, g_d2h{0};
+void io_bytes(unsigned long long* h2d_b, unsigned long long* d2h_b) { *h2d_b = g_h2d.load(); *d2h_b = g_d2h.load(); }
+
+// ---- per-kernel-family CUDA-event profiler (bench.py roofline leg).  Off by default: one branch per wrapper.
+struct ProfRec { const char* name; cudaEvent_t a, b; double bytes; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+  bool on; size_t idx; cudaStream_t s;
+  ProfScope(const char* name, double bytes, cudaStream_t st) : on(g_prof), idx(0), s(st) {
+    if (!on) return;
+    ProfRec r{name, prof_event(), prof_event(), bytes};
+    cudaEventRecord(r.a, s);
+    idx = g_recs.size();
+    g_recs.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(g_recs[idx].b, s); }
+};
+void prof_enable(bool on) {
+  g_prof = on;
+  for (auto& r : g_recs) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
+  g_recs.clear();
+}
+// "name:launches:total_ms:total_algorithmic_bytes;" per family, after a device synchronise
+std::string prof_report() {
+  cudaDeviceSynchronize();
+  struct Agg { double ms = 0, bytes = 0; unsigned long long n = 0; };
+  std::vector<std::pair<std::string, Agg>> aggs;
+  for (auto& r : g_recs) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    size_t k = 0;
+    for (; k < aggs.size(); k++) if (aggs[k].first == r.name) break;
+    if (k == aggs.size()) aggs.push_back({r.name, Agg()});
+    aggs[k].second.ms += ms; aggs[k].second.bytes += r.bytes; aggs[k].second.n++;
+  }
+  std::string out;
+  for (auto& a : aggs) out += a.first + ":" + std::to_string(a.second.n) + ":" + std::to_string(a.second.ms) + ":" + std::to_string(a.second.bytes) + ";";
+  return out;
+}
 
 void check(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -41,8 +87,8 @@ void* dmalloc(size_t b) { void* p = nullptr; ck(cudaMalloc(&p, b ? b : 16), "cud
 void dfree(void* p) { if (p) cudaFree(p); }
 void* hmalloc_pinned(size_t b) { void* p = nullptr; ck(cudaMallocHost(&p, b ? b : 16), "cudaMallocHost"); return p; }
 void hfree_pinned(void* p) { if (p) cudaFreeHost(p); }
-void h2d(void* d, const void* h, size_t b, cudaStream_t s) { if (b) ck(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s), "h2d"); }
-void d2h(void* h, const void* d, size_t b, cudaStream_t s) { if (b) ck(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s), "d2h"); }
+void h2d(void* d, const void* h, size_t b, cudaStream_t s) { g_h2d += b; if (b) ck(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s), "h2d"); }
+void d2h(void* h, const void* d, size_t b, cudaStream_t s) { g_d2h += b; if (b) ck(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s), "d2h"); }
 void d2d(void* dst, const void* src, size_t b, cudaStream_t s) { if (b) ck(cudaMemcpyAsync(dst, src, b, cudaMemcpyDeviceToDevice, s), "d2d"); }
 void dzero(void* d, size_t b, cudaStream_t s) { if (b) ck(cudaMemsetAsync(d, 0, b, s), "memset"); }
 int sm_count() {
@@ -253,6 +299,7 @@ static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
 }
 
 void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s) {
+  ProfScope ps("sc_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 32.0, s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
@@ -266,6 +313,7 @@ void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out,
   SP_LAUNCHED(); check("sc_eval");
 }
 void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256* d_r, u256* out, void* scratch, cudaStream_t s) {
+  ProfScope ps("sc_fold_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 48.0, s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
@@ -279,6 +327,7 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
   SP_LAUNCHED(); check("sc_fold_eval");
 }
 void fold_top(u256* const* tables, int ntables, size_t len, const u256* d_r, cudaStream_t s) {
+  ProfScope ps("fold_top", (double)ntables * len * 48.0, s);
   for (int base = 0; base < ntables; base += 64) {
     FoldBatch fb; int n = ntables - base < 64 ? ntables - base : 64;
     for (int i = 0; i < n; i++) fb.t[i] = tables[base + i];
@@ -309,6 +358,7 @@ __global__ void k_eq_combine(u256* out, const u256* __restrict__ hi, const u256*
     st256(out + i, fq_mul(ld256_ro(hi + (i >> nlo)), ld256_ro(lo + (i & (((size_t)1 << nlo) - 1)))));
 }
 void eq_evals(u256* out, const u256* d_r, int ell, u256* small, cudaStream_t s) {
+  ProfScope ps("eq_evals", 32.0 * (double)((size_t)1 << ell), s);
   if (ell <= 10) {
     size_t n = (size_t)1 << ell;
     k_eq_small<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(out, d_r, ell);
@@ -335,6 +385,7 @@ __global__ void __launch_bounds__(256) k_dot(const u256* __restrict__ a, const u
   block_reduce_finish<1>(acc, partials, counters, out, 1);
 }
 void dot3(u256* out, const u256* a, const u256* b, const u256* c, size_t n, void* scratch, cudaStream_t s) {
+  ProfScope ps("dot", (c ? 96.0 : 64.0) * (double)n, s);
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
   dim3 grid(grid_for(n, 256, 2), 1);
@@ -363,6 +414,7 @@ __global__ void k_sum_slabs(u256* out, const u256* __restrict__ part, size_t R_s
   st256(out + i, acc);
 }
 void bound_rows(u256* out, const u256* Z, const u256* L, size_t L_size, size_t R_size, u256* scratch, cudaStream_t s) {
+  ProfScope ps("bound_rows", 32.0 * (double)L_size * (double)R_size, s);
   int nslabs = 64;
   while (nslabs > 1 && (size_t)nslabs > L_size) nslabs >>= 1;
   size_t rows_per_slab = (L_size + nslabs - 1) / nslabs;
@@ -379,6 +431,7 @@ __global__ void k_lincomb3(u256* out, const u256* __restrict__ A, const u256* __
     st256(out + i, fq_add(fq_add(fq_mul(ra, ld256_ro(A + i)), fq_mul(rb, ld256_ro(B + i))), fq_mul(rc, ld256_ro(C + i))));
 }
 void lincomb3(u256* out, const u256* A, const u256* B, const u256* C, const u256* d_rabc, size_t n, cudaStream_t s) {
+  ProfScope ps("lincomb3", 128.0 * (double)n, s);
   k_lincomb3<<<grid_for(n, 256, 4), 256, 0, s>>>(out, A, B, C, d_rabc, n);
   SP_LAUNCHED(); check("lincomb3");
 }
@@ -387,6 +440,7 @@ __global__ void k_hadamard(u256* out, const u256* a, const u256* b, size_t n) {
     st256(out + i, fq_mul(ld256(a + i), ld256(b + i)));
 }
 void hadamard(u256* out, const u256* a, const u256* b, size_t n, cudaStream_t s) {
+  ProfScope ps("hadamard", 96.0 * (double)n, s);
   k_hadamard<<<grid_for(n, 256, 8), 256, 0, s>>>(out, a, b, n);
   SP_LAUNCHED(); check("hadamard");
 }
@@ -418,6 +472,7 @@ __global__ void k_gather(u256* out, const u256* __restrict__ mem, const uint32_t
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st256(out + i, ld256_ro(mem + idx[i]));
 }
 void gather(u256* out, const u256* mem, const uint32_t* idx, size_t n, cudaStream_t s) {
+  ProfScope ps("gather", 68.0 * (double)n, s);
   k_gather<<<grid_for(n, 256, 8), 256, 0, s>>>(out, mem, idx, n);
   SP_LAUNCHED(); check("gather");
 }
@@ -433,6 +488,7 @@ __global__ void k_spark_hash(u256* out, size_t n, const u256* __restrict__ addr,
   }
 }
 void spark_hash(u256* out, size_t n, const u256* addr, const u256* val, const u256* ts, int ts_plus_one, const u256* d_rg, cudaStream_t s) {
+  ProfScope ps("spark_hash", 128.0 * (double)n, s);
   k_spark_hash<<<grid_for(n, 256, 4), 256, 0, s>>>(out, n, addr, val, ts, ts_plus_one, d_rg);
   SP_LAUNCHED(); check("spark_hash");
 }
@@ -454,6 +510,7 @@ __global__ void k_ipa_fold_ab(u256* a, u256* b, size_t n, const u256* __restrict
   }
 }
 void ipa_fold_ab(u256* a, u256* b, size_t n, const u256* d_u, cudaStream_t s) {
+  ProfScope ps("ipa_fold_ab", 192.0 * (double)n, s);
   k_ipa_fold_ab<<<grid_for(n, 128, 8), 128, 0, s>>>(a, b, n, d_u);
   SP_LAUNCHED(); check("ipa_fold_ab");
 }
@@ -494,6 +551,7 @@ __global__ void k_spmv(u256* out, size_t nrows, const uint32_t* __restrict__ ptr
   }
 }
 void spmv(u256* out, size_t nrows, const uint32_t* ptr, const uint32_t* idx, const u256* val, const u256* x, cudaStream_t s) {
+  ProfScope ps("spmv", 100.0 * (double)nrows, s);
   k_spmv<<<grid_for(nrows, 128, 8), 128, 0, s>>>(out, nrows, ptr, idx, val, x);
   SP_LAUNCHED(); check("spmv");
 }
@@ -550,6 +608,7 @@ __global__ void k_compress(uint8_t* out, const ge* __restrict__ in, size_t n) {
   st256(reinterpret_cast<u256*>(out + 32 * i), ristretto_encode(ld_ge(in + i)));
 }
 void compress_batch(uint8_t* out32, const ge* in, size_t n, cudaStream_t s) {
+  ProfScope ps("compress_batch", 160.0 * (double)n, s);
   k_compress<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(out32, in, n);
   SP_LAUNCHED(); check("compress");
 }
@@ -658,6 +717,7 @@ size_t msm_scratch_bytes(size_t L, size_t R) {
 }
 void msm_rows(ge* out, const ge_niels* table, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
               void* scratch, cudaStream_t s) {
+  ProfScope ps("msm_rows", 32.0 * (double)L * (double)R + 32.0 * (double)R, s);
   int wpt = msm_pick_wpt(L, R);
   size_t chunks = msm_chunks(R + (blinds ? 1 : 0), wpt);
   ge* partial = (ge*)scratch;

@@ -3,6 +3,8 @@
 // proof bytes equal the reference's for identical instance, assignment, transcript label and RandomTape seed.
 #include "prover.hpp"
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace sp {
 
@@ -30,13 +32,14 @@ Ctx::Ctx(int dev_) : device(dev_) {
   pinned_bytes = 1 << 20;
   pinned = (uint8_t*)dev::hmalloc_pinned(pinned_bytes);
   small.alloc(4096);
-  scratch.alloc(dev::sc_scratch_bytes(24) + (1 << 20));
-  dev::dzero(scratch.p, scratch.n, stream);
+  scratch.alloc(1 << 20);
+  red.alloc(dev::sc_scratch_bytes(24));
+  dev::dzero(red.p, red.n, stream);
   sync();
 }
 Ctx::~Ctx() {
   try { sync(); } catch (...) {}
-  scratch.release(); small.release();
+  scratch.release(); red.release(); small.release();
   dev::hfree_pinned(pinned);
   dev::stream_destroy(stream);
 }
@@ -97,7 +100,7 @@ R1CSGens::R1CSGens(Ctx* ctx, const std::string& label, size_t num_vars) {
   size_t ell = 0;
   while (((size_t)1 << ell) < num_vars) ell++;
   size_t n = (size_t)1 << (ell - ell / 2);
-  set.reset(new GenSet(ctx, label, n + 2, {0, 1, 2, 3, 4, n, n + 1}));
+  set.reset(new GenSet(ctx, label, std::max<size_t>(n + 2, 5), {0, 1, 2, 3, 4, n, n + 1}));  // gens_4 draws 5 points of the same stream
   gens_pc.n = n;
   gens_pc.gens_n = CommitKey{set.get(), 0, n, n + 1};
   gens_pc.gens_1 = CommitKey{set.get(), n, 1, n + 1};
@@ -259,7 +262,7 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
   u256* d_out = ctx.small.p + 0;     // 3 result scalars
   u256* d_r = ctx.small.p + 8;       // round challenge
   size_t len = (size_t)1 << num_rounds;
-  dev::sc_eval(kind, &inst, 1, len, d_out, ctx.scratch.p, ctx.stream);
+  dev::sc_eval(kind, &inst, 1, len, d_out, ctx.red.p, ctx.stream);
   for (size_t j = 0; j < num_rounds; j++) {
     Fq e[3];
     ctx.get_small(0, e, 3);
@@ -273,7 +276,7 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
     // bind the tables to r_j on the device right away (fused with the next round's evaluation); the host continues with the
     // sigma protocol of this round while the kernel runs
     ctx.put_small(8, &r_j, 1);
-    if (j + 1 < num_rounds) dev::sc_fold_eval(kind, &inst, 1, len, d_r, d_out, ctx.scratch.p, ctx.stream);
+    if (j + 1 < num_rounds) dev::sc_fold_eval(kind, &inst, 1, len, d_r, d_out, ctx.red.p, ctx.stream);
     else dev::fold_top(tables, nt, len, d_r, ctx.stream);
     len >>= 1;
 
@@ -346,8 +349,8 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
   size_t cur = n, k = 0;
   while (cur != 1) {
     size_t half = cur / 2;
-    dev::dot(d_c, d_a, d_b + half, half, ctx.scratch.p, ctx.stream);          // c_L = <a_L, b_R>   bullet.rs:78
-    dev::dot(d_c + 1, d_a + half, d_b, half, ctx.scratch.p, ctx.stream);      // c_R = <a_R, b_L>   bullet.rs:79
+    dev::dot(d_c, d_a, d_b + half, half, ctx.red.p, ctx.stream);          // c_L = <a_L, b_R>   bullet.rs:78
+    dev::dot(d_c + 1, d_a + half, d_b, half, ctx.red.p, ctx.stream);      // c_R = <a_R, b_L>   bullet.rs:79
     dev::ipa_lr_scalars(lr.p, lr.p + n, d_a, svec.p, cur, n, ctx.stream);
     dev::msm_rows(pts.p, gs.table.p, lr.p, n, 2, n, nullptr, 0, ctx.scratch.p, ctx.stream);
     dev::d2h(ctx.pinned, d_c, 64, ctx.stream);
@@ -570,7 +573,7 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
     DevBuf<u256> d_eq(num_vars);
     dev::h2d(d_chal.p, ry1.data(), ry1.size() * sizeof(u256), ctx.stream);
     dev::eq_evals(d_eq.p, d_chal.p, (int)ry1.size(), eq_small.p, ctx.stream);
-    dev::dot(ctx.small.p + 32, d_vars, d_eq.p, num_vars, ctx.scratch.p, ctx.stream);
+    dev::dot(ctx.small.p + 32, d_vars, d_eq.p, num_vars, ctx.red.p, ctx.stream);
     Fq eval_vars_at_ry;
     ctx.get_small(32, &eval_vars_at_ry, 1);
     Fq blind_eval = tape.random_scalar("blind_eval");
