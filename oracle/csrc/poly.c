@@ -242,3 +242,8 @@ void poly_commit_rows(uint8_t *out32, const fq_t *Z, size_t L_size, size_t R_siz
     ristretto_encode(out32 + 32 * i, &acc);
   }
 }
+
+/* AddrTimestamps::new inner loop, sparse_mlpoly.rs:229-243: read_ts[i] = audit_ts[addr]; audit_ts[addr] += 1 */
+void spark_timestamps(uint64_t *read_ts, uint64_t *audit_ts, const uint64_t *addr, size_t num_ops) {
+  for (size_t i = 0; i < num_ops; i++) { uint64_t a = addr[i]; read_ts[i] = audit_ts[a]; audit_ts[a] += 1; }
+}
