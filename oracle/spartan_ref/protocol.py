@@ -747,3 +747,37 @@ class R1CSProof:
         expected_claim_post_phase2 = (comm_eval_Z_at_ry * ((r_A * eA + r_B * eB + r_C * eC) % Q)).compress()
         self.proof_eq_sc_phase2.verify(gens.gens_sc.gens_1, T, expected_claim_post_phase2, comm_claim_post_phase2)
         return rx, ry
+
+
+# ----------------------------------------------------------------------------- bincode reader (for verifying proofs produced elsewhere)
+def deser(tp, buf, pos=0):
+    """inverse of ser() driven by the dataclass type hints: returns (value, new_pos)"""
+    import typing
+    origin = typing.get_origin(tp)
+    if tp is int:
+        return oc.from_mont_bytes(buf[pos:pos + 32]), pos + 32
+    if tp is bytes:
+        return bytes(buf[pos:pos + 32]), pos + 32
+    if origin in (list, typing.List):
+        (inner,) = typing.get_args(tp)
+        n = int.from_bytes(buf[pos:pos + 8], "little")
+        pos += 8
+        out = []
+        for _ in range(n):
+            v, pos = deser(inner, buf, pos)
+            out.append(v)
+        return out, pos
+    if origin in (tuple, typing.Tuple):
+        out = []
+        for inner in typing.get_args(tp):
+            v, pos = deser(inner, buf, pos)
+            out.append(v)
+        return tuple(out), pos
+    if dataclasses.is_dataclass(tp):
+        hints = typing.get_type_hints(tp)
+        vals = []
+        for f in dataclasses.fields(tp):
+            v, pos = deser(hints[f.name], buf, pos)
+            vals.append(v)
+        return tp(*vals), pos
+    raise TypeError(tp)

@@ -394,6 +394,27 @@ void dot3(u256* out, const u256* a, const u256* b, const u256* c, size_t n, void
 }
 void dot(u256* out, const u256* a, const u256* b, size_t n, void* scratch, cudaStream_t s) { dot3(out, a, b, nullptr, n, scratch, s); }
 
+// out[k] = <a_k, b> for up to 32 tables sharing b (the 21 + 2 evaluations of HashLayerProof::prove, sparse_mlpoly.rs:696-764, all at one point)
+struct DotBatch { const u256* a[32]; };
+__global__ void __launch_bounds__(256) k_dot_many(DotBatch batch, const u256* __restrict__ b, size_t n, u256* partials, unsigned int* counters, u256* out) {
+  const u256* a = batch.a[blockIdx.y];
+  u256 acc[1] = {fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc[0] = fq_add(acc[0], fq_mul(ld256_ro(a + i), ld256_ro(b + i)));
+  block_reduce_finish<1>(acc, partials, counters, out, 1);
+}
+void dot_many(u256* out, const u256* const* a_list, int count, const u256* b, size_t n, void* scratch, cudaStream_t s) {
+  ProfScope ps("dot_many", 32.0 * (double)n * (count + 1), s);
+  if (count > 32) throw std::runtime_error("spartan_b200: dot_many supports at most 32 tables");
+  DotBatch db;
+  for (int i = 0; i < count; i++) db.a[i] = a_list[i];
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(n, 256, 1), count);
+  k_dot_many<<<grid, 256, 0, s>>>(db, b, n, partials, counters, out);
+  SP_LAUNCHED(); check("dot_many");
+}
+
 // DensePolynomial::bound (dense_mlpoly.rs:206-213): out[i] = sum_j L[j]*Z[j*R+i].  Column-per-thread (coalesced over i),
 // rows split into gridDim.y slabs whose partial sums land in scratch and are combined by a second tiny kernel.
 __global__ void __launch_bounds__(128) k_bound_rows_partial(u256* part, const u256* __restrict__ Z, const u256* __restrict__ L, size_t L_size,

@@ -116,6 +116,48 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
 void nizk_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T,
                 const Fq& tape_seed, NizkProof& out);
 
+struct UniPoly {  // unipoly.rs
+  std::vector<Fq> coeffs;
+  static UniPoly from_evals(const std::vector<Fq>& e) {  // unipoly.rs:23-54
+    static const Fq two_inv = Fq::from_u64(2).inv(), six_inv = Fq::from_u64(6).inv();
+    UniPoly p;
+    if (e.size() == 3) {
+      Fq c = e[0];
+      Fq a = two_inv * (e[2] - e[1] - e[1] + c);
+      Fq b = e[1] - c - a;
+      p.coeffs = {c, b, a};
+    } else {
+      Fq d = e[0];
+      Fq a = six_inv * (e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0]);
+      Fq b = two_inv * (e[0] + e[0] - e[1] - e[1] - e[1] - e[1] - e[1] + e[2] + e[2] + e[2] + e[2] - e[3]);
+      Fq c = e[1] - d - a - b;
+      p.coeffs = {d, c, b, a};
+    }
+    return p;
+  }
+  Fq evaluate(const Fq& r) const {  // unipoly.rs:72-80
+    Fq ev = coeffs[0], power = r;
+    for (size_t i = 1; i < coeffs.size(); i++) { ev += power * coeffs[i]; power *= r; }
+    return ev;
+  }
+  CompressedUniPoly compress() const {  // unipoly.rs:82-88
+    CompressedUniPoly c;
+    c.coeffs_except_linear_term.push_back(coeffs[0]);
+    for (size_t i = 2; i < coeffs.size(); i++) c.coeffs_except_linear_term.push_back(coeffs[i]);
+    return c;
+  }
+  void append_to_transcript(const char* label, Transcript& T) const {  // unipoly.rs:112-120
+    T.append_message(label, "UniPoly_begin");
+    for (auto& c : coeffs) T.append_scalar("coeff", c);
+    T.append_message(label, "UniPoly_end");
+  }
+};
+
+void append_poly_commitment(Transcript& T, const char* label, const PolyCommitment& c);
+// PolyEvalProof::prove (dense_mlpoly.rs:312-365) on a device-resident table
+void polyeval_prove(Ctx& ctx, const u256* d_Z, const std::vector<Fq>* blinds_opt, const std::vector<Fq>& r, const Fq& Zr, const Fq* blind_Zr_opt,
+                    const PolyCommitmentGens& gens, Transcript& T, RandomTape& tape, PolyEvalProof& proof, Cp& C_Zr);
+
 // exposed pieces (C-ABI operator level and tests)
 Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalars, size_t stride, size_t L, size_t R, const Fq* blinds,
                             std::vector<Cp>& out);

@@ -1,12 +1,491 @@
-// spartan_b200 — SNARK path (placeholder until the SPARK driver lands; every entry point fails loudly).
+// spartan_b200 — SNARK path: SNARK::encode / SNARK::prove (src/lib.rs:325-420) with the SPARK sparse-polynomial evaluation proof
+// (src/sparse_mlpoly.rs:1447-1514, src/product_tree.rs:259-383) driven on the device.  Every table of the memory-checking network
+// (hash layers, 16 product trees with all their layers, dereferenced values) lives in HBM; the host only runs the transcript.
 #include "snark.hpp"
+#include <algorithm>
 #include "../../include/spartan_b200.h"
 
 namespace sp {
-SnarkGens::SnarkGens(Ctx*, size_t, size_t, size_t, size_t) { throw SpError(SP_ERR_INTERNAL, "SNARK path not built yet"); }
-void SnarkEncoding::ser_commitment(Writer&) const {}
-void snark_encode(Ctx&, const Instance&, const SnarkGens&, SnarkEncoding&) { throw SpError(SP_ERR_INTERNAL, "SNARK path not built yet"); }
-void snark_prove(Ctx&, const Instance&, const SnarkEncoding&, const u256*, const std::vector<Fq>&, const SnarkGens&, Transcript&, const Fq&, Writer&) {
-  throw SpError(SP_ERR_INTERNAL, "SNARK path not built yet");
+
+static size_t log2_ceil(size_t x) { size_t l = 0; while (((size_t)1 << l) < x) l++; return l; }
+static size_t next_pow2(size_t x) { return (size_t)1 << log2_ceil(x); }
+
+static PolyCommitmentGens pc_view(const GenSet* set, size_t num_vars) {  // PolyCommitmentGens::new (dense_mlpoly.rs:31-35)
+  PolyCommitmentGens g;
+  g.n = (size_t)1 << (num_vars - num_vars / 2);
+  g.gens_n = CommitKey{set, 0, g.n, g.n + 1};
+  g.gens_1 = CommitKey{set, g.n, 1, g.n + 1};
+  return g;
 }
+
+SnarkGens::SnarkGens(Ctx* ctx, size_t num_cons, size_t num_vars, size_t num_inputs, size_t num_nz_entries) {
+  size_t nvp = next_pow2(std::max(num_vars, num_inputs + 1));  // lib.rs:288-294
+  gens_r1cs_sat.reset(new R1CSGens(ctx, "gens_r1cs_sat", nvp));
+  // R1CSCommitmentGens::new (r1cs.rs:34-47) -> SparseMatPolyCommitmentGens::new(label, x, y, nz, 3) (sparse_mlpoly.rs:292-317)
+  size_t x = log2_ceil(num_cons), y = log2_ceil(2 * nvp), lgnz = log2_ceil(next_pow2(num_nz_entries));
+  size_t v_ops = lgnz + log2_ceil(next_pow2(3 * 5)), v_mem = std::max(x, y) + 1, v_derefs = lgnz + log2_ceil(next_pow2(3 * 2));
+  size_t n_ops = (size_t)1 << (v_ops - v_ops / 2), n_mem = (size_t)1 << (v_mem - v_mem / 2), n_der = (size_t)1 << (v_derefs - v_derefs / 2);
+  size_t nmax = std::max(n_ops, std::max(n_mem, n_der));
+  eval_set.reset(new GenSet(ctx, "gens_r1cs_eval", nmax + 2, {n_ops, n_ops + 1, n_mem, n_mem + 1, n_der, n_der + 1}));
+  gens_ops = pc_view(eval_set.get(), v_ops);
+  gens_mem = pc_view(eval_set.get(), v_mem);
+  gens_derefs = pc_view(eval_set.get(), v_derefs);
+}
+
+void SnarkEncoding::ser_commitment(Writer& w) const {  // ComputationCommitment { R1CSCommitment { .., SparseMatPolyCommitment } } (r1cs.rs:49-55, sparse_mlpoly.rs:319-327)
+  w.u64(num_cons); w.u64(num_vars); w.u64(num_inputs);
+  w.u64(batch_size); w.u64(num_ops); w.u64(num_mem_cells);
+  comm_comb_ops.ser(w); comm_comb_mem.ser(w);
+}
+
+static void commit_poly(Ctx& ctx, const u256* d_Z, size_t len, const PolyCommitmentGens& gens, PolyCommitment& out) {  // DensePolynomial::commit, no blinds
+  size_t ell = log2_ceil(len);
+  size_t L = (size_t)1 << (ell / 2), R = (size_t)1 << (ell - ell / 2);
+  if (R != gens.n) throw SpError(SP_ERR_INVALID_ARG, "polynomial size does not match the commitment generators (num_nz_entries too small?)");
+  commit_rows_and_compress(ctx, gens.gens_n, d_Z, R, L, R, nullptr, out.C);
+}
+
+// ================================================================================================ SNARK::encode
+void snark_encode(Ctx& ctx, const Instance& inst, const SnarkGens& gens, SnarkEncoding& e) {
+  // SparseMatPolynomial::multi_commit -> multi_sparse_to_dense_rep (sparse_mlpoly.rs:366-420, :483-503)
+  e.num_cons = inst.num_cons; e.num_vars = inst.num_vars; e.num_inputs = inst.num_inputs;
+  e.batch_size = 3;
+  size_t N = 1;
+  for (int m = 0; m < 3; m++) N = std::max(N, next_pow2(inst.M[m].row.size()));
+  size_t x = log2_ceil(inst.num_cons), y = log2_ceil(2 * inst.num_vars);
+  size_t cells = (size_t)1 << std::max(x, y);
+  e.num_ops = N; e.num_mem_cells = cells;
+  e.comb_ops.alloc(16 * N);   // row.ops_addr[3] | row.read_ts[3] | col.ops_addr[3] | col.read_ts[3] | val[3] | zero pad  (DensePolynomial::merge)
+  e.comb_mem.alloc(2 * cells);
+  dev::dzero(e.comb_ops.p, 16 * N * sizeof(u256), ctx.stream);
+  DevBuf<uint64_t> tmp64(std::max(N, cells));
+  std::vector<uint64_t> audit(cells), rts(N), addr64(N);
+  for (int side = 0; side < 2; side++) {  // AddrTimestamps::new (sparse_mlpoly.rs:220-254), row then col
+    std::fill(audit.begin(), audit.end(), 0);
+    AddrTimestampsDev& at = side == 0 ? e.row : e.col;
+    at.ops_addr_idx.resize(3);
+    for (int m = 0; m < 3; m++) {
+      const std::vector<uint32_t>& src = side == 0 ? inst.M[m].row : inst.M[m].col;
+      std::vector<uint32_t> a32(N, 0);
+      std::copy(src.begin(), src.end(), a32.begin());
+      for (size_t i = 0; i < N; i++) {
+        size_t a = a32[i];
+        if (a >= cells) throw SpError(SP_ERR_INVALID_INDEX, "address out of range");
+        rts[i] = audit[a];
+        audit[a] += 1;
+        addr64[i] = a;
+      }
+      at.ops_addr_idx[m].alloc(N);
+      dev::h2d(at.ops_addr_idx[m].p, a32.data(), N * sizeof(uint32_t), ctx.stream);
+      u256* d_addr = e.comb_ops.p + (size_t)(side * 6 + m) * N;
+      u256* d_rts = e.comb_ops.p + (size_t)(side * 6 + 3 + m) * N;
+      dev::h2d(tmp64.p, addr64.data(), N * 8, ctx.stream);
+      dev::from_u64(d_addr, tmp64.p, N, ctx.stream);
+      dev::h2d(tmp64.p, rts.data(), N * 8, ctx.stream);
+      dev::from_u64(d_rts, tmp64.p, N, ctx.stream);
+      ctx.sync();
+    }
+    dev::h2d(tmp64.p, audit.data(), cells * 8, ctx.stream);
+    dev::from_u64(e.comb_mem.p + (size_t)side * cells, tmp64.p, cells, ctx.stream);
+    ctx.sync();
+  }
+  for (int m = 0; m < 3; m++)
+    dev::h2d(e.comb_ops.p + (size_t)(12 + m) * N, inst.M[m].val.data(), inst.M[m].val.size() * sizeof(u256), ctx.stream);
+  ctx.sync();
+  commit_poly(ctx, e.comb_ops.p, 16 * N, gens.gens_ops, e.comm_comb_ops);
+  commit_poly(ctx, e.comb_mem.p, 2 * cells, gens.gens_mem, e.comm_comb_mem);
+}
+
+// views into the dense representation
+struct DenseView {
+  size_t N, cells;
+  const u256 *row_addr[3], *row_ts[3], *col_addr[3], *col_ts[3], *val[3], *row_audit, *col_audit;
+  explicit DenseView(const SnarkEncoding& e) : N(e.num_ops), cells(e.num_mem_cells) {
+    for (int m = 0; m < 3; m++) {
+      row_addr[m] = e.comb_ops.p + (size_t)m * N; row_ts[m] = e.comb_ops.p + (size_t)(3 + m) * N;
+      col_addr[m] = e.comb_ops.p + (size_t)(6 + m) * N; col_ts[m] = e.comb_ops.p + (size_t)(9 + m) * N;
+      val[m] = e.comb_ops.p + (size_t)(12 + m) * N;
+    }
+    row_audit = e.comb_mem.p; col_audit = e.comb_mem.p + cells;
+  }
+};
+
+// ProductCircuit (product_tree.rs:11-63): every layer kept, layer k (size n/2^k, left half | right half) at offset 2n - 2n/2^k
+struct ProdCircuit {
+  DevBuf<u256> buf;
+  size_t n = 0, num_layers = 0;
+  void alloc(size_t n_) { n = n_; num_layers = log2_ceil(n_); buf.alloc(2 * n_); }
+  u256* layer(size_t k) { return buf.p + (2 * n - 2 * (n >> k)); }
+  size_t layer_len(size_t k) const { return n >> k; }
+  void build(Ctx& ctx) {  // layer 0 already written
+    for (size_t k = 0; k + 1 < num_layers; k++) {
+      size_t h = layer_len(k) / 2;
+      dev::hadamard(layer(k + 1), layer(k), layer(k) + h, h, ctx.stream);  // compute_layer (product_tree.rs:18-34)
+    }
+  }
+};
+
+static Fq circuit_evaluate(Ctx& ctx, ProdCircuit& c) {  // ProductCircuit::evaluate (product_tree.rs:58-63)
+  std::vector<Fq> v = ctx.download(c.layer(c.num_layers - 1), 2);
+  return v[0] * v[1];
+}
+
+struct DotpCircuit { u256 *left, *right, *weight; size_t len; };
+
+// ProductCircuitEvalProofBatched::prove (product_tree.rs:259-383) with SumcheckInstanceProof::prove_cubic_batched (sumcheck.rs:254-424) inlined
+static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vector<DotpCircuit>& dotps, Transcript& T, ProductCircuitEvalProofBatched& out,
+                          std::vector<Fq>& rand_out) {
+  const size_t np = prods.size(), nd = dotps.size();
+  const size_t num_layers = prods[0]->num_layers;
+  std::vector<Fq> claims_to_verify(np);
+  {  // all evaluate()s with one sync
+    for (size_t i = 0; i < np; i++) dev::d2h(ctx.pinned + 64 * i, prods[i]->layer(num_layers - 1), 64, ctx.stream);
+    ctx.sync();
+    for (size_t i = 0; i < np; i++) { Fq v[2]; memcpy(v, ctx.pinned + 64 * i, 64); claims_to_verify[i] = v[0] * v[1]; }
+  }
+  const size_t max_half = prods[0]->n / 2;
+  DevBuf<u256> cpar_a(std::max<size_t>(max_half / 2, 1)), cpar_b(std::max<size_t>(max_half / 2, 1)), d_rand(64), eq_small(2 * ((size_t)1 << ((num_layers + 1) / 2)) + 8);
+  DevBuf<u256> cpar0(std::max<size_t>(max_half, 1));
+  std::vector<Fq> rand;
+  u256* d_out = ctx.small.p + 64;   // ninst * 3 scalars
+  u256* d_r = ctx.small.p + 8;
+  for (size_t layer_id = num_layers; layer_id-- > 0;) {
+    const size_t len = prods[0]->layer_len(layer_id);  // left + right
+    const size_t half = len / 2;                       // table length of this layer's sumcheck
+    const size_t num_rounds = log2_ceil(half);
+    // poly_C_par = eq(rand)                                                  (product_tree.rs:279-280)
+    if (!rand.empty()) dev::h2d(d_rand.p, rand.data(), rand.size() * sizeof(u256), ctx.stream);
+    dev::eq_evals(cpar0.p, d_rand.p, (int)rand.size(), eq_small.p, ctx.stream);
+    std::vector<dev::ScInst> insts;
+    for (size_t i = 0; i < np; i++) {
+      dev::ScInst in;
+      in.t[0] = prods[i]->layer(layer_id); in.t[1] = prods[i]->layer(layer_id) + half; in.t[2] = cpar0.p; in.t[3] = nullptr;
+      in.c_out = cpar_a.p; in.write_c = i == 0;
+      insts.push_back(in);
+    }
+    const bool with_dotp = layer_id == 0 && nd > 0;
+    if (with_dotp) {
+      for (size_t i = 0; i < nd; i++) {
+        dev::dot3(ctx.small.p + 128 + i, dotps[i].left, dotps[i].right, dotps[i].weight, dotps[i].len, ctx.red.p, ctx.stream);  // DotProductCircuit::evaluate
+        dev::ScInst in;
+        in.t[0] = dotps[i].left; in.t[1] = dotps[i].right; in.t[2] = dotps[i].weight; in.t[3] = nullptr;
+        in.c_out = dotps[i].weight; in.write_c = 1;
+        insts.push_back(in);
+      }
+      std::vector<Fq> dv(nd);
+      ctx.get_small(128, dv.data(), nd);
+      for (auto& v : dv) claims_to_verify.push_back(v);
+    }
+    const size_t ninst = insts.size();
+    std::vector<Fq> coeff_vec = T.challenge_vector("rand_coeffs_next_layer", claims_to_verify.size());
+    Fq claim = Fq::zero();
+    for (size_t i = 0; i < claims_to_verify.size(); i++) claim += claims_to_verify[i] * coeff_vec[i];
+
+    LayerProofBatched lp;
+    std::vector<Fq> rand_prod;
+    Fq e = claim;
+    size_t cur = half;
+    if (num_rounds > 0) dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream);
+    u256* cin = cpar0.p;
+    u256* cpp[2] = {cpar_a.p, cpar_b.p};
+    int flip = 0;
+    for (size_t j = 0; j < num_rounds; j++) {
+      std::vector<Fq> ev(3 * ninst);
+      ctx.get_small(64, ev.data(), 3 * ninst);
+      Fq c0 = Fq::zero(), c2 = Fq::zero(), c3 = Fq::zero();
+      for (size_t i = 0; i < ninst; i++) { c0 += ev[3 * i] * coeff_vec[i]; c2 += ev[3 * i + 1] * coeff_vec[i]; c3 += ev[3 * i + 2] * coeff_vec[i]; }  // sumcheck.rs:359-361
+      UniPoly poly = UniPoly::from_evals({c0, e - c0, c2, c3});
+      poly.append_to_transcript("poly", T);
+      Fq r_j = T.challenge_scalar("challenge_nextround");
+      rand_prod.push_back(r_j);
+      ctx.put_small(8, &r_j, 1);
+      // bind every table (shared C written once, through a ping-pong buffer)
+      for (size_t i = 0; i < np; i++) { insts[i].t[2] = cin; insts[i].c_out = cpp[flip]; }
+      if (j + 1 < num_rounds) dev::sc_fold_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_r, d_out, ctx.red.p, ctx.stream);
+      else {
+        std::vector<u256*> tabs;
+        for (size_t i = 0; i < ninst; i++) { tabs.push_back(insts[i].t[0]); tabs.push_back(insts[i].t[1]); if (i >= np) tabs.push_back(insts[i].t[2]); }
+        dev::fold_top(tabs.data(), (int)tabs.size(), cur, d_r, ctx.stream);
+        // the shared C's final value is never used by the prover (claims_prod.2 is dropped, product_tree.rs:336)
+      }
+      cin = cpp[flip];
+      flip ^= 1;
+      cur >>= 1;
+      e = poly.evaluate(r_j);
+      lp.proof.compressed_polys.push_back(poly.compress());
+    }
+    // final claims: first element of every A / B (and C for the dot-product circuits)
+    for (size_t i = 0; i < ninst; i++) {
+      dev::d2h(ctx.pinned + 96 * i, insts[i].t[0], 32, ctx.stream);
+      dev::d2h(ctx.pinned + 96 * i + 32, insts[i].t[1], 32, ctx.stream);
+      if (i >= np) dev::d2h(ctx.pinned + 96 * i + 64, insts[i].t[2], 32, ctx.stream);
+    }
+    ctx.sync();
+    lp.claims_prod_left.resize(np); lp.claims_prod_right.resize(np);
+    for (size_t i = 0; i < np; i++) { memcpy(&lp.claims_prod_left[i], ctx.pinned + 96 * i, 32); memcpy(&lp.claims_prod_right[i], ctx.pinned + 96 * i + 32, 32); }
+    for (size_t i = 0; i < np; i++) {
+      T.append_scalar("claim_prod_left", lp.claims_prod_left[i]);
+      T.append_scalar("claim_prod_right", lp.claims_prod_right[i]);
+    }
+    if (with_dotp) {
+      out.dotp_left.resize(nd); out.dotp_right.resize(nd); out.dotp_weight.resize(nd);
+      for (size_t i = 0; i < nd; i++) {
+        memcpy(&out.dotp_left[i], ctx.pinned + 96 * (np + i), 32);
+        memcpy(&out.dotp_right[i], ctx.pinned + 96 * (np + i) + 32, 32);
+        memcpy(&out.dotp_weight[i], ctx.pinned + 96 * (np + i) + 64, 32);
+        T.append_scalar("claim_dotp_left", out.dotp_left[i]);
+        T.append_scalar("claim_dotp_right", out.dotp_right[i]);
+        T.append_scalar("claim_dotp_weight", out.dotp_weight[i]);
+      }
+    }
+    Fq r_layer = T.challenge_scalar("challenge_r_layer");
+    claims_to_verify.resize(np);
+    for (size_t i = 0; i < np; i++) claims_to_verify[i] = lp.claims_prod_left[i] + r_layer * (lp.claims_prod_right[i] - lp.claims_prod_left[i]);
+    std::vector<Fq> ext = {r_layer};
+    ext.insert(ext.end(), rand_prod.begin(), rand_prod.end());
+    rand = ext;
+    out.proof.push_back(std::move(lp));
+  }
+  rand_out = rand;
+}
+
+static void append_scalar_vec(Transcript& T, const char* label, const std::vector<Fq>& v) { T.append_scalars(label, v); }
+
+static std::vector<Fq> bound_bot_all(std::vector<Fq> v, const std::vector<Fq>& ch) {  // repeated bound_poly_var_bot (dense_mlpoly.rs:225-233), last challenge first
+  for (size_t k = ch.size(); k-- > 0;) {
+    size_t n = v.size() / 2;
+    std::vector<Fq> o(n);
+    for (size_t i = 0; i < n; i++) o[i] = v[2 * i] + ch[k] * (v[2 * i + 1] - v[2 * i]);
+    v = o;
+  }
+  return v;
+}
+
+// ================================================================================================ SNARK::prove
+void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const u256* d_vars, const std::vector<Fq>& input, const SnarkGens& gens,
+                 Transcript& T, const Fq& tape_seed, Writer& w) {
+  ctx.timings.clear();
+  auto t_start = std::chrono::steady_clock::now();
+  auto mark = [&](const char* name, std::chrono::steady_clock::time_point t0) {
+    ctx.timings.push_back({name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()});
+  };
+  RandomTape tape("proof", tape_seed);                    // lib.rs:352
+  T.append_protocol_name("Spartan SNARK proof");          // lib.rs:354
+  // comm.comm.append_to_transcript (r1cs.rs:58-65, sparse_mlpoly.rs:329-341)
+  T.append_u64("num_cons", enc.num_cons); T.append_u64("num_vars", enc.num_vars); T.append_u64("num_inputs", enc.num_inputs);
+  T.append_u64("batch_size", enc.batch_size); T.append_u64("num_ops", enc.num_ops); T.append_u64("num_mem_cells", enc.num_mem_cells);
+  append_poly_commitment(T, "comm_comb_ops", enc.comm_comb_ops);
+  append_poly_commitment(T, "comm_comb_mem", enc.comm_comb_mem);
+
+  R1CSProof sat;
+  std::vector<Fq> rx, ry;
+  r1cs_prove(ctx, inst, d_vars, input, *gens.gens_r1cs_sat, T, tape, sat, rx, ry);
+
+  const DenseView dv(enc);
+  const size_t N = dv.N, cells = dv.cells;
+  const size_t lgN = log2_ceil(N), lgC = log2_ceil(cells);
+  DevBuf<u256> d_chal(64), eq_small(2 * ((size_t)1 << ((std::max(lgN + 4, lgC + 1) + 1) / 2)) + 8);
+
+  // ---- inst.evaluate(rx, ry) (r1cs.rs:300-303 -> multi_evaluate sparse_mlpoly.rs:440-452)
+  auto t0 = std::chrono::steady_clock::now();
+  Fq inst_evals[3];
+  {
+    DevBuf<u256> trx((size_t)1 << rx.size()), try_((size_t)1 << ry.size());
+    dev::h2d(d_chal.p, rx.data(), rx.size() * sizeof(u256), ctx.stream);
+    dev::eq_evals(trx.p, d_chal.p, (int)rx.size(), eq_small.p, ctx.stream);
+    dev::h2d(d_chal.p + 32, ry.data(), ry.size() * sizeof(u256), ctx.stream);
+    dev::eq_evals(try_.p, d_chal.p + 32, (int)ry.size(), eq_small.p, ctx.stream);
+    for (int m = 0; m < 3; m++)
+      dev::sparse_eval3(ctx.small.p + 40 + m, inst.M[m].coo_row.p, inst.M[m].coo_col.p, inst.M[m].coo_val.p, inst.M[m].row.size(), trx.p, try_.p, ctx.red.p, ctx.stream);
+    ctx.get_small(40, inst_evals, 3);
+  }
+  T.append_scalar("Ar_claim", inst_evals[0]);
+  T.append_scalar("Br_claim", inst_evals[1]);
+  T.append_scalar("Cr_claim", inst_evals[2]);
+  mark("eval_sparse_polys", t0);
+
+  // ---- R1CSEvalProof::prove -> SparseMatPolyEvalProof::prove (sparse_mlpoly.rs:1447-1514)
+  auto t_eval = std::chrono::steady_clock::now();
+  SparseMatPolyEvalProof ep;
+  T.append_protocol_name("Sparse polynomial evaluation proof");
+  // equalize (sparse_mlpoly.rs:1429-1445): left-pad the shorter point with zeros
+  std::vector<Fq> rx_ext = rx, ry_ext = ry;
+  if (rx.size() < ry.size()) rx_ext.insert(rx_ext.begin(), ry.size() - rx.size(), Fq::zero());
+  if (ry.size() < rx.size()) ry_ext.insert(ry_ext.begin(), rx.size() - ry.size(), Fq::zero());
+  DevBuf<u256> mem_rx(cells), mem_ry(cells);
+  dev::h2d(d_chal.p, rx_ext.data(), rx_ext.size() * sizeof(u256), ctx.stream);
+  dev::eq_evals(mem_rx.p, d_chal.p, (int)rx_ext.size(), eq_small.p, ctx.stream);
+  dev::h2d(d_chal.p + 32, ry_ext.data(), ry_ext.size() * sizeof(u256), ctx.stream);
+  dev::eq_evals(mem_ry.p, d_chal.p + 32, (int)ry_ext.size(), eq_small.p, ctx.stream);
+  // derefs (sparse_mlpoly.rs:507-512): comb = row_ops_val[3] | col_ops_val[3] | zero pad
+  DevBuf<u256> derefs(8 * N);
+  dev::dzero(derefs.p + 6 * N, 2 * N * sizeof(u256), ctx.stream);
+  u256 *row_val[3], *col_val[3];
+  for (int m = 0; m < 3; m++) {
+    row_val[m] = derefs.p + (size_t)m * N; col_val[m] = derefs.p + (size_t)(3 + m) * N;
+    dev::gather(row_val[m], mem_rx.p, enc.row.ops_addr_idx[m].p, N, ctx.stream);
+    dev::gather(col_val[m], mem_ry.p, enc.col.ops_addr_idx[m].p, N, ctx.stream);
+  }
+  {
+    auto tc = std::chrono::steady_clock::now();
+    commit_poly(ctx, derefs.p, 8 * N, gens.gens_derefs, ep.comm_derefs);
+    T.append_message("derefs_commitment", "begin_derefs_commitment");  // sparse_mlpoly.rs:213-219
+    append_poly_commitment(T, "comm_poly_row_col_ops_val", ep.comm_derefs);
+    T.append_message("derefs_commitment", "end_derefs_commitment");
+    mark("commit_nondet_witness", tc);
+  }
+  std::vector<Fq> r_mem_check = T.challenge_vector("challenge_r_hash", 2);
+
+  // ---- build_layered_network: hash layers (sparse_mlpoly.rs:529-604) written straight into layer 0 of the 16 product circuits
+  auto tb = std::chrono::steady_clock::now();
+  dev::h2d(d_chal.p, r_mem_check.data(), 2 * sizeof(u256), ctx.stream);
+  struct Side { ProdCircuit init, audit, read[3], write[3]; } S[2];
+  for (int side = 0; side < 2; side++) {
+    Side& s = S[side];
+    const u256* mem = side == 0 ? mem_rx.p : mem_ry.p;
+    s.init.alloc(cells); s.audit.alloc(cells);
+    dev::spark_hash(s.init.layer(0), cells, nullptr, mem, nullptr, 0, d_chal.p, ctx.stream);
+    dev::spark_hash(s.audit.layer(0), cells, nullptr, mem, side == 0 ? dv.row_audit : dv.col_audit, 0, d_chal.p, ctx.stream);
+    for (int m = 0; m < 3; m++) {
+      s.read[m].alloc(N); s.write[m].alloc(N);
+      const u256* addr = side == 0 ? dv.row_addr[m] : dv.col_addr[m];
+      const u256* ts = side == 0 ? dv.row_ts[m] : dv.col_ts[m];
+      const u256* val = side == 0 ? row_val[m] : col_val[m];
+      dev::spark_hash(s.read[m].layer(0), N, addr, val, ts, 0, d_chal.p, ctx.stream);
+      dev::spark_hash(s.write[m].layer(0), N, addr, val, ts, 1, d_chal.p, ctx.stream);
+    }
+    s.init.build(ctx); s.audit.build(ctx);
+    for (int m = 0; m < 3; m++) { s.read[m].build(ctx); s.write[m].build(ctx); }
+  }
+  ctx.sync();
+  mark("build_layered_network", tb);
+
+  // ---- PolyEvalNetworkProof::prove (sparse_mlpoly.rs:1318-1354)
+  auto tn = std::chrono::steady_clock::now();
+  T.append_protocol_name("Sparse polynomial evaluation proof");
+  ProductLayerProof& pl = ep.proof_prod_layer;
+  T.append_protocol_name("Sparse polynomial product layer proof");  // ProductLayerProof::prove (sparse_mlpoly.rs:1035-1226)
+  for (int side = 0; side < 2; side++) {
+    Side& s = S[side];
+    Fq init = circuit_evaluate(ctx, s.init), audit = circuit_evaluate(ctx, s.audit);
+    std::vector<Fq> read(3), write(3);
+    for (int m = 0; m < 3; m++) { read[m] = circuit_evaluate(ctx, s.read[m]); write[m] = circuit_evaluate(ctx, s.write[m]); }
+    Fq ws = write[0] * write[1] * write[2], rs = read[0] * read[1] * read[2];
+    if (!(init * ws == rs * audit)) throw SpError(SP_ERR_INTERNAL, "memory-check subset test failed (sparse_mlpoly.rs:1060)");
+    const char* li = side == 0 ? "claim_row_eval_init" : "claim_col_eval_init";
+    const char* lr = side == 0 ? "claim_row_eval_read" : "claim_col_eval_read";
+    const char* lw = side == 0 ? "claim_row_eval_write" : "claim_col_eval_write";
+    const char* la = side == 0 ? "claim_row_eval_audit" : "claim_col_eval_audit";
+    T.append_scalar(li, init); append_scalar_vec(T, lr, read); append_scalar_vec(T, lw, write); T.append_scalar(la, audit);
+    if (side == 0) { pl.row_init = init; pl.row_read = read; pl.row_write = write; pl.row_audit = audit; }
+    else { pl.col_init = init; pl.col_read = read; pl.col_write = write; pl.col_audit = audit; }
+  }
+  // dot-product circuits: clones of (row_ops_val, col_ops_val, val), split in halves (sparse_mlpoly.rs:1090-1117)
+  DevBuf<u256> dotp_buf(9 * N);
+  std::vector<DotpCircuit> dotps;
+  for (int m = 0; m < 3; m++) {
+    u256* l = dotp_buf.p + (size_t)(3 * m) * N; u256* r = l + N; u256* wgt = r + N;
+    dev::d2d(l, row_val[m], N * sizeof(u256), ctx.stream);
+    dev::d2d(r, col_val[m], N * sizeof(u256), ctx.stream);
+    dev::d2d(wgt, dv.val[m], N * sizeof(u256), ctx.stream);
+    size_t h = N / 2;
+    dev::dot3(ctx.small.p + 48, l, r, wgt, h, ctx.red.p, ctx.stream);
+    dev::dot3(ctx.small.p + 49, l + h, r + h, wgt + h, h, ctx.red.p, ctx.stream);
+    Fq lr2[2];
+    ctx.get_small(48, lr2, 2);
+    T.append_scalar("claim_eval_dotp_left", lr2[0]);
+    T.append_scalar("claim_eval_dotp_right", lr2[1]);
+    if (!(lr2[0] + lr2[1] == inst_evals[m])) throw SpError(SP_ERR_INTERNAL, "dot-product circuit does not evaluate to the claimed matrix evaluation");
+    pl.eval_dotp_left.push_back(lr2[0]); pl.eval_dotp_right.push_back(lr2[1]);
+    dotps.push_back(DotpCircuit{l, r, wgt, h});
+    dotps.push_back(DotpCircuit{l + h, r + h, wgt + h, h});
+  }
+  std::vector<Fq> rand_ops, rand_mem;
+  {
+    std::vector<ProdCircuit*> prods = {&S[0].read[0], &S[0].read[1], &S[0].read[2], &S[0].write[0], &S[0].write[1], &S[0].write[2],
+                                       &S[1].read[0], &S[1].read[1], &S[1].read[2], &S[1].write[0], &S[1].write[1], &S[1].write[2]};
+    batched_prove(ctx, prods, dotps, T, pl.proof_ops, rand_ops);
+    std::vector<ProdCircuit*> mems = {&S[0].init, &S[0].audit, &S[1].init, &S[1].audit};
+    std::vector<DotpCircuit> none;
+    batched_prove(ctx, mems, none, T, pl.proof_mem, rand_mem);
+  }
+
+  // ---- HashLayerProof::prove (sparse_mlpoly.rs:722-835)
+  HashLayerProof& hl = ep.proof_hash_layer;
+  T.append_protocol_name("Sparse polynomial hash layer proof");
+  {
+    DevBuf<u256> eq_ops(N), eq_mem(cells);
+    dev::h2d(d_chal.p, rand_ops.data(), rand_ops.size() * sizeof(u256), ctx.stream);
+    dev::eq_evals(eq_ops.p, d_chal.p, (int)rand_ops.size(), eq_small.p, ctx.stream);
+    dev::h2d(d_chal.p + 32, rand_mem.data(), rand_mem.size() * sizeof(u256), ctx.stream);
+    dev::eq_evals(eq_mem.p, d_chal.p + 32, (int)rand_mem.size(), eq_small.p, ctx.stream);
+    // 21 evaluations at rand_ops, 2 at rand_mem
+    std::vector<const u256*> tabs;
+    for (int m = 0; m < 3; m++) tabs.push_back(row_val[m]);
+    for (int m = 0; m < 3; m++) tabs.push_back(col_val[m]);
+    for (int m = 0; m < 3; m++) tabs.push_back(dv.row_addr[m]);
+    for (int m = 0; m < 3; m++) tabs.push_back(dv.row_ts[m]);
+    for (int m = 0; m < 3; m++) tabs.push_back(dv.col_addr[m]);
+    for (int m = 0; m < 3; m++) tabs.push_back(dv.col_ts[m]);
+    for (int m = 0; m < 3; m++) tabs.push_back(dv.val[m]);
+    dev::dot_many(ctx.small.p + 64, tabs.data(), (int)tabs.size(), eq_ops.p, N, ctx.red.p, ctx.stream);
+    const u256* mt[2] = {dv.row_audit, dv.col_audit};
+    dev::dot_many(ctx.small.p + 64 + 21, mt, 2, eq_mem.p, cells, ctx.red.p, ctx.stream);
+    std::vector<Fq> ev(23);
+    ctx.get_small(64, ev.data(), 23);
+    hl.derefs_row.assign(ev.begin(), ev.begin() + 3);
+    hl.derefs_col.assign(ev.begin() + 3, ev.begin() + 6);
+    hl.row_addr.assign(ev.begin() + 6, ev.begin() + 9);
+    hl.row_read_ts.assign(ev.begin() + 9, ev.begin() + 12);
+    hl.col_addr.assign(ev.begin() + 12, ev.begin() + 15);
+    hl.col_read_ts.assign(ev.begin() + 15, ev.begin() + 18);
+    hl.eval_val.assign(ev.begin() + 18, ev.begin() + 21);
+    hl.row_audit_ts = ev[21]; hl.col_audit_ts = ev[22];
+  }
+  Cp dummy;
+  {  // DerefsEvalProof::prove (sparse_mlpoly.rs:125-149, prove_single :80-123)
+    T.append_protocol_name("Derefs evaluation proof");
+    std::vector<Fq> evals = hl.derefs_row;
+    evals.insert(evals.end(), hl.derefs_col.begin(), hl.derefs_col.end());
+    evals.resize(next_pow2(evals.size()), Fq::zero());
+    T.append_scalars("evals_ops_val", evals);
+    std::vector<Fq> ch = T.challenge_vector("challenge_combine_n_to_one", log2_ceil(evals.size()));
+    Fq joint = bound_bot_all(evals, ch)[0];
+    std::vector<Fq> r_joint = ch;
+    r_joint.insert(r_joint.end(), rand_ops.begin(), rand_ops.end());
+    T.append_scalar("joint_claim_eval", joint);
+    polyeval_prove(ctx, derefs.p, nullptr, r_joint, joint, nullptr, gens.gens_derefs, T, tape, hl.proof_derefs, dummy);
+  }
+  {  // ops decommitment (sparse_mlpoly.rs:766-797)
+    std::vector<Fq> evals;
+    for (auto* v : {&hl.row_addr, &hl.row_read_ts, &hl.col_addr, &hl.col_read_ts, &hl.eval_val}) evals.insert(evals.end(), v->begin(), v->end());
+    evals.resize(next_pow2(evals.size()), Fq::zero());
+    T.append_scalars("claim_evals_ops", evals);
+    std::vector<Fq> ch = T.challenge_vector("challenge_combine_n_to_one", log2_ceil(evals.size()));
+    Fq joint = bound_bot_all(evals, ch)[0];
+    std::vector<Fq> r_joint = ch;
+    r_joint.insert(r_joint.end(), rand_ops.begin(), rand_ops.end());
+    T.append_scalar("joint_claim_eval_ops", joint);
+    polyeval_prove(ctx, enc.comb_ops.p, nullptr, r_joint, joint, nullptr, gens.gens_ops, T, tape, hl.proof_ops, dummy);
+  }
+  {  // mem decommitment (sparse_mlpoly.rs:799-824)
+    std::vector<Fq> evals = {hl.row_audit_ts, hl.col_audit_ts};
+    T.append_scalars("claim_evals_mem", evals);
+    std::vector<Fq> ch = T.challenge_vector("challenge_combine_two_to_one", 1);
+    Fq joint = bound_bot_all(evals, ch)[0];
+    std::vector<Fq> r_joint = ch;
+    r_joint.insert(r_joint.end(), rand_mem.begin(), rand_mem.end());
+    T.append_scalar("joint_claim_eval_mem", joint);
+    polyeval_prove(ctx, enc.comb_mem.p, nullptr, r_joint, joint, nullptr, gens.gens_mem, T, tape, hl.proof_mem, dummy);
+  }
+  mark("evalproof_layered_network", tn);
+  mark("R1CSEvalProof::prove", t_eval);
+  mark("SNARK::prove", t_start);
+
+  // bincode(SNARK { r1cs_sat_proof, inst_evals, r1cs_eval_proof }) (lib.rs:313-317)
+  sat.ser(w);
+  for (int m = 0; m < 3; m++) w.scalar(inst_evals[m]);
+  ep.ser(w);
+}
+
 }  // namespace sp

@@ -1,6 +1,7 @@
 // spartan_b200 — SNARK path: SPARK sparse-polynomial commitment (src/sparse_mlpoly.rs, src/product_tree.rs) driven on the device.
 #pragma once
 #include "prover.hpp"
+#include <chrono>
 
 namespace sp {
 

@@ -1,0 +1,103 @@
+"""GPU parity for the SNARK path (BASELINE.json configs[1]/[4] shape): SNARK::encode commitments and SNARK::prove proof bytes diffed
+against the oracle at sizes the oracle proves in seconds; at 2^16 / 2^20 the oracle's SNARK::verify must accept the GPU proof and the
+published structural lengths (README.md:362,371,374) must hold.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.spartan_ref import core as oc  # noqa: E402
+from oracle.spartan_ref import protocol as pr  # noqa: E402
+from oracle.spartan_ref import r1cs, spark  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import spartan_b200 as m
+    m.default_context()
+    return m
+
+
+def parse_commitment(b):
+    vals = [int.from_bytes(b[8 * i:8 * i + 8], "little") for i in range(6)]
+    ops, pos = pr.deser(pr.PolyCommitment, b, 48)
+    mem, pos = pr.deser(pr.PolyCommitment, b, pos)
+    assert pos == len(b)
+    return spark.R1CSCommitment(vals[0], vals[1], vals[2], spark.SparseMatPolyCommitment(vals[3], vals[4], vals[5], ops, mem))
+
+
+@pytest.mark.parametrize("num_cons,num_vars,num_inputs,seed", [(16, 16, 3, 0), (256, 256, 10, 1), (1024, 1024, 10, 2), (64, 256, 7, 3), (512, 32, 5, 4), (2, 2, 1, 5)])
+def test_snark_bytes_match_oracle(sb, num_cons, num_vars, num_inputs, seed):
+    nz = num_cons
+    oi, ovars, oinputs = r1cs.Instance.produce_synthetic_r1cs(num_cons, num_vars, num_inputs, seed)
+    ogens = spark.SNARKGens(num_cons, num_vars, num_inputs, nz)
+    ocomm, odecomm = spark.SNARK.encode(oi, ogens)
+    oproof = spark.SNARK.prove(oi, ocomm, odecomm, ovars, oinputs, ogens, oc.Transcript(b"snark_example"), r1cs.tape_seed(seed))
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(num_cons, num_vars, num_inputs, seed=seed)
+    gens = sb.SNARKGens(num_cons, num_vars, num_inputs, nz)
+    comm = sb.SNARK.encode(inst, gens)
+    assert comm.commitment_bytes() == ocomm.ser()
+    proof = sb.SNARK.prove(inst, comm, vars_, inputs, gens, b"snark_example", sb.tape_seed(seed))
+    want = oproof.ser()
+    assert len(proof.bytes) == len(want)
+    first = next((i for i in range(len(want)) if want[i] != proof.bytes[i]), None)
+    assert first is None, "first differing byte at %d of %d" % (first, len(want))
+    proof2 = sb.SNARK.prove(inst, comm, sb.DensePolynomial(vars_.limbs), inputs, gens, b"snark_example", sb.tape_seed(seed))
+    assert proof2.bytes == want
+    assert sb.SNARK.prove(inst, comm, vars_, inputs, gens, b"snark_example", sb.tape_seed(seed + 7)).bytes != want
+
+
+def test_snark_padded_constraints(sb):
+    """lib.rs:672-752 test_padded_constraints through the GPU prover, bytes equal to the oracle and accepted by its verifier"""
+    def s32(v):
+        return (v % oc.Q).to_bytes(32, "little")
+    num_cons, num_vars, num_inputs, nz = 1, 0, 3, 3
+    A = [(0, num_vars + 2, s32(1))]
+    B = [(0, num_vars + 2, s32(1))]
+    Cm = [(0, num_vars + 1, s32(1)), (0, num_vars, s32(-13)), (0, num_vars + 3, s32(-1))]
+    inst = sb.Instance.new(num_cons, num_vars, num_inputs, A, B, Cm)
+    vars_ = sb.Assignment([])
+    inputs = sb.Assignment([s32(16), s32(1), s32(2)])
+    assert inst.is_sat(vars_, inputs)
+    gens = sb.SNARKGens(num_cons, num_vars, num_inputs, nz)
+    comm = sb.SNARK.encode(inst, gens)
+    proof = sb.SNARK.prove(inst, comm, vars_, inputs, gens, b"snark_example", sb.tape_seed(0))
+    oi = r1cs.Instance.new(num_cons, num_vars, num_inputs, A, B, Cm)
+    ogens = spark.SNARKGens(num_cons, num_vars, num_inputs, nz)
+    ocomm, odecomm = spark.SNARK.encode(oi, ogens)
+    assert comm.commitment_bytes() == ocomm.ser()
+    oproof = spark.SNARK.prove(oi, ocomm, odecomm, oc.zeros(0), [16, 1, 2], ogens, oc.Transcript(b"snark_example"), r1cs.tape_seed(0))
+    assert proof.bytes == oproof.ser()
+    parsed, pos = pr.deser(spark.SNARK, proof.bytes)
+    assert pos == len(proof.bytes)
+    parsed.verify(ocomm, [16, 1, 2], oc.Transcript(b"snark_example"), ogens)
+
+
+@pytest.mark.parametrize("logn", [14, 20])
+def test_snark_large_accepted_by_oracle_verifier(sb, logn):
+    """BASELINE.json configs[1] (2^20 constraints / variables / non-zeros): the oracle's SNARK::verify accepts the GPU proof and the
+    proof has the reference's published structure: len_r1cs_sat_proof 47024, len_product_layer_proof 64712, len_r1cs_eval_proof 133720
+    (README.md:362,371,374)"""
+    n = 1 << logn
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(n, n, 10, seed=1)
+    gens = sb.SNARKGens(n, n, 10, n)
+    comm = sb.SNARK.encode(inst, gens)
+    proof = sb.SNARK.prove(inst, comm, vars_, inputs, gens, b"snark_example", sb.tape_seed(1))
+    parsed, pos = pr.deser(spark.SNARK, proof.bytes)
+    assert pos == len(proof.bytes)
+    if logn == 20:
+        assert len(pr.ser(parsed.r1cs_sat_proof)) == 47024
+        assert len(pr.ser(parsed.r1cs_eval_proof.poly_eval_network_proof.proof_prod_layer)) == 64712
+        assert len(pr.ser(parsed.r1cs_eval_proof)) == 133720
+    ocomm = parse_commitment(comm.commitment_bytes())
+    ogens = spark.SNARKGens(n, n, 10, n)
+    parsed.verify(ocomm, oc.to_ints(inputs.limbs), oc.Transcript(b"snark_example"), ogens)
+    # tampering is rejected
+    bad = bytearray(proof.bytes)
+    bad[len(bad) // 2] ^= 1
+    try:
+        tampered, _ = pr.deser(spark.SNARK, bytes(bad))
+        with pytest.raises((pr.ProofVerifyError, AssertionError)):
+            tampered.verify(ocomm, oc.to_ints(inputs.limbs), oc.Transcript(b"snark_example"), ogens)
+    except (AssertionError, ValueError):
+        pass
