@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of spartan_b200 (driver contract: see the task statement).
+
+metric   : R1CS constraints proved per second, SNARK::prove on Instance::produce_synthetic_r1cs (BASELINE.json `metric`)
+workload : BASELINE.json configs[1] — 2^20 constraints, 2^20 variables, 10 inputs, 2^20 non-zeros per matrix, one B200
+step     : one SNARK::prove (transcript creation + prove; gens, instance synthesis and SNARK::encode excluded, exactly what
+           /root/reference/benches/snark.rs:55-68 times)
+value    : inputs (the assignment) resident in HBM when the clock starts;   e2e: assignment in pinned HOST memory, copied to the device
+           inside the timed region, proof bytes copied back to the host
+N > 1    : one process per GPU (torchrun); every rank proves its own instance of the same size (independent proofs: no data-path
+           collective), value = N * constraints / max-over-ranks time          -> "scaling": "weak"
+--impl reference : the CPU restatement of the reference (oracle/, C loops under OpenMP on all host cores) on a bounded sample of the
+           same workload (SNARK::prove at 2^SAMPLE_LOG constraints); rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "R1CS constraints/sec (SNARK::prove, synthetic R1CS)"
+UNIT = "constraints/s"
+LOG_N = int(os.environ.get("SP_BENCH_LOGN", "20"))
+NUM_INPUTS = 10
+CPU_SAMPLE_LOG = int(os.environ.get("SP_BENCH_CPU_LOGN", "16"))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+
+    def __init__(self, gpu_index):
+        self.lines = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """CPU arm: the oracle's SNARK::prove (restatement of the reference; the Rust crate cannot be built here) on all host cores."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle.spartan_ref import core as oc, r1cs, spark
+    cores = int(oc.lib.oracle_max_threads())
+    oc.lib.oracle_set_threads(cores)
+    n = 1 << CPU_SAMPLE_LOG
+    inst, vars_arr, inputs = r1cs.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, 0)
+    gens = spark.SNARKGens(n, n, NUM_INPUTS, n)
+    comm, decomm = spark.SNARK.encode(inst, gens)
+
+    def step():
+        spark.SNARK.prove(inst, comm, decomm, vars_arr.copy(), inputs, gens, oc.Transcript(b"example"), r1cs.tape_seed(0))
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n / dt
+    sample = "SNARK::prove at 2^%d constraints/variables/non-zeros (bounded sample of the 2^%d workload), oracle C loops + Python protocol layer" % (CPU_SAMPLE_LOG, LOG_N)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs)", "data": "synthetic",
+        "config": {"workload": "SNARK::prove synthetic R1CS 2^%d cons/vars, 2^%d non-zero" % (LOG_N, LOG_N), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_leg(budget_s=20.0):
+    """bounded oracle run on the box's host cores, reported beside the GPU number (rank 0, N = 1 only)"""
+    from oracle.spartan_ref import core as oc, r1cs, spark
+    cores = int(oc.lib.oracle_max_threads())
+    oc.lib.oracle_set_threads(cores)
+    n = 1 << CPU_SAMPLE_LOG
+    inst, vars_arr, inputs = r1cs.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, 0)
+    gens = spark.SNARKGens(n, n, NUM_INPUTS, n)
+    comm, decomm = spark.SNARK.encode(inst, gens)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 2 or (time.perf_counter() - t0 < budget_s and reps < 5):
+        spark.SNARK.prove(inst, comm, decomm, vars_arr.copy(), inputs, gens, oc.Transcript(b"example"), r1cs.tape_seed(0))
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "SNARK::prove at 2^%d (oracle = CPU restatement of the reference; %d reps, %.2f s each)" % (CPU_SAMPLE_LOG, reps, dt)}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    from spartan_b200 import dist as sd
+    rank, world, local = sd.init("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    import spartan_b200 as sb
+    from spartan_b200 import api
+    ctx = sb.Context(local if world > 1 else 0)
+    n = 1 << LOG_N
+    # every rank proves its own instance (seed = rank): independent proofs, no data-path collective
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, seed=sd.rank_seed(rank), ctx=ctx)
+    gens = sb.SNARKGens(n, n, NUM_INPUTS, n, ctx=ctx)
+    comm = sb.SNARK.encode(inst, gens)
+    d_vars = sb.DensePolynomial(vars_.limbs, ctx=ctx)
+    pinned = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    pinned.numpy().view(np.uint64)[:] = vars_.limbs
+    host_vars = sb.Assignment.__new__(sb.Assignment)
+    host_vars.limbs = pinned.numpy().view(np.uint64)
+    seed = sb.tape_seed(sd.rank_seed(rank))
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda:%d" % (local if world > 1 else 0))  # > L2 (126 MB)
+
+    def barrier():
+        sd.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return sb.SNARK.prove(inst, comm, d_vars, inputs, gens, b"example", seed)
+
+    def step_e2e():
+        return sb.SNARK.prove(inst, comm, host_vars, inputs, gens, b"example", seed)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local if world > 1 else 0)
+    # ---- timed region 1: inputs resident ("value")
+    launches0 = sb.kernel_launches()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    per_step = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        api.timer_start(ctx)
+        proof = step_resident()
+        per_step.append(api.timer_stop_ms(ctx))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sb.kernel_launches() - launches0
+    t_res = sum(per_step) / 1e3
+    # ---- timed region 2: end to end through the public API with host buffers
+    step_e2e()
+    h0, d0 = api.io_bytes()
+    barrier()
+    per_step_e2e = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        api.timer_start(ctx)
+        proof = step_e2e()
+        per_step_e2e.append(api.timer_stop_ms(ctx))
+    barrier()
+    h1, d1 = api.io_bytes()
+    t_e2e = sum(per_step_e2e) / 1e3
+    t_res, t_e2e = sd.max_over_ranks([t_res, t_e2e])
+    # ---- roofline leg: CUDA-event timing of every kernel family over one more step (separate from the timed regions above)
+    roof = None
+    if rank == 0:
+        api.prof_enable(True)
+        step_resident()
+        rep = api.prof_report()
+        api.prof_enable(False)
+        pk, which = peaks()
+        tot = sum(v["ms"] for v in rep.values())
+        dom = max(rep.items(), key=lambda kv: kv[1]["ms"])
+        fold = rep.get("sc_fold_eval")
+
+        def rl(name, v):
+            ach = v["bytes"] / 1e9 / (v["ms"] / 1e3) if v["ms"] else 0.0
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                    "launches": v["launches"], "ms_per_step": v["ms"], "share_of_kernel_time": v["ms"] / tot if tot else None, "peak_source": which}
+        roof = rl(dom[0], dom[1])
+        roof["note"] = ("dominant kernel by time; msm_rows is integer-ALU bound (fixed-base ristretto255 comb, ~7 field muls per table lookup), its algorithmic bytes "
+                        "are only scalars+bases, so the HBM fraction is honestly small; see roofline_fold for the HBM-bound kernel named by BASELINE.json")
+        roof_fold = rl("sc_fold_eval", fold) if fold else None
+        kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
+    if rank != 0:
+        sd.finalize()
+        return
+    cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
+    out = {
+        "metric": METRIC, "value": sd.aggregate_throughput(n * args.steps, world, t_res), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 (8x32-bit limbs, 256-bit modular integer arithmetic)", "data": "synthetic",
+        "config": {"workload": "SNARK::prove synthetic R1CS 2^%d cons/vars, 2^%d non-zero, %d inputs (BASELINE.json configs[1])" % (LOG_N, LOG_N, NUM_INPUTS),
+                   "per_gpu": "one independent proof per GPU per step", "l2": "512 MiB buffer zeroed between timed iterations (L2 flush); working set ~2.5 GB >> 126 MB L2",
+                   "timed_region": "Transcript::new + SNARK::prove (benches/snark.rs:55-68); gens / instance / encode excluded", "timer": "CUDA events on the prover stream, max over ranks"},
+        "clocks": clocks,
+        "e2e": {"value": sd.aggregate_throughput(n * args.steps, world, t_e2e), "unit": UNIT, "ms_per_step": t_e2e / args.steps * 1e3, "h2d_bytes_per_step": (h1 - h0) // args.steps,
+                "d2h_bytes_per_step": (d1 - d0) // args.steps, "api": "spartan_b200.SNARK.prove -> sp_snark_prove (C ABI), assignment in pinned host memory"},
+        "gpu_launches": launches,
+        "proof_bytes": len(proof.bytes),
+        "roofline": roof, "roofline_fold": roof_fold, "kernels_ms_per_step": kernels,
+        "phases_ms": {k: round(v, 3) for k, v in ctx.timings().items()},
+        "cpu_baseline": cpu,
+        "reference_published": {"value": 2 ** 20 / 39.1297568, "unit": UNIT, "what": "README.md:375 SNARK::prove 2^20 on one core of an i7-1065G7 (other hardware)"},
+    }
+    print(json.dumps(out), flush=True)
+    sd.finalize()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
