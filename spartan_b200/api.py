@@ -7,7 +7,7 @@ import zlib
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libspartan_b200.so")
+_LIB_PATH = os.path.join(_HERE, "libspartan_b200%s.so" % os.environ.get("SP_LIB_TAG", ""))  # SP_LIB_TAG: tuning builds only
 
 SP_OK, SP_ERR_NO_DEVICE, SP_ERR_CUDA, SP_ERR_INVALID_ARG, SP_ERR_INVALID_INDEX, SP_ERR_INVALID_SCALAR, SP_ERR_INVALID_INPUTS, SP_ERR_INTERNAL = range(8)
 

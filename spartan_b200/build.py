@@ -5,13 +5,18 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libspartan_b200.so")
+TAG = os.environ.get("SP_BUILD_TAG", "")
+# defaults chosen on the B200 (profiles/r01_tuning.md): out-of-line field multiplications keep the fused kernels inside the instruction cache,
+# 2 CTAs of 256 threads per SM for the sumcheck kernels, <= 80 registers for the MSM kernel
+DEFAULT_FLAGS = "-DSP_NI_FQ -DSP_NI_FP -DSP_SC_LB=2 -DSP_MSM_LB=6"
+EXTRA = os.environ.get("SP_BUILD_FLAGS", DEFAULT_FLAGS).split()
+OUT = os.path.join(HERE, "libspartan_b200%s.so" % TAG)
 NVCC = os.environ.get("SP_NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU = ["kernels.cu"]
+CU = ["kernels.cu", "kernels_sc.cu"]
 CPP = ["prover.cpp", "snark.cpp", "capi.cpp"]
-HDR = ["field.cuh", "curve.cuh", "dev.hpp", "host.hpp", "engine.hpp", "prover.hpp", "snark.hpp", os.path.join("..", "..", "include", "spartan_b200.h")]
+HDR = ["field.cuh", "curve.cuh", "kcommon.cuh", "dev.hpp", "host.hpp", "engine.hpp", "prover.hpp", "snark.hpp", os.path.join("..", "..", "include", "spartan_b200.h")]
 
 
 def _stale(target, deps):
@@ -22,20 +27,20 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, "build" + TAG), exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HDR]
     objs = []
     procs = []
     for f in CU:
-        o = os.path.join(HERE, "build", f + ".o")
+        o = os.path.join(HERE, "build" + TAG, f + ".o")
         objs.append(o)
         if force or _stale(o, [os.path.join(CSRC, f)] + hdrs):
-            cmd = [NVCC, "-ccbin", CXX] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, f), "-o", o]
+            cmd = [NVCC, "-ccbin", CXX] + ARCH + EXTRA + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, f), "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             procs.append((cmd, subprocess.Popen(cmd)))
     for f in CPP:
-        o = os.path.join(HERE, "build", f + ".o")
+        o = os.path.join(HERE, "build" + TAG, f + ".o")
         objs.append(o)
         if force or _stale(o, [os.path.join(CSRC, f)] + hdrs):
             cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-c", os.path.join(CSRC, f), "-o", o]

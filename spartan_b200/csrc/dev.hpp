@@ -23,6 +23,11 @@ void stream_destroy(cudaStream_t s);
 void stream_sync(cudaStream_t s);
 void* dmalloc(size_t bytes);
 void dfree(void* p);
+// size-bucketed caching allocator on top of cudaMalloc: a prove call allocates the same multi-hundred-MB buffers every time, and
+// cudaMalloc / cudaFree (which synchronises the device) would otherwise cost milliseconds per proof
+void* pool_alloc(size_t bytes);
+void pool_free(void* p);
+void pool_trim();   // return every cached block to the driver
 void* hmalloc_pinned(size_t bytes);
 void hfree_pinned(void* p);
 void h2d(void* d, const void* h, size_t bytes, cudaStream_t s);

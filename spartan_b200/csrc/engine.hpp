@@ -26,8 +26,8 @@ struct DevBuf {  // owning device allocation
   DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
   ~DevBuf() { release(); }
-  void alloc(size_t count) { release(); p = (T*)dev::dmalloc(count * sizeof(T)); n = count; }
-  void release() { if (p) dev::dfree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) { release(); p = (T*)dev::pool_alloc(count * sizeof(T)); n = count; }
+  void release() { if (p) dev::pool_free(p); p = nullptr; n = 0; }
 };
 
 struct Ctx {

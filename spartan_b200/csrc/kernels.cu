@@ -15,39 +15,29 @@
 #include <cuda_runtime.h>
 #include <stdexcept>
 #include <string>
+#include <map>
+#include <mutex>
 #include <atomic>
 #include <vector>
 #include "dev.hpp"
+#include "kcommon.cuh"
 
 namespace sp {
 namespace dev {
 
-static std::atomic<unsigned long long> g_launches{0};
-#define SP_LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+std::atomic<unsigned long long> g_launches{0};
 unsigned long long launch_count() { return g_launches.load(); }
 static std::atomic<unsigned long long> g_h2d{0}, g_d2h{0};
 void io_bytes(unsigned long long* h2d_b, unsigned long long* d2h_b) { *h2d_b = g_h2d.load(); *d2h_b = g_d2h.load(); }
 
 // ---- per-kernel-family CUDA-event profiler (bench.py roofline leg).  Off by default: one branch per wrapper.
-struct ProfRec { const char* name; cudaEvent_t a, b; double bytes; };
-static bool g_prof = false;
-static std::vector<ProfRec> g_recs;
+bool g_prof = false;
+std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_event_pool;
-static cudaEvent_t prof_event() {
+cudaEvent_t prof_event() {
   if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-struct ProfScope {
-  bool on; size_t idx; cudaStream_t s;
-  ProfScope(const char* name, double bytes, cudaStream_t st) : on(g_prof), idx(0), s(st) {
-    if (!on) return;
-    ProfRec r{name, prof_event(), prof_event(), bytes};
-    cudaEventRecord(r.a, s);
-    idx = g_recs.size();
-    g_recs.push_back(r);
-  }
-  ~ProfScope() { if (on) cudaEventRecord(g_recs[idx].b, s); }
-};
 void prof_enable(bool on) {
   g_prof = on;
   for (auto& r : g_recs) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
@@ -85,6 +75,51 @@ void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
 void stream_sync(cudaStream_t s) { ck(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
 void* dmalloc(size_t b) { void* p = nullptr; ck(cudaMalloc(&p, b ? b : 16), "cudaMalloc"); return p; }
 void dfree(void* p) { if (p) cudaFree(p); }
+namespace {
+std::mutex g_pool_mu;
+std::multimap<std::pair<int, size_t>, void*> g_pool_free;  // (device, rounded size) -> cached block
+std::map<void*, std::pair<int, size_t>> g_pool_live;       // block -> (device, rounded size)
+size_t pool_round(size_t b) {
+  if (b < 256) b = 256;
+  if (b <= (1u << 20)) { size_t r = 256; while (r < b) r <<= 1; return r; }
+  const size_t g = 2u << 20;                   // 2 MiB granularity above 1 MiB
+  return (b + g - 1) / g * g;
+}
+}  // namespace
+void* pool_alloc(size_t bytes) {
+  size_t r = pool_round(bytes);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_pool_free.find({dev, r});
+  void* p;
+  if (it != g_pool_free.end()) { p = it->second; g_pool_free.erase(it); }
+  else {
+    cudaError_t e = cudaMalloc(&p, r);
+    if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+      cudaGetLastError();
+      for (auto& kv : g_pool_free) cudaFree(kv.second);
+      g_pool_free.clear();
+      ck(cudaMalloc(&p, r), "cudaMalloc");
+    }
+  }
+  g_pool_live[p] = {dev, r};
+  return p;
+}
+void pool_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_pool_live.find(p);
+  if (it == g_pool_live.end()) { cudaFree(p); return; }
+  g_pool_free.insert({it->second, p});
+  g_pool_live.erase(it);
+}
+void pool_trim() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  cudaDeviceSynchronize();
+  for (auto& kv : g_pool_free) cudaFree(kv.second);
+  g_pool_free.clear();
+}
 void* hmalloc_pinned(size_t b) { void* p = nullptr; ck(cudaMallocHost(&p, b ? b : 16), "cudaMallocHost"); return p; }
 void hfree_pinned(void* p) { if (p) cudaFreeHost(p); }
 void h2d(void* d, const void* h, size_t b, cudaStream_t s) { g_h2d += b; if (b) ck(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s), "h2d"); }
@@ -106,182 +141,7 @@ float event_elapsed_ms(void* a, void* b) {
 }
 void event_destroy(void* ev) { cudaEventDestroy((cudaEvent_t)ev); }
 
-// =============================================================================================== helpers
-__device__ __forceinline__ u256 ld256(const u256* p) {  // two 128-bit loads
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = q[0], b = q[1];
-  u256 r;
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
-}
-__device__ __forceinline__ u256 ld256_ro(const u256* p) {  // read-only path for data never written by the kernel
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
-  u256 r;
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
-}
-__device__ __forceinline__ u256 ld256_cg(const u256* p) {  // L2-coherent loads for cross-block partial sums
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldcg(q), b = __ldcg(q + 1);
-  u256 r;
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
-}
-__device__ __forceinline__ void st256(u256* p, const u256& x) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
-}
-__device__ __forceinline__ u256 shfl_down_256(const u256& x, int delta) {
-  u256 r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], delta);
-  return r;
-}
-__device__ __forceinline__ u256 warp_sum_fq(u256 x) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) x = fq_add(x, shfl_down_256(x, d));
-  return x;
-}
-
-// Block-wide sum of NV field values per thread, then cross-block finalisation by the last block to arrive.
-// partials: [gridDim.y][gridDim.x][NV]; counters: [gridDim.y] zero-initialised, self-resetting.
-template <int NV>
-__device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* partials, unsigned int* counters, u256* out, int out_stride) {
-  __shared__ u256 sm[32][NV];
-  __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-#pragma unroll
-  for (int k = 0; k < NV; k++) {
-    u256 s = warp_sum_fq(acc[k]);
-    if (lane == 0) sm[warp][k] = s;
-  }
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-      u256 s = lane < nwarps ? sm[lane][k] : fq_zero();
-      s = warp_sum_fq(s);
-      if (lane == 0) st256(&partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NV + k], s);
-    }
-  }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned int ticket = atomicAdd(&counters[blockIdx.y], 1u);
-    is_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    if (warp == 0) {
-#pragma unroll
-      for (int k = 0; k < NV; k++) {
-        u256 s = fq_zero();
-        for (unsigned int b = lane; b < gridDim.x; b += 32) s = fq_add(s, ld256_cg(&partials[((size_t)blockIdx.y * gridDim.x + b) * NV + k]));
-        s = warp_sum_fq(s);
-        if (lane == 0) st256(&out[(size_t)blockIdx.y * out_stride + k], s);
-      }
-      if (lane == 0) counters[blockIdx.y] = 0;
-    }
-  }
-}
-
-// =============================================================================================== sumcheck rounds
-#define SC_MAX_INST 24
-struct ScBatch {
-  ScInst inst[SC_MAX_INST];
-};
-
-template <int KIND>
-__device__ __forceinline__ u256 sc_comb(const u256& a, const u256& b, const u256& c, const u256& d) {
-  if (KIND == SC_QUAD) return fq_mul(a, b);                        // r1csproof.rs:122-123
-  if (KIND == SC_CUBIC3) return fq_mul(fq_mul(a, b), c);           // product_tree.rs:283-286
-  return fq_mul(a, fq_sub(fq_mul(b, c), d));                       // r1csproof.rs:87-91
-}
-
-template <int KIND>
-__device__ __forceinline__ void sc_accumulate(u256 (&acc)[3], const u256 (&lo)[4], const u256 (&hi)[4]) {
-  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
-  u256 x[4], dl[4];
-#pragma unroll
-  for (int t = 0; t < 4; t++) { x[t] = fq_zero(); dl[t] = fq_zero(); }
-  // t = 0 : low halves                                             (sumcheck.rs:463 / :627)
-  acc[0] = fq_add(acc[0], sc_comb<KIND>(lo[0], lo[1], lo[2], lo[3]));
-  // t = 2 : 2*hi - lo = hi + (hi - lo)                              (sumcheck.rs:466-468 / :630-639)
-#pragma unroll
-  for (int t = 0; t < NT; t++) { dl[t] = fq_sub(hi[t], lo[t]); x[t] = fq_add(hi[t], dl[t]); }
-  acc[1] = fq_add(acc[1], sc_comb<KIND>(x[0], x[1], x[2], x[3]));
-  if (KIND != SC_QUAD) {
-    // t = 3 : previous point + (hi - lo)                            (sumcheck.rs:642-651)
-#pragma unroll
-    for (int t = 0; t < NT; t++) x[t] = fq_add(x[t], dl[t]);
-    acc[2] = fq_add(acc[2], sc_comb<KIND>(x[0], x[1], x[2], x[3]));
-  }
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(256) k_sc_eval(ScBatch batch, size_t len, u256* partials, unsigned int* counters, u256* out) {
-  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
-  const ScInst& in = batch.inst[blockIdx.y];
-  const size_t half = len >> 1;
-  u256 acc[3] = {fq_zero(), fq_zero(), fq_zero()};
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
-    u256 lo[4], hi[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) { lo[t] = fq_zero(); hi[t] = fq_zero(); }
-#pragma unroll
-    for (int t = 0; t < NT; t++) { lo[t] = ld256(in.t[t] + i); hi[t] = ld256(in.t[t] + i + half); }
-    sc_accumulate<KIND>(acc, lo, hi);
-  }
-  block_reduce_finish<3>(acc, partials, counters, out, 3);
-}
-
-// Fused: bind the top variable with r (len -> len/2) and evaluate the next round's polynomial on the folded table.
-// Thread i owns elements {i, i+len/4, i+len/2, i+3len/4} of every table: in-place update is race-free.
-template <int KIND>
-__global__ void __launch_bounds__(256) k_sc_fold_eval(ScBatch batch, size_t len, const u256* __restrict__ rp, u256* partials,
-                                                       unsigned int* counters, u256* out) {
-  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
-  const ScInst& in = batch.inst[blockIdx.y];
-  const size_t half = len >> 1, quarter = len >> 2;
-  const u256 r = ld256_ro(rp);
-  u256 acc[3] = {fq_zero(), fq_zero(), fq_zero()};
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quarter; i += (size_t)gridDim.x * blockDim.x) {
-    u256 lo[4], hi[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) { lo[t] = fq_zero(); hi[t] = fq_zero(); }
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-      u256 a0 = ld256(in.t[t] + i), a1 = ld256(in.t[t] + i + half);
-      u256 b0 = ld256(in.t[t] + i + quarter), b1 = ld256(in.t[t] + i + quarter + half);
-      lo[t] = fq_add(a0, fq_mul(r, fq_sub(a1, a0)));   // dense_mlpoly.rs:218
-      hi[t] = fq_add(b0, fq_mul(r, fq_sub(b1, b0)));
-      if (t == 2) {
-        if (in.write_c) { st256(in.c_out + i, lo[t]); st256(in.c_out + i + quarter, hi[t]); }
-      } else {
-        st256(in.t[t] + i, lo[t]); st256(in.t[t] + i + quarter, hi[t]);
-      }
-    }
-    sc_accumulate<KIND>(acc, lo, hi);
-  }
-  block_reduce_finish<3>(acc, partials, counters, out, 3);
-}
-
-struct FoldBatch {
-  u256* t[64];
-};
-__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const u256* __restrict__ rp) {
-  const size_t half = len >> 1;
-  u256* T = tabs.t[blockIdx.y];
-  const u256 r = ld256_ro(rp);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
-    u256 a0 = ld256(T + i), a1 = ld256(T + i + half);
-    st256(T + i, fq_add(a0, fq_mul(r, fq_sub(a1, a0))));
-  }
-}
-
-static unsigned int grid_for(size_t work, int threads, int per_sm) {
+unsigned int grid_for(size_t work, int threads, int per_sm) {
   size_t blocks = (work + threads - 1) / threads;
   size_t cap = (size_t)sm_count() * per_sm;
   if (blocks > cap) blocks = cap;
@@ -289,55 +149,6 @@ static unsigned int grid_for(size_t work, int threads, int per_sm) {
   return (unsigned int)blocks;
 }
 
-// scratch layout: [counters: 64 x u32][partials]
-static const size_t SC_MAX_BLOCKS = 148 * 4 + 64;
-size_t sc_scratch_bytes(int ninst) { return 256 + (size_t)ninst * SC_MAX_BLOCKS * 3 * sizeof(u256); }
-
-static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
-  if (ninst > SC_MAX_INST) throw std::runtime_error("spartan_b200: too many sumcheck instances in one batch");
-  for (int i = 0; i < ninst; i++) b.inst[i] = insts[i];
-}
-
-void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s) {
-  ProfScope ps("sc_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 32.0, s);
-  ScBatch b; fill_batch(b, insts, ninst);
-  unsigned int* counters = (unsigned int*)scratch;
-  u256* partials = (u256*)((char*)scratch + 256);
-  dim3 grid(grid_for(len / 2, 256, 2), ninst);
-  if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
-  switch (kind) {
-    case SC_QUAD: k_sc_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
-    case SC_CUBIC3: k_sc_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
-    default: k_sc_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
-  }
-  SP_LAUNCHED(); check("sc_eval");
-}
-void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256* d_r, u256* out, void* scratch, cudaStream_t s) {
-  ProfScope ps("sc_fold_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 48.0, s);
-  ScBatch b; fill_batch(b, insts, ninst);
-  unsigned int* counters = (unsigned int*)scratch;
-  u256* partials = (u256*)((char*)scratch + 256);
-  dim3 grid(grid_for(len / 4, 256, 2), ninst);
-  if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
-  switch (kind) {
-    case SC_QUAD: k_sc_fold_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
-    case SC_CUBIC3: k_sc_fold_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
-    default: k_sc_fold_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
-  }
-  SP_LAUNCHED(); check("sc_fold_eval");
-}
-void fold_top(u256* const* tables, int ntables, size_t len, const u256* d_r, cudaStream_t s) {
-  ProfScope ps("fold_top", (double)ntables * len * 48.0, s);
-  for (int base = 0; base < ntables; base += 64) {
-    FoldBatch fb; int n = ntables - base < 64 ? ntables - base : 64;
-    for (int i = 0; i < n; i++) fb.t[i] = tables[base + i];
-    dim3 grid(grid_for(len / 2, 256, 4), n);
-    k_fold_top<<<grid, 256, 0, s>>>(fb, len, d_r);
-    SP_LAUNCHED();
-  }
-  check("fold_top");
-}
-void fold_top_single(u256* table, size_t len, const u256* d_r, cudaStream_t s) { u256* t[1] = {table}; fold_top(t, 1, len, d_r, s); }
 
 // =============================================================================================== dense helpers
 // eq(r, .) table (dense_mlpoly.rs:68-84): out[i] = prod_j (bit_j(i) ? r_j : 1 - r_j), bit 0 of r = most significant bit of i.
@@ -663,8 +474,11 @@ void build_tables(ge_niels* table, const ge* G, size_t nbases, cudaStream_t s) {
 // grid = (chunks, L); block = 128 threads; a block covers COLS = 128*WPT/32 columns of one row.  Thread t handles column
 // t / (32/WPT) of the chunk and WPT consecutive 8-bit windows.  Signed digits in [-127,128]; zero digits are skipped
 // (vartime, like the reference's vartime_multiscalar_mul).  Partial sums are tree-reduced through shared memory.
+#ifndef SP_MSM_LB
+#define SP_MSM_LB 1
+#endif
 template <int WPT>
-__global__ void __launch_bounds__(128) k_msm_rows(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ scalars, size_t stride,
+__global__ void __launch_bounds__(128, SP_MSM_LB) k_msm_rows(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ scalars, size_t stride,
                                                   size_t R, const u256* __restrict__ blinds, size_t blind_base) {
   constexpr int GROUPS = MSM_WINDOWS / WPT;      // threads per column
   constexpr int COLS = 128 / GROUPS;             // columns per block

@@ -1,0 +1,157 @@
+// spartan_b200 — sumcheck-round kernels (K1/K2 of SURVEY.md §2b), their own translation unit so the two .cu files build in parallel.
+#include "kcommon.cuh"
+
+#ifndef SP_SC_LB
+#define SP_SC_LB 1
+#endif
+
+namespace sp {
+namespace dev {
+
+// =============================================================================================== sumcheck rounds
+#define SC_MAX_INST 24
+struct ScBatch {
+  ScInst inst[SC_MAX_INST];
+};
+
+template <int KIND>
+__device__ __forceinline__ u256 sc_comb(const u256& a, const u256& b, const u256& c, const u256& d) {
+  if (KIND == SC_QUAD) return fq_mul(a, b);                        // r1csproof.rs:122-123
+  if (KIND == SC_CUBIC3) return fq_mul(fq_mul(a, b), c);           // product_tree.rs:283-286
+  return fq_mul(a, fq_sub(fq_mul(b, c), d));                       // r1csproof.rs:87-91
+}
+
+template <int KIND>
+__device__ __forceinline__ void sc_accumulate(u256 (&acc)[3], const u256 (&lo)[4], const u256 (&hi)[4]) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  u256 x[4], dl[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) { x[t] = fq_zero(); dl[t] = fq_zero(); }
+  // t = 0 : low halves                                             (sumcheck.rs:463 / :627)
+  acc[0] = fq_add(acc[0], sc_comb<KIND>(lo[0], lo[1], lo[2], lo[3]));
+  // t = 2 : 2*hi - lo = hi + (hi - lo)                              (sumcheck.rs:466-468 / :630-639)
+#pragma unroll
+  for (int t = 0; t < NT; t++) { dl[t] = fq_sub(hi[t], lo[t]); x[t] = fq_add(hi[t], dl[t]); }
+  acc[1] = fq_add(acc[1], sc_comb<KIND>(x[0], x[1], x[2], x[3]));
+  if (KIND != SC_QUAD) {
+    // t = 3 : previous point + (hi - lo)                            (sumcheck.rs:642-651)
+#pragma unroll
+    for (int t = 0; t < NT; t++) x[t] = fq_add(x[t], dl[t]);
+    acc[2] = fq_add(acc[2], sc_comb<KIND>(x[0], x[1], x[2], x[3]));
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t len, u256* partials, unsigned int* counters, u256* out) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1;
+  u256 acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    u256 lo[4], hi[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { lo[t] = fq_zero(); hi[t] = fq_zero(); }
+#pragma unroll
+    for (int t = 0; t < NT; t++) { lo[t] = ld256(in.t[t] + i); hi[t] = ld256(in.t[t] + i + half); }
+    sc_accumulate<KIND>(acc, lo, hi);
+  }
+  block_reduce_finish<3>(acc, partials, counters, out, 3);
+}
+
+// Fused: bind the top variable with r (len -> len/2) and evaluate the next round's polynomial on the folded table.
+// Thread i owns elements {i, i+len/4, i+len/2, i+3len/4} of every table: in-place update is race-free.
+template <int KIND>
+__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, size_t len, const u256* __restrict__ rp, u256* partials,
+                                                       unsigned int* counters, u256* out) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1, quarter = len >> 2;
+  const u256 r = ld256_ro(rp);
+  u256 acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quarter; i += (size_t)gridDim.x * blockDim.x) {
+    u256 lo[4], hi[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { lo[t] = fq_zero(); hi[t] = fq_zero(); }
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      u256 a0 = ld256(in.t[t] + i), a1 = ld256(in.t[t] + i + half);
+      u256 b0 = ld256(in.t[t] + i + quarter), b1 = ld256(in.t[t] + i + quarter + half);
+      lo[t] = fq_add(a0, fq_mul(r, fq_sub(a1, a0)));   // dense_mlpoly.rs:218
+      hi[t] = fq_add(b0, fq_mul(r, fq_sub(b1, b0)));
+      if (t == 2) {
+        if (in.write_c) { st256(in.c_out + i, lo[t]); st256(in.c_out + i + quarter, hi[t]); }
+      } else {
+        st256(in.t[t] + i, lo[t]); st256(in.t[t] + i + quarter, hi[t]);
+      }
+    }
+    sc_accumulate<KIND>(acc, lo, hi);
+  }
+  block_reduce_finish<3>(acc, partials, counters, out, 3);
+}
+
+struct FoldBatch {
+  u256* t[64];
+};
+__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const u256* __restrict__ rp) {
+  const size_t half = len >> 1;
+  u256* T = tabs.t[blockIdx.y];
+  const u256 r = ld256_ro(rp);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    u256 a0 = ld256(T + i), a1 = ld256(T + i + half);
+    st256(T + i, fq_add(a0, fq_mul(r, fq_sub(a1, a0))));
+  }
+}
+
+// scratch layout: [counters: 64 x u32][partials]
+static const size_t SC_MAX_BLOCKS = 148 * 4 + 64;
+size_t sc_scratch_bytes(int ninst) { return 256 + (size_t)ninst * SC_MAX_BLOCKS * 3 * sizeof(u256); }
+
+static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
+  if (ninst > SC_MAX_INST) throw std::runtime_error("spartan_b200: too many sumcheck instances in one batch");
+  for (int i = 0; i < ninst; i++) b.inst[i] = insts[i];
+}
+
+void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s) {
+  ProfScope ps("sc_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 32.0, s);
+  ScBatch b; fill_batch(b, insts, ninst);
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(len / 2, 256, 2), ninst);
+  if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
+  switch (kind) {
+    case SC_QUAD: k_sc_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
+    case SC_CUBIC3: k_sc_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
+    default: k_sc_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
+  }
+  SP_LAUNCHED(); check("sc_eval");
+}
+void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256* d_r, u256* out, void* scratch, cudaStream_t s) {
+  ProfScope ps("sc_fold_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 48.0, s);
+  ScBatch b; fill_batch(b, insts, ninst);
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(len / 4, 256, 2), ninst);
+  if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
+  switch (kind) {
+    case SC_QUAD: k_sc_fold_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
+    case SC_CUBIC3: k_sc_fold_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
+    default: k_sc_fold_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
+  }
+  SP_LAUNCHED(); check("sc_fold_eval");
+}
+void fold_top(u256* const* tables, int ntables, size_t len, const u256* d_r, cudaStream_t s) {
+  ProfScope ps("fold_top", (double)ntables * len * 48.0, s);
+  for (int base = 0; base < ntables; base += 64) {
+    FoldBatch fb; int n = ntables - base < 64 ? ntables - base : 64;
+    for (int i = 0; i < n; i++) fb.t[i] = tables[base + i];
+    dim3 grid(grid_for(len / 2, 256, 4), n);
+    k_fold_top<<<grid, 256, 0, s>>>(fb, len, d_r);
+    SP_LAUNCHED();
+  }
+  check("fold_top");
+}
+void fold_top_single(u256* table, size_t len, const u256* d_r, cudaStream_t s) { u256* t[1] = {table}; fold_top(t, 1, len, d_r, s); }
+
+
+}  // namespace dev
+}  // namespace sp
