@@ -92,13 +92,13 @@ void sparse_eval3(u256* out, const uint32_t* row, const uint32_t* col, const u25
 void gens_from_uniform(ge* out, const uint8_t* d_uniform64, size_t n, cudaStream_t s);
 void decompress_batch(ge* out, int* ok, const uint8_t* in32, size_t n, cudaStream_t s);
 void compress_batch(uint8_t* out32, const ge* in, size_t n, cudaStream_t s);
-// table[(j*32 + w)*128 + (d-1)] = d * 2^(8w) * G_j in affine-niels form
-size_t table_entries(size_t nbases);
-void build_tables(ge_niels* table, const ge* G, size_t nbases, cudaStream_t s);
+// table[(j*NWIN + w)*2^(W-1) + (d-1)] = d * 2^(W*w) * G_j in affine-niels form; W (wbits) is 8 or 13, NWIN = ceil(253 / W)
+size_t table_entries(size_t nbases, int wbits);
+void build_tables(ge_niels* table, const ge* G, size_t nbases, int wbits, cudaStream_t s);
 // out[row] = sum_{j<R} scalars[row*stride + j] * G_j  (+ blinds[row] * G_{blind_base} when blinds != null)
 // scalars are Montgomery-form; partial: scratch >= msm_scratch_bytes(L, R)
 size_t msm_scratch_bytes(size_t L, size_t R);
-void msm_rows(ge* out, const ge_niels* table, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
+void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
               void* scratch, cudaStream_t s);
 
 }  // namespace dev

@@ -61,6 +61,7 @@ struct GenSet {
   size_t nbases;
   DevBuf<ge> G;
   DevBuf<ge_niels> table;
+  int wbits = 8;               // window width of `table` (host_tab is always 8-bit)
   std::map<size_t, HostBaseTable> host_tab;
   std::vector<Cp> compressed;  // lazily filled export
   GenSet(Ctx* c, const std::string& label, size_t nbases, const std::vector<size_t>& host_bases);

@@ -2,6 +2,7 @@
 // Follows the exact Fiat-Shamir schedule of /root/reference/src/r1csproof.rs:144-349 so that the
 // proof bytes equal the reference's for identical instance, assignment, transcript label and RandomTape seed.
 #include "prover.hpp"
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -72,17 +73,29 @@ GenSet::GenSet(Ctx* c, const std::string& label_, size_t nbases_, const std::vec
   dev::h2d(d_uni.p, uni.data(), uni.size(), ctx->stream);
   G.alloc(nbases);
   dev::gens_from_uniform(G.p, d_uni.p, nbases, ctx->stream);
-  table.alloc(dev::table_entries(nbases));
-  dev::build_tables(table.p, G.p, nbases, ctx->stream);
-  ctx->sync();
-  for (size_t b : host_bases) {
-    if (b >= nbases) continue;
-    HostBaseTable t;
-    t.e.resize(32 * 128);
-    dev::d2h(t.e.data(), table.p + b * 32 * 128, sizeof(ge_niels) * 32 * 128, ctx->stream);
-    ctx->sync();
-    host_tab[b] = std::move(t);
+  // large generator sets get 13-bit windows (20 additions per term instead of 32; 7.9 MB of table per generator)
+  const char* wenv = getenv("SP_MSM_WINDOW");
+  wbits = wenv ? atoi(wenv) : (nbases >= 512 ? 13 : 8);
+  if (wbits != 8 && wbits != 13) throw std::runtime_error("spartan_b200: SP_MSM_WINDOW must be 8 or 13");
+  table.alloc(dev::table_entries(nbases, wbits));
+  dev::build_tables(table.p, G.p, nbases, wbits, ctx->stream);
+  // host copies (8-bit windows) of the few generators the sigma protocols commit against
+  std::vector<size_t> hb;
+  for (size_t b : host_bases) if (b < nbases && std::find(hb.begin(), hb.end(), b) == hb.end()) hb.push_back(b);
+  if (!hb.empty()) {
+    DevBuf<ge> sel(hb.size());
+    for (size_t i = 0; i < hb.size(); i++) dev::d2d(sel.p + i, G.p + hb[i], sizeof(ge), ctx->stream);
+    DevBuf<ge_niels> small(dev::table_entries(hb.size(), 8));
+    dev::build_tables(small.p, sel.p, hb.size(), 8, ctx->stream);
+    for (size_t i = 0; i < hb.size(); i++) {
+      HostBaseTable t;
+      t.e.resize(32 * 128);
+      dev::d2h(t.e.data(), small.p + i * 32 * 128, sizeof(ge_niels) * 32 * 128, ctx->stream);
+      ctx->sync();
+      host_tab[hb[i]] = std::move(t);
+    }
   }
+  ctx->sync();
 }
 ge GenSet::host_point(size_t base) const {
   ge acc = ge_identity();
@@ -282,7 +295,7 @@ Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalar
   DevBuf<ge> rows(L);
   DevBuf<u256> d_bl;
   if (blinds) { d_bl.alloc(L); dev::h2d(d_bl.p, blinds, L * sizeof(u256), ctx.stream); }
-  dev::msm_rows(rows.p, key.set->table.p, d_scalars, stride, L, R, blinds ? d_bl.p : nullptr, key.h, ctx.scratch.p, ctx.stream);
+  dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars, stride, L, R, blinds ? d_bl.p : nullptr, key.h, ctx.scratch.p, ctx.stream);
   DevBuf<uint8_t> comp(32 * L);
   dev::compress_batch(comp.p, rows.p, L, ctx.stream);
   out.resize(L);
@@ -315,7 +328,7 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
     dev::dot(d_c, d_a, d_b + half, half, ctx.red.p, ctx.stream);          // c_L = <a_L, b_R>   bullet.rs:78
     dev::dot(d_c + 1, d_a + half, d_b, half, ctx.red.p, ctx.stream);      // c_R = <a_R, b_L>   bullet.rs:79
     dev::ipa_lr_scalars(lr.p, lr.p + n, d_a, svec.p, cur, n, ctx.stream);
-    dev::msm_rows(pts.p, gs.table.p, lr.p, n, 2, n, nullptr, 0, ctx.scratch.p, ctx.stream);
+    dev::msm_rows(pts.p, gs.table.p, gs.wbits, lr.p, n, 2, n, nullptr, 0, ctx.scratch.p, ctx.stream);
     dev::d2h(ctx.pinned, d_c, 64, ctx.stream);
     dev::d2h(ctx.pinned + 64, pts.p, 2 * sizeof(ge), ctx.stream);
     ctx.sync();
@@ -345,7 +358,7 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
     k++;
   }
   // g_hat = G_final[0] = <s, G>
-  dev::msm_rows(pts.p, gs.table.p, svec.p, n, 1, n, nullptr, 0, ctx.scratch.p, ctx.stream);
+  dev::msm_rows(pts.p, gs.table.p, gs.wbits, svec.p, n, 1, n, nullptr, 0, ctx.scratch.p, ctx.stream);
   dev::d2h(ctx.pinned, d_a, 32, ctx.stream);
   dev::d2h(ctx.pinned + 32, d_b, 32, ctx.stream);
   dev::d2h(ctx.pinned + 64, pts.p, sizeof(ge), ctx.stream);
