@@ -122,10 +122,9 @@ int sp_fold_top(sp_ctx* ctx, sp_poly* const* polys, int k, const uint64_t r[4]) 
   SP_TRY(ctx)
   check_same_len(polys, k);
   Fq rr = fq_in(r);
-  ctx->c.put_small(8, &rr, 1);
   std::vector<u256*> t(k);
   for (int i = 0; i < k; i++) t[i] = polys[i]->d.p;
-  dev::fold_top(t.data(), k, polys[0]->len, ctx->c.small.p + 8, ctx->c.stream);
+  dev::fold_top(t.data(), k, polys[0]->len, rr.m, ctx->c.stream);
   ctx->c.sync();
   for (int i = 0; i < k; i++) polys[i]->len /= 2;
   SP_CATCH(ctx)
@@ -157,9 +156,8 @@ int sp_sumcheck_fold_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, const ui
   check_same_len(polys, nt);
   if (polys[0]->len < 4) throw SpError(SP_ERR_INVALID_ARG, "fold_eval needs length >= 4");
   Fq rr = fq_in(r);
-  ctx->c.put_small(8, &rr, 1);
   dev::ScInst in = make_inst(polys, nt);
-  dev::sc_fold_eval((dev::ScKind)kind, &in, 1, polys[0]->len, ctx->c.small.p + 8, ctx->c.small.p, ctx->c.red.p, ctx->c.stream);
+  dev::sc_fold_eval((dev::ScKind)kind, &in, 1, polys[0]->len, rr.m, ctx->c.small.p, ctx->c.red.p, ctx->c.stream);
   Fq e[3];
   ctx->c.get_small(0, e, 3);
   memcpy(out, e, 96);

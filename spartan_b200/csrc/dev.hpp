@@ -52,14 +52,23 @@ struct ScInst {        // one sumcheck instance: up to four tables of the same c
   u256* c_out;         // where the folded C goes (== t[2] for private C; a ping-pong buffer when C is shared)
   int write_c;         // 1: this instance stores the folded C
 };
+// Optional host notification of a reduction kernel: results are also stored to `host_out` (mapped pinned memory) and `seq` is then
+// published in `*flag`; `done` is a zero-initialised device counter (instances of a batched launch finish independently).
+struct HostSig {
+  u256* host_out = nullptr;
+  unsigned int* flag = nullptr;
+  unsigned int* done = nullptr;
+  unsigned int seq = 0;
+};
 // scratch: >= sc_scratch_bytes(); out: ninst*3 scalars [e0,e2,e3] (e3 = 0 for SC_QUAD), device memory
 size_t sc_scratch_bytes(int ninst);
-void sc_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s);
-// fold every table of every instance by r (len -> len/2, in place) and evaluate the next round on the result
-void sc_fold_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, const u256* d_r, u256* out, void* scratch, cudaStream_t s);
+void sc_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s, HostSig sig = HostSig());
+// fold every table of every instance by r (len -> len/2, in place) and evaluate the next round on the result; r travels as a kernel argument
+void sc_fold_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s,
+                  HostSig sig = HostSig());
 // fold only (bound_poly_var_top, dense_mlpoly.rs:215-223): tables[k][i] += r*(tables[k][i+len/2]-tables[k][i])
-void fold_top(u256* const* d_tables, int ntables, size_t len, const u256* d_r, cudaStream_t s);
-void fold_top_single(u256* table, size_t len, const u256* d_r, cudaStream_t s);
+void fold_top(u256* const* d_tables, int ntables, size_t len, const u256& r, cudaStream_t s);
+void fold_top_single(u256* table, size_t len, const u256& r, cudaStream_t s);
 
 // ---- dense polynomial helpers (K7)
 void eq_evals(u256* out, const u256* d_r, int ell, u256* scratch_small /* >= 2*2^ceil(ell/2) */, cudaStream_t s);
@@ -69,6 +78,7 @@ void dot3(u256* out, const u256* a, const u256* b, const u256* c, size_t n, void
 void bound_rows(u256* out, const u256* Z, const u256* L, size_t L_size, size_t R_size, u256* scratch /* >= 64*R_size */, cudaStream_t s);
 void lincomb3(u256* out, const u256* A, const u256* B, const u256* C, const u256* d_rabc /*3*/, size_t n, cudaStream_t s);
 void hadamard(u256* out, const u256* a, const u256* b, size_t n, cudaStream_t s);
+void hadamard_many(u256* const* outs, const u256* const* as, const u256* const* bs, int count, size_t n, cudaStream_t s);
 void from_u64(u256* out, const uint64_t* v, size_t n, cudaStream_t s);
 void from_bytes_wide(u256* out, const uint8_t* in64, size_t n, cudaStream_t s);
 void batch_invert_elems(u256* inout, size_t n, cudaStream_t s);
@@ -77,10 +87,10 @@ void gather(u256* out, const u256* mem, const uint32_t* idx, size_t n, cudaStrea
 // addr == null: addr = index i;  ts == null: ts = 0;  ts_plus_one adds one.   d_rg = [r_hash, r_multiset]
 void spark_hash(u256* out, size_t n, const u256* addr, const u256* val, const u256* ts, int ts_plus_one, const u256* d_rg, cudaStream_t s);
 // IPA vector folds (bullet.rs:105-107): a[i] = a[i]*u + uinv*a[i+n];  b[i] = b[i]*uinv + u*b[i+n]   d_u = [u, uinv]
-void ipa_fold_ab(u256* a, u256* b, size_t n, const u256* d_u, cudaStream_t s);
+void ipa_fold_ab(u256* a, u256* b, size_t n, const u256& u, const u256& uinv, cudaStream_t s);
 // scalars for the L / R commitments against the UNFOLDED generators: see DESIGN.md "IPA without folding G"
 void ipa_lr_scalars(u256* outL, u256* outR, const u256* a, const u256* svec, size_t n_cur, size_t n_full, cudaStream_t s);
-void ipa_update_s(u256* svec, size_t n_cur_half, size_t n_full, const u256* d_u, cudaStream_t s);
+void ipa_update_s(u256* svec, size_t n_cur_half, size_t n_full, const u256& u, const u256& uinv, cudaStream_t s);
 void fill_one(u256* out, size_t n, cudaStream_t s);
 
 // ---- sparse matrix-vector products on CSR (row-major) / CSC (column-major) copies of the COO triples

@@ -44,6 +44,13 @@ struct Ctx {
 
   explicit Ctx(int dev);
   ~Ctx();
+  // host-polled kernel results (mapped pinned memory): see dev::HostSig
+  u256* host_res = nullptr;
+  unsigned int* host_flag = nullptr;
+  DevBuf<unsigned int> sig_done;
+  unsigned int sig_seq = 0;
+  dev::HostSig next_sig() { dev::HostSig s; s.host_out = host_res; s.flag = host_flag; s.done = sig_done.p; s.seq = ++sig_seq; return s; }
+  void wait_sig(const dev::HostSig& s);   // spins on the flag; falls back to a stream synchronise to surface CUDA errors
   void sync() { dev::stream_sync(stream); }
   void ensure_scratch(size_t bytes) { if (scratch.n < bytes) { sync(); scratch.alloc(bytes); } }
   // upload k scalars to small[slot..]

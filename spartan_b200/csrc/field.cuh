@@ -285,7 +285,46 @@ SP_HD void fp_fold(u256& x, uint64_t c) {
   }
 }
 
+#if defined(__CUDA_ARCH__)
+// carry-chain forms for the device (values stay loose in [0, 2^256), congruent mod p; 2^256 = 38 mod p)
+__device__ __forceinline__ u256 fp_add_ptx(const u256& a, const u256& b) {
+  u256 s, r;
+  uint32_t c, c2;
+  asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.cc.u32 %7, %16, %24;\n\taddc.u32 %8, 0, 0;"
+      : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7]), "=r"(c)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  uint32_t k = c * 38u;   // fold the carry-out back in
+  asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, 0;\n\taddc.cc.u32 %2, %11, 0;\n\taddc.cc.u32 %3, %12, 0;\n\t"
+      "addc.cc.u32 %4, %13, 0;\n\taddc.cc.u32 %5, %14, 0;\n\taddc.cc.u32 %6, %15, 0;\n\taddc.cc.u32 %7, %16, 0;\n\taddc.u32 %8, 0, 0;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c2)
+      : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]), "r"(k));
+  r.v[0] += c2 * 38u;     // a second wrap leaves a value < 38*2, so this cannot carry
+  return r;
+}
+__device__ __forceinline__ u256 fp_sub_ptx(const u256& a, const u256& b) {
+  u256 d, r;
+  uint32_t bw, bw2;
+  asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\tsubc.u32 %8, 0, 0;"
+      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7]), "=r"(bw)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  uint32_t k = bw & 38u;  // wrapped by 2^256 = 38 (mod p): take 38 back out
+  asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, 0;\n\tsubc.cc.u32 %2, %11, 0;\n\tsubc.cc.u32 %3, %12, 0;\n\t"
+      "subc.cc.u32 %4, %13, 0;\n\tsubc.cc.u32 %5, %14, 0;\n\tsubc.cc.u32 %6, %15, 0;\n\tsubc.cc.u32 %7, %16, 0;\n\tsubc.u32 %8, 0, 0;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(bw2)
+      : "r"(d.v[0]), "r"(d.v[1]), "r"(d.v[2]), "r"(d.v[3]), "r"(d.v[4]), "r"(d.v[5]), "r"(d.v[6]), "r"(d.v[7]), "r"(k));
+  r.v[0] -= bw2 & 38u;    // second wrap: the value is then >= 2^256 - 38, so this cannot borrow
+  return r;
+}
+#endif
+
 SP_HD u256 fp_add(const u256& a, const u256& b) {
+#if defined(__CUDA_ARCH__) && !defined(SP_NO_PTX)
+  return fp_add_ptx(a, b);
+#else
   u256 s;
   uint64_t c = 0;
 #pragma unroll
@@ -296,8 +335,12 @@ SP_HD u256 fp_add(const u256& a, const u256& b) {
   }
   fp_fold(s, c);
   return s;
+#endif
 }
 SP_HD u256 fp_sub(const u256& a, const u256& b) {
+#if defined(__CUDA_ARCH__) && !defined(SP_NO_PTX)
+  return fp_sub_ptx(a, b);
+#else
   u256 d;
   int64_t borrow = 0;
 #pragma unroll
@@ -319,6 +362,7 @@ SP_HD u256 fp_sub(const u256& a, const u256& b) {
     borrow = k;
   }
   return d;
+#endif
 }
 SP_HD u256 fp_neg(const u256& a) { return fp_sub(fp_zero(), a); }
 

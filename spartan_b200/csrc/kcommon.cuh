@@ -72,8 +72,11 @@ __device__ __forceinline__ u256 warp_sum_fq(u256 x) {
 
 // Block-wide sum of NV field values per thread, then cross-block finalisation by the last block to arrive.
 // partials: [gridDim.y][gridDim.x][NV]; counters: [gridDim.y] zero-initialised, self-resetting.
+// `sig` (optional): the finishing block also stores the results into mapped pinned host memory and then publishes `seq` in a host flag
+// word, so the host can pick a round's evaluations up by polling instead of a memcpy + stream synchronise.
 template <int NV>
-__device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* partials, unsigned int* counters, u256* out, int out_stride) {
+__device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* partials, unsigned int* counters, u256* out, int out_stride,
+                                                    HostSig sig = HostSig()) {
   __shared__ u256 sm[32][NV];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -105,9 +108,19 @@ __device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* parti
         u256 s = fq_zero();
         for (unsigned int b = lane; b < gridDim.x; b += 32) s = fq_add(s, ld256_cg(&partials[((size_t)blockIdx.y * gridDim.x + b) * NV + k]));
         s = warp_sum_fq(s);
-        if (lane == 0) st256(&out[(size_t)blockIdx.y * out_stride + k], s);
+        if (lane == 0) {
+          st256(&out[(size_t)blockIdx.y * out_stride + k], s);
+          if (sig.host_out) st256(&sig.host_out[(size_t)blockIdx.y * out_stride + k], s);
+        }
       }
-      if (lane == 0) counters[blockIdx.y] = 0;
+      if (lane == 0) {
+        counters[blockIdx.y] = 0;
+        if (sig.flag) {
+          __threadfence_system();
+          unsigned int done = atomicAdd(sig.done, 1u) + 1;       // instances (blockIdx.y) finish independently
+          if (done == gridDim.y) { *sig.done = 0; __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
+        }
+      }
     }
   }
 }

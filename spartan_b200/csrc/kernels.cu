@@ -277,6 +277,22 @@ void hadamard(u256* out, const u256* a, const u256* b, size_t n, cudaStream_t s)
   k_hadamard<<<grid_for(n, 256, 8), 256, 0, s>>>(out, a, b, n);
   SP_LAUNCHED(); check("hadamard");
 }
+// one product-tree layer of up to 16 circuits of equal size in one launch (blockIdx.y = circuit)
+struct HadBatch { u256* out[16]; const u256* a[16]; const u256* b[16]; };
+__global__ void k_hadamard_many(HadBatch hb, size_t n) {
+  u256* out = hb.out[blockIdx.y]; const u256* a = hb.a[blockIdx.y]; const u256* b = hb.b[blockIdx.y];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st256(out + i, fq_mul(ld256(a + i), ld256(b + i)));
+}
+void hadamard_many(u256* const* outs, const u256* const* as, const u256* const* bs, int count, size_t n, cudaStream_t s) {
+  ProfScope ps("hadamard", 96.0 * (double)n * count, s);
+  if (count > 16) throw std::runtime_error("spartan_b200: hadamard_many supports at most 16 tables");
+  HadBatch hb;
+  for (int i = 0; i < count; i++) { hb.out[i] = outs[i]; hb.a[i] = as[i]; hb.b[i] = bs[i]; }
+  dim3 grid(grid_for(n, 256, 4), count);
+  k_hadamard_many<<<grid, 256, 0, s>>>(hb, n);
+  SP_LAUNCHED(); check("hadamard_many");
+}
 __global__ void k_from_u64(u256* out, const uint64_t* __restrict__ v, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st256(out + i, fq_from_u64(v[i]));
 }
@@ -334,17 +350,16 @@ void fill_one(u256* out, size_t n, cudaStream_t s) {
 }
 
 // ---- IPA helpers (nizk/bullet.rs:72-119)
-__global__ void k_ipa_fold_ab(u256* a, u256* b, size_t n, const u256* __restrict__ up) {
-  u256 u = ld256_ro(up), ui = ld256_ro(up + 1);
+__global__ void k_ipa_fold_ab(u256* a, u256* b, size_t n, const u256 u, const u256 ui) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     u256 aL = ld256(a + i), aR = ld256(a + i + n), bL = ld256(b + i), bR = ld256(b + i + n);
     st256(a + i, fq_add(fq_mul(aL, u), fq_mul(ui, aR)));   // bullet.rs:106
     st256(b + i, fq_add(fq_mul(bL, ui), fq_mul(u, bR)));   // bullet.rs:107
   }
 }
-void ipa_fold_ab(u256* a, u256* b, size_t n, const u256* d_u, cudaStream_t s) {
+void ipa_fold_ab(u256* a, u256* b, size_t n, const u256& u, const u256& uinv, cudaStream_t s) {
   ProfScope ps("ipa_fold_ab", 192.0 * (double)n, s);
-  k_ipa_fold_ab<<<grid_for(n, 128, 8), 128, 0, s>>>(a, b, n, d_u);
+  k_ipa_fold_ab<<<grid_for(n, 128, 8), 128, 0, s>>>(a, b, n, u, uinv);
   SP_LAUNCHED(); check("ipa_fold_ab");
 }
 // G is never folded on the device: after k rounds G_k[i] = sum_{j = i mod n_k} s[j]*G[j], so the round's
@@ -362,15 +377,14 @@ void ipa_lr_scalars(u256* outL, u256* outR, const u256* a, const u256* svec, siz
   k_ipa_lr<<<grid_for(n_full, 128, 8), 128, 0, s>>>(outL, outR, a, svec, n_cur, n_full);
   SP_LAUNCHED(); check("ipa_lr");
 }
-__global__ void k_ipa_update_s(u256* sv, size_t half, size_t n_full, const u256* __restrict__ up) {
-  u256 u = ld256_ro(up), ui = ld256_ro(up + 1);
+__global__ void k_ipa_update_s(u256* sv, size_t half, size_t n_full, const u256 u, const u256 ui) {
   for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_full; j += (size_t)gridDim.x * blockDim.x) {
     bool right = (j & (2 * half - 1)) >= half;
     st256(sv + j, fq_mul(ld256(sv + j), right ? u : ui));   // G_L[i] <- u^-1 G_L[i] + u G_R[i], bullet.rs:108
   }
 }
-void ipa_update_s(u256* svec, size_t half, size_t n_full, const u256* d_u, cudaStream_t s) {
-  k_ipa_update_s<<<grid_for(n_full, 128, 8), 128, 0, s>>>(svec, half, n_full, d_u);
+void ipa_update_s(u256* svec, size_t half, size_t n_full, const u256& u, const u256& uinv, cudaStream_t s) {
+  k_ipa_update_s<<<grid_for(n_full, 128, 8), 128, 0, s>>>(svec, half, n_full, u, uinv);
   SP_LAUNCHED(); check("ipa_update_s");
 }
 

@@ -42,7 +42,7 @@ __device__ __forceinline__ void sc_accumulate(u256 (&acc)[3], const u256 (&lo)[4
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t len, u256* partials, unsigned int* counters, u256* out) {
+__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t len, u256* partials, unsigned int* counters, u256* out, HostSig sig) {
   constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
   const ScInst& in = batch.inst[blockIdx.y];
   const size_t half = len >> 1;
@@ -55,18 +55,17 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t
     for (int t = 0; t < NT; t++) { lo[t] = ld256(in.t[t] + i); hi[t] = ld256(in.t[t] + i + half); }
     sc_accumulate<KIND>(acc, lo, hi);
   }
-  block_reduce_finish<3>(acc, partials, counters, out, 3);
+  block_reduce_finish<3>(acc, partials, counters, out, 3, sig);
 }
 
 // Fused: bind the top variable with r (len -> len/2) and evaluate the next round's polynomial on the folded table.
 // Thread i owns elements {i, i+len/4, i+len/2, i+3len/4} of every table: in-place update is race-free.
 template <int KIND>
-__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, size_t len, const u256* __restrict__ rp, u256* partials,
-                                                       unsigned int* counters, u256* out) {
+__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, size_t len, const u256 r, u256* partials,
+                                                       unsigned int* counters, u256* out, HostSig sig) {
   constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
   const ScInst& in = batch.inst[blockIdx.y];
   const size_t half = len >> 1, quarter = len >> 2;
-  const u256 r = ld256_ro(rp);
   u256 acc[3] = {fq_zero(), fq_zero(), fq_zero()};
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quarter; i += (size_t)gridDim.x * blockDim.x) {
     u256 lo[4], hi[4];
@@ -86,16 +85,15 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, s
     }
     sc_accumulate<KIND>(acc, lo, hi);
   }
-  block_reduce_finish<3>(acc, partials, counters, out, 3);
+  block_reduce_finish<3>(acc, partials, counters, out, 3, sig);
 }
 
 struct FoldBatch {
   u256* t[64];
 };
-__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const u256* __restrict__ rp) {
+__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const u256 r) {
   const size_t half = len >> 1;
   u256* T = tabs.t[blockIdx.y];
-  const u256 r = ld256_ro(rp);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
     u256 a0 = ld256(T + i), a1 = ld256(T + i + half);
     st256(T + i, fq_add(a0, fq_mul(r, fq_sub(a1, a0))));
@@ -111,7 +109,7 @@ static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
   for (int i = 0; i < ninst; i++) b.inst[i] = insts[i];
 }
 
-void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s) {
+void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s, HostSig sig) {
   ProfScope ps("sc_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 32.0, s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
@@ -119,13 +117,13 @@ void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out,
   dim3 grid(grid_for(len / 2, 256, 2), ninst);
   if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
   switch (kind) {
-    case SC_QUAD: k_sc_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
-    case SC_CUBIC3: k_sc_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
-    default: k_sc_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, partials, counters, out); break;
+    case SC_QUAD: k_sc_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig); break;
+    case SC_CUBIC3: k_sc_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig); break;
+    default: k_sc_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig); break;
   }
   SP_LAUNCHED(); check("sc_eval");
 }
-void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256* d_r, u256* out, void* scratch, cudaStream_t s) {
+void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s, HostSig sig) {
   ProfScope ps("sc_fold_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 48.0, s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
@@ -133,24 +131,24 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
   dim3 grid(grid_for(len / 4, 256, 2), ninst);
   if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
   switch (kind) {
-    case SC_QUAD: k_sc_fold_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
-    case SC_CUBIC3: k_sc_fold_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
-    default: k_sc_fold_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, d_r, partials, counters, out); break;
+    case SC_QUAD: k_sc_fold_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, r, partials, counters, out, sig); break;
+    case SC_CUBIC3: k_sc_fold_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, r, partials, counters, out, sig); break;
+    default: k_sc_fold_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, r, partials, counters, out, sig); break;
   }
   SP_LAUNCHED(); check("sc_fold_eval");
 }
-void fold_top(u256* const* tables, int ntables, size_t len, const u256* d_r, cudaStream_t s) {
+void fold_top(u256* const* tables, int ntables, size_t len, const u256& r, cudaStream_t s) {
   ProfScope ps("fold_top", (double)ntables * len * 48.0, s);
   for (int base = 0; base < ntables; base += 64) {
     FoldBatch fb; int n = ntables - base < 64 ? ntables - base : 64;
     for (int i = 0; i < n; i++) fb.t[i] = tables[base + i];
     dim3 grid(grid_for(len / 2, 256, 4), n);
-    k_fold_top<<<grid, 256, 0, s>>>(fb, len, d_r);
+    k_fold_top<<<grid, 256, 0, s>>>(fb, len, r);
     SP_LAUNCHED();
   }
   check("fold_top");
 }
-void fold_top_single(u256* table, size_t len, const u256* d_r, cudaStream_t s) { u256* t[1] = {table}; fold_top(t, 1, len, d_r, s); }
+void fold_top_single(u256* table, size_t len, const u256& r, cudaStream_t s) { u256* t[1] = {table}; fold_top(t, 1, len, r, s); }
 
 
 }  // namespace dev

@@ -3,6 +3,7 @@
 // proof bytes equal the reference's for identical instance, assignment, transcript label and RandomTape seed.
 #include "prover.hpp"
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,11 @@ Ctx::Ctx(int dev_) : device(dev_) {
   stream = dev::stream_create();
   pinned_bytes = 1 << 20;
   pinned = (uint8_t*)dev::hmalloc_pinned(pinned_bytes);
+  host_res = reinterpret_cast<u256*>(pinned + (512 << 10));
+  host_flag = reinterpret_cast<unsigned int*>(pinned + (768 << 10));
+  *host_flag = 0;
+  sig_done.alloc(4);
+  dev::dzero(sig_done.p, 16, stream);
   small.alloc(4096);
   scratch.alloc(1 << 20);
   red.alloc(dev::sc_scratch_bytes(24));
@@ -43,6 +49,18 @@ Ctx::~Ctx() {
   scratch.release(); red.release(); small.release();
   dev::hfree_pinned(pinned);
   dev::stream_destroy(stream);
+}
+void Ctx::wait_sig(const dev::HostSig& s) {
+  volatile unsigned int* f = s.flag;
+  auto t0 = std::chrono::steady_clock::now();
+  unsigned long spins = 0;
+  while (*f != s.seq) {
+    if ((++spins & 0xffff) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
+      sync();   // throws on a CUDA error; otherwise the kernel has finished and the flag must be visible
+      if (*f != s.seq) throw std::runtime_error("spartan_b200: kernel completed without publishing its result flag");
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
 }
 void Ctx::put_small(size_t slot, const Fq* v, size_t k) {
   // staged through pageable memory on purpose: cudaMemcpyAsync from pageable memory snapshots the source before returning
@@ -178,23 +196,27 @@ static ProductProof product_prove(const CommitKey& g, Transcript& T, RandomTape&
   return p;
 }
 // DotProductProof::prove (nizk/mod.rs:311-370); Cx is passed in when the caller already holds commit(x_vec; blind_x)
+// `pre` (optional): tape draws made ahead of time in the reference's order, with the commitments that depend on the tape only
+struct DotPre { std::vector<Fq> d_vec; Fq r_delta, r_beta; Cp delta; ge r_beta_h; };
 static DotProductProof dotproduct_prove(const CommitKey& g1, const CommitKey& gn, Transcript& T, RandomTape& tape, const std::vector<Fq>& x_vec,
-                                        const Fq& blind_x, const std::vector<Fq>& a_vec, const Fq& y, const Fq& blind_y, const Cp* Cx_known) {
+                                        const Fq& blind_x, const std::vector<Fq>& a_vec, const Fq& y, const Fq& blind_y, const Cp* Cx_known,
+                                        const DotPre* pre = nullptr) {
   T.append_protocol_name("dot product proof");
   size_t n = x_vec.size();
-  std::vector<Fq> d_vec = tape.random_vector("d_vec", n);
-  Fq r_delta = tape.random_scalar("r_delta"), r_beta = tape.random_scalar("r_beta");
+  std::vector<Fq> d_vec = pre ? pre->d_vec : tape.random_vector("d_vec", n);
+  Fq r_delta = pre ? pre->r_delta : tape.random_scalar("r_delta"), r_beta = pre ? pre->r_beta : tape.random_scalar("r_beta");
   Cp Cx = Cx_known ? *Cx_known : commitv(gn, x_vec, blind_x);
   T.append_point("Cx", Cx.b);
   Cp Cy = commit1(g1, y, blind_y);
   T.append_point("Cy", Cy.b);
   T.append_scalars("a", a_vec);
   DotProductProof p;
-  p.delta = commitv(gn, d_vec, r_delta);
+  p.delta = pre ? pre->delta : commitv(gn, d_vec, r_delta);
   T.append_point("delta", p.delta.b);
   Fq dot = Fq::zero();
   for (size_t i = 0; i < n; i++) dot += a_vec[i] * d_vec[i];
-  p.beta = commit1(g1, dot, r_beta);
+  if (pre) { Term t1[1] = {{g1.off, dot}}; p.beta = compress(ge_add(host_commit(*g1.set, t1, 1), pre->r_beta_h)); }
+  else p.beta = commit1(g1, dot, r_beta);
   T.append_point("beta", p.beta.b);
   Fq c = T.challenge_scalar("c");
   p.z.resize(n);
@@ -231,33 +253,76 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
   std::vector<Fq> blinds_evals = tape.random_vector("blinds_evals", num_rounds);
   Fq claim_per_round = claim;
   Cp comm_claim_per_round = commit1(g1, claim_per_round, blind_claim);
+  // The tape does not depend on the transcript: draw the per-round randomness of DotProductProof::prove (nizk/mod.rs:329-331) now, in the
+  // reference's order, and commit to everything that depends on the tape only in four batched device MSMs, off the per-round critical path:
+  //   delta_j = commit(d_vec_j; r_delta_j) and the blind halves blinds_poly[j]*h, blinds_evals[j]*h, r_beta_j*h.
+  const size_t nco = (size_t)degree + 1;
+  std::vector<DotPre> pre(num_rounds);
+  std::vector<ge> bp_h(num_rounds), be_h(num_rounds);
+  {
+    std::vector<Fq> dmat(num_rounds * nco), rdel(num_rounds), rbet(num_rounds);
+    for (size_t j = 0; j < num_rounds; j++) {
+      pre[j].d_vec = tape.random_vector("d_vec", nco);
+      pre[j].r_delta = tape.random_scalar("r_delta");
+      pre[j].r_beta = tape.random_scalar("r_beta");
+      for (size_t i = 0; i < nco; i++) dmat[j * nco + i] = pre[j].d_vec[i];
+      rdel[j] = pre[j].r_delta; rbet[j] = pre[j].r_beta;
+    }
+    DevBuf<u256> d_s(num_rounds * nco), d_b(4 * num_rounds);
+    DevBuf<ge> d_pts(4 * num_rounds);
+    DevBuf<uint8_t> d_c(32 * num_rounds);
+    dev::h2d(d_s.p, dmat.data(), dmat.size() * sizeof(u256), ctx.stream);
+    dev::h2d(d_b.p, rdel.data(), num_rounds * sizeof(u256), ctx.stream);
+    dev::h2d(d_b.p + num_rounds, rbet.data(), num_rounds * sizeof(u256), ctx.stream);
+    dev::h2d(d_b.p + 2 * num_rounds, blinds_poly.data(), num_rounds * sizeof(u256), ctx.stream);
+    dev::h2d(d_b.p + 3 * num_rounds, blinds_evals.data(), num_rounds * sizeof(u256), ctx.stream);
+    ctx.ensure_scratch(dev::msm_scratch_bytes(num_rounds, nco) + 64);
+    const GenSet& gs = *gn.set;
+    dev::msm_rows(d_pts.p, gs.table.p, gs.wbits, d_s.p, nco, num_rounds, nco, d_b.p, gn.h, ctx.scratch.p, ctx.stream);                    // delta_j
+    dev::compress_batch(d_c.p, d_pts.p, num_rounds, ctx.stream);
+    dev::msm_rows(d_pts.p + num_rounds, gs.table.p, gs.wbits, d_s.p, 0, num_rounds, 0, d_b.p + num_rounds, g1.h, ctx.scratch.p, ctx.stream);      // r_beta_j * h
+    dev::msm_rows(d_pts.p + 2 * num_rounds, gs.table.p, gs.wbits, d_s.p, 0, num_rounds, 0, d_b.p + 2 * num_rounds, gn.h, ctx.scratch.p, ctx.stream);  // blinds_poly[j] * h
+    dev::msm_rows(d_pts.p + 3 * num_rounds, gs.table.p, gs.wbits, d_s.p, 0, num_rounds, 0, d_b.p + 3 * num_rounds, g1.h, ctx.scratch.p, ctx.stream);  // blinds_evals[j] * h
+    std::vector<Cp> deltas(num_rounds);
+    std::vector<ge> pts(3 * num_rounds);
+    dev::d2h(deltas.data(), d_c.p, 32 * num_rounds, ctx.stream);
+    dev::d2h(pts.data(), d_pts.p + num_rounds, 3 * num_rounds * sizeof(ge), ctx.stream);
+    ctx.sync();
+    for (size_t j = 0; j < num_rounds; j++) { pre[j].delta = deltas[j]; pre[j].r_beta_h = pts[j]; bp_h[j] = pts[num_rounds + j]; be_h[j] = pts[2 * num_rounds + j]; }
+  }
+  auto commit_poly_pre = [&](const std::vector<Fq>& coeffs, size_t j) {   // commit(coeffs; blinds_poly[j]; gens_n) = sum coeff_i*G_i + (blinds_poly[j]*h)
+    std::vector<Term> t;
+    for (size_t i = 0; i < coeffs.size(); i++) t.push_back({gn.off + i, coeffs[i]});
+    return compress(ge_add(host_commit(*gn.set, t.data(), t.size()), bp_h[j]));
+  };
   dev::ScInst inst;
   for (int t = 0; t < 4; t++) inst.t[t] = t < nt ? tables[t] : nullptr;
   inst.c_out = inst.t[2];
   inst.write_c = 1;
   u256* d_out = ctx.small.p + 0;     // 3 result scalars
-  u256* d_r = ctx.small.p + 8;       // round challenge
   size_t len = (size_t)1 << num_rounds;
-  dev::sc_eval(kind, &inst, 1, len, d_out, ctx.red.p, ctx.stream);
+  dev::HostSig sig = ctx.next_sig();
+  dev::sc_eval(kind, &inst, 1, len, d_out, ctx.red.p, ctx.stream, sig);
   for (size_t j = 0; j < num_rounds; j++) {
     Fq e[3];
-    ctx.get_small(0, e, 3);
+    ctx.wait_sig(sig);
+    memcpy(e, ctx.host_res, sizeof e);
     std::vector<Fq> evals = {e[0], claim_per_round - e[0], e[1]};
     if (degree == 3) evals.push_back(e[2]);
     UniPoly poly = UniPoly::from_evals(evals);
-    Cp comm_poly = commitv(gn, poly.coeffs, blinds_poly[j]);
+    Cp comm_poly = commit_poly_pre(poly.coeffs, j);
     T.append_point("comm_poly", comm_poly.b);
     proof.comm_polys.push_back(comm_poly);
     Fq r_j = T.challenge_scalar("challenge_nextround");
     // bind the tables to r_j on the device right away (fused with the next round's evaluation); the host continues with the
     // sigma protocol of this round while the kernel runs
-    ctx.put_small(8, &r_j, 1);
-    if (j + 1 < num_rounds) dev::sc_fold_eval(kind, &inst, 1, len, d_r, d_out, ctx.red.p, ctx.stream);
-    else dev::fold_top(tables, nt, len, d_r, ctx.stream);
+    if (j + 1 < num_rounds) { sig = ctx.next_sig(); dev::sc_fold_eval(kind, &inst, 1, len, r_j.m, d_out, ctx.red.p, ctx.stream, sig); }
+    else dev::fold_top(tables, nt, len, r_j.m, ctx.stream);
     len >>= 1;
 
     Fq eval = poly.evaluate(r_j);
-    Cp comm_eval = commit1(g1, eval, blinds_evals[j]);
+    Term te[1] = {{g1.off, eval}};
+    Cp comm_eval = compress(ge_add(host_commit(*g1.set, te, 1), be_h[j]));   // eval*G + blinds_evals[j]*h
     T.append_point("comm_claim_per_round", comm_claim_per_round.b);
     T.append_point("comm_eval", comm_eval.b);
     std::vector<Fq> w = T.challenge_vector("combine_two_claims_to_one", 2);
@@ -273,7 +338,7 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
       a[i] = w[0] * a_sc + w[1] * rpow;
       rpow *= r_j;
     }
-    proof.proofs.push_back(dotproduct_prove(g1, gn, T, tape, poly.coeffs, blinds_poly[j], a, target, blind, &comm_poly));
+    proof.proofs.push_back(dotproduct_prove(g1, gn, T, tape, poly.coeffs, blinds_poly[j], a, target, blind, &comm_poly, &pre[j]));
     claim_per_round = eval;
     comm_claim_per_round = comm_eval;
     r.push_back(r_j);
@@ -320,7 +385,6 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
   dev::fill_one(svec.p, n, ctx.stream);
   ctx.ensure_scratch(dev::msm_scratch_bytes(2, n) + 64);
   u256* d_c = ctx.small.p + 16;  // c_L, c_R
-  u256* d_u = ctx.small.p + 24;  // u, u^-1
   blind_final = blind;
   size_t cur = n, k = 0;
   while (cur != 1) {
@@ -347,10 +411,8 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
     T.append_point("R", Rc.b);
     Fq u = T.challenge_scalar("u");
     Fq u_inv = u.inv();
-    Fq uu[2] = {u, u_inv};
-    ctx.put_small(24, uu, 2);
-    dev::ipa_fold_ab(d_a, d_b, half, d_u, ctx.stream);
-    dev::ipa_update_s(svec.p, half, n, d_u, ctx.stream);
+    dev::ipa_fold_ab(d_a, d_b, half, u.m, u_inv.m, ctx.stream);
+    dev::ipa_update_s(svec.p, half, n, u.m, u_inv.m, ctx.stream);
     blind_final = blind_final + blind_L * u * u + blind_R * u_inv * u_inv;  // bullet.rs:111
     proof.L_vec.push_back(Lc);
     proof.R_vec.push_back(Rc);

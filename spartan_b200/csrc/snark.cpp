@@ -148,7 +148,6 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
   DevBuf<u256> cpar0(std::max<size_t>(max_half, 1));
   std::vector<Fq> rand;
   u256* d_out = ctx.small.p + 64;   // ninst * 3 scalars
-  u256* d_r = ctx.small.p + 8;
   for (size_t layer_id = num_layers; layer_id-- > 0;) {
     const size_t len = prods[0]->layer_len(layer_id);  // left + right
     const size_t half = len / 2;                       // table length of this layer's sumcheck
@@ -185,27 +184,28 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     std::vector<Fq> rand_prod;
     Fq e = claim;
     size_t cur = half;
-    if (num_rounds > 0) dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream);
+    dev::HostSig sig;
+    if (num_rounds > 0) { sig = ctx.next_sig(); dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream, sig); }
     u256* cin = cpar0.p;
     u256* cpp[2] = {cpar_a.p, cpar_b.p};
     int flip = 0;
     for (size_t j = 0; j < num_rounds; j++) {
       std::vector<Fq> ev(3 * ninst);
-      ctx.get_small(64, ev.data(), 3 * ninst);
+      ctx.wait_sig(sig);
+      memcpy(ev.data(), ctx.host_res, 3 * ninst * sizeof(u256));
       Fq c0 = Fq::zero(), c2 = Fq::zero(), c3 = Fq::zero();
       for (size_t i = 0; i < ninst; i++) { c0 += ev[3 * i] * coeff_vec[i]; c2 += ev[3 * i + 1] * coeff_vec[i]; c3 += ev[3 * i + 2] * coeff_vec[i]; }  // sumcheck.rs:359-361
       UniPoly poly = UniPoly::from_evals({c0, e - c0, c2, c3});
       poly.append_to_transcript("poly", T);
       Fq r_j = T.challenge_scalar("challenge_nextround");
       rand_prod.push_back(r_j);
-      ctx.put_small(8, &r_j, 1);
       // bind every table (shared C written once, through a ping-pong buffer)
       for (size_t i = 0; i < np; i++) { insts[i].t[2] = cin; insts[i].c_out = cpp[flip]; }
-      if (j + 1 < num_rounds) dev::sc_fold_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_r, d_out, ctx.red.p, ctx.stream);
+      if (j + 1 < num_rounds) { sig = ctx.next_sig(); dev::sc_fold_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, r_j.m, d_out, ctx.red.p, ctx.stream, sig); }
       else {
         std::vector<u256*> tabs;
         for (size_t i = 0; i < ninst; i++) { tabs.push_back(insts[i].t[0]); tabs.push_back(insts[i].t[1]); if (i >= np) tabs.push_back(insts[i].t[2]); }
-        dev::fold_top(tabs.data(), (int)tabs.size(), cur, d_r, ctx.stream);
+        dev::fold_top(tabs.data(), (int)tabs.size(), cur, r_j.m, ctx.stream);
         // the shared C's final value is never used by the prover (claims_prod.2 is dropped, product_tree.rs:336)
       }
       cin = cpp[flip];
@@ -354,8 +354,19 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
       dev::spark_hash(s.read[m].layer(0), N, addr, val, ts, 0, d_chal.p, ctx.stream);
       dev::spark_hash(s.write[m].layer(0), N, addr, val, ts, 1, d_chal.p, ctx.stream);
     }
-    s.init.build(ctx); s.audit.build(ctx);
-    for (int m = 0; m < 3; m++) { s.read[m].build(ctx); s.write[m].build(ctx); }
+  }
+  {  // every layer of the 4 memory-sized and the 12 ops-sized product trees: one launch per layer (product_tree.rs:36-56)
+    auto build_group = [&](std::vector<ProdCircuit*> cs) {
+      for (size_t k = 0; k + 1 < cs[0]->num_layers; k++) {
+        size_t h = cs[0]->layer_len(k) / 2;
+        std::vector<u256*> outs; std::vector<const u256*> as, bs;
+        for (auto* c : cs) { outs.push_back(c->layer(k + 1)); as.push_back(c->layer(k)); bs.push_back(c->layer(k) + h); }
+        dev::hadamard_many(outs.data(), as.data(), bs.data(), (int)cs.size(), h, ctx.stream);
+      }
+    };
+    build_group({&S[0].init, &S[0].audit, &S[1].init, &S[1].audit});
+    build_group({&S[0].read[0], &S[0].read[1], &S[0].read[2], &S[0].write[0], &S[0].write[1], &S[0].write[2],
+                 &S[1].read[0], &S[1].read[1], &S[1].read[2], &S[1].write[0], &S[1].write[1], &S[1].write[2]});
   }
   ctx.sync();
   mark("build_layered_network", tb);
