@@ -16,7 +16,7 @@ CXX = "/usr/bin/g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU = ["kernels.cu", "kernels_sc.cu"]
 CPP = ["prover.cpp", "snark.cpp", "capi.cpp"]
-HDR = ["field.cuh", "curve.cuh", "kcommon.cuh", "dev.hpp", "host.hpp", "engine.hpp", "prover.hpp", "snark.hpp", os.path.join("..", "..", "include", "spartan_b200.h")]
+HDR = ["field.cuh", "mul_ptx.cuh", "curve.cuh", "kcommon.cuh", "dev.hpp", "host.hpp", "engine.hpp", "prover.hpp", "snark.hpp", os.path.join("..", "..", "include", "spartan_b200.h")]
 
 
 def _stale(target, deps):

@@ -40,6 +40,10 @@ inline u256 host_fp_mul(const u256& a, const u256& b);
 #define SP_HOST_FAST 0
 #endif
 
+}  // namespace sp
+#include "mul_ptx.cuh"
+namespace sp {
+
 // ---------------------------------------------------------------------------------------------- Fq
 // modulus / Montgomery constants (ristretto255.rs:248,304,307,315,323 split into 32-bit limbs)
 #define SPQ0 0x5cf5d3edu
@@ -85,6 +89,18 @@ SP_HD u256 fq_cond_sub_q(const u256& a) {
 
 #if defined(__CUDA_ARCH__)
 // carry-chain forms for the device: one asm block per chain so the condition-code register never crosses statements
+__device__ __forceinline__ u256 fq_csub_ptx(const u256& s) {   // s - q if s >= q else s   (s < 2q)
+  u256 d, r;
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, 0;\n\tsubc.cc.u32 %5, %14, 0;\n\tsubc.cc.u32 %6, %15, 0;\n\tsubc.cc.u32 %7, %16, %21;\n\tsubc.u32 %8, 0, 0;"
+      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7]), "=r"(borrow)
+      : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]),
+        "r"(SPQ0), "r"(SPQ1), "r"(SPQ2), "r"(SPQ3), "r"(SPQ7));
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = borrow ? s.v[i] : d.v[i];   // borrow set <=> s < q
+  return r;
+}
 __device__ __forceinline__ u256 fq_add_ptx(const u256& a, const u256& b) {
   u256 s, d;
   uint32_t borrow;
@@ -194,6 +210,8 @@ SP_HD u256 fq_mul(const u256& a, const u256& b) {
 SP_HD u256 fq_mul_impl(const u256& a, const u256& b) {
 #if SP_HOST_FAST
   return host_fq_mul(a, b);
+#elif defined(__CUDA_ARCH__) && !defined(SP_NO_PTX)
+  return fq_csub_ptx(fq_mul_ptx(a, b));   // generated carry-chain form (tools/gen_ptx_mul.py); the portable form below is the specification
 #else
   uint32_t t[10];
 #pragma unroll
@@ -380,6 +398,8 @@ SP_HD u256 fp_mul(const u256& a, const u256& b) {
 SP_HD u256 fp_mul_impl(const u256& a, const u256& b) {
 #if SP_HOST_FAST
   return host_fp_mul(a, b);
+#elif defined(__CUDA_ARCH__) && !defined(SP_NO_PTX)
+  return fp_mul_ptx(a, b);
 #else
   uint32_t t[16];
 #pragma unroll
