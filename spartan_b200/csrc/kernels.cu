@@ -501,65 +501,76 @@ __device__ __forceinline__ uint32_t msm_window(const u256& k, int w) {
   if (sh + WBITS > 32 && limb + 1 < 8) v |= k.v[limb + 1] << (32 - sh);
   return v & ((1u << WBITS) - 1u);
 }
-template <int WBITS, int GROUPS>
+__device__ __forceinline__ ge shfl_down_ge(const ge& p, int delta) {
+  ge r;
+  r.X = shfl_down_256(p.X, delta); r.Y = shfl_down_256(p.Y, delta); r.Z = shfl_down_256(p.Z, delta); r.T = shfl_down_256(p.T, delta);
+  return r;
+}
+// block-wide point sum: shuffle tree inside each warp (no barriers, so a warp that runs out of non-zero digits early reduces at once),
+// then the four warp leaders through shared memory
+__device__ __forceinline__ ge block_sum_ge_128(ge acc) {
+#pragma unroll 1
+  for (int d = 16; d > 0; d >>= 1) acc = ge_add(acc, shfl_down_ge(acc, d));
+  __shared__ ge sm[4];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { acc = ge_add(acc, sm[1]); acc = ge_add(acc, ge_add(sm[2], sm[3])); }
+  return acc;
+}
+template <int WBITS, int GROUPS, int CPT>
 __global__ void __launch_bounds__(128, SP_MSM_LB) k_msm_rows(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ scalars, size_t stride,
                                                              size_t R, const u256* __restrict__ blinds, size_t blind_base) {
   constexpr int NWIN = (253 + WBITS - 1) / WBITS;
   constexpr int WPT = (NWIN + GROUPS - 1) / GROUPS;   // windows per thread
-  constexpr int COLS = 128 / GROUPS;                  // columns per block
+  constexpr int COLS = 128 / GROUPS;                  // columns per block per pass; CPT passes amortise the reduction tree
   constexpr uint32_t HALF = 1u << (WBITS - 1);
   constexpr size_t DEPTH = (size_t)1 << (WBITS - 1);
   const size_t row = blockIdx.y;
   const size_t ncols = R + (blinds ? 1 : 0);
-  const size_t col = (size_t)blockIdx.x * COLS + threadIdx.x / GROUPS;
   const int g = threadIdx.x % GROUPS;
   ge acc = ge_identity();
-  if (col < ncols) {
+#pragma unroll 1
+  for (int pass = 0; pass < CPT; pass++) {
+    const size_t col = ((size_t)blockIdx.x * CPT + pass) * COLS + threadIdx.x / GROUPS;
+    if (col >= ncols) break;
     u256 k;
     size_t base;
     if (col < R) { k = ld256_ro(scalars + row * stride + col); base = col; }
     else { k = ld256_ro(blinds + row); base = blind_base; }
-    if (!fq_is_zero(k)) {
-      k = fq_from_mont(k);  // group.rs:110-113: scalars leave Montgomery form before the MSM
-      // carry into this thread's first window from the signed recoding of the lower windows
-      uint32_t carry = 0;
-      for (int w = 0; w < g * WPT; w++) carry = (msm_window<WBITS>(k, w) + carry) > HALF ? 1u : 0u;
-      const int w_end = (g + 1) * WPT < NWIN ? (g + 1) * WPT : NWIN;
-      const ge_niels* tb = table + (base * NWIN + (size_t)g * WPT) * DEPTH;
+    if (fq_is_zero(k)) continue;
+    k = fq_from_mont(k);  // group.rs:110-113: scalars leave Montgomery form before the MSM
+    // carry into this thread's first window from the signed recoding of the lower windows
+    uint32_t carry = 0;
+    for (int w = 0; w < g * WPT; w++) carry = (msm_window<WBITS>(k, w) + carry) > HALF ? 1u : 0u;
+    const int w_end = (g + 1) * WPT < NWIN ? (g + 1) * WPT : NWIN;
+    const ge_niels* tb = table + (base * NWIN + (size_t)g * WPT) * DEPTH;
 #pragma unroll 1
-      for (int w = g * WPT; w < w_end; w++, tb += DEPTH) {
-        uint32_t v = msm_window<WBITS>(k, w) + carry;
-        int d;
-        if (v > HALF) { d = (int)v - (int)(2 * HALF); carry = 1; } else { d = (int)v; carry = 0; }
-        if (d == 0) continue;
-        int ad = d < 0 ? -d : d;
-        const ge_niels* e = tb + (ad - 1);
-        ge_niels nl;
-        nl.ypx = ld256_ro(&e->ypx); nl.ymx = ld256_ro(&e->ymx); nl.t2d = ld256_ro(&e->t2d);
-        acc = ge_madd(acc, nl, d < 0);
-      }
+    for (int w = g * WPT; w < w_end; w++, tb += DEPTH) {
+      uint32_t v = msm_window<WBITS>(k, w) + carry;
+      int d;
+      if (v > HALF) { d = (int)v - (int)(2 * HALF); carry = 1; } else { d = (int)v; carry = 0; }
+      if (d == 0) continue;
+      int ad = d < 0 ? -d : d;
+      const ge_niels* e = tb + (ad - 1);
+      ge_niels nl;
+      nl.ypx = ld256_ro(&e->ypx); nl.ymx = ld256_ro(&e->ymx); nl.t2d = ld256_ro(&e->t2d);
+      acc = ge_madd(acc, nl, d < 0);
     }
   }
-  __shared__ ge sm[64];
-  for (int s = 64; s > 0; s >>= 1) {
-    if (threadIdx.x >= s && threadIdx.x < 2 * s) sm[threadIdx.x - s] = acc;
-    __syncthreads();
-    if (threadIdx.x < s) acc = ge_add(acc, sm[threadIdx.x]);
-    __syncthreads();
-  }
+  acc = block_sum_ge_128(acc);
   if (threadIdx.x == 0) st_ge(partial + row * gridDim.x + blockIdx.x, acc);
 }
-__global__ void __launch_bounds__(32) k_msm_reduce(ge* out, const ge* __restrict__ partial, int chunks) {
+__global__ void __launch_bounds__(128) k_msm_reduce(ge* out, const ge* __restrict__ partial, int chunks) {
   const size_t row = blockIdx.x;
   ge acc = ge_identity();
-  for (int c = threadIdx.x; c < chunks; c += 32) acc = ge_add(acc, ld_ge(partial + row * chunks + c));
-  __shared__ ge sm[16];
-  for (int s = 16; s > 0; s >>= 1) {
-    if (threadIdx.x >= s && threadIdx.x < 2 * s) sm[threadIdx.x - s] = acc;
-    __syncwarp();
-    if (threadIdx.x < s) acc = ge_add(acc, sm[threadIdx.x]);
-    __syncwarp();
-  }
+  for (int c = threadIdx.x; c < chunks; c += 128) acc = ge_add(acc, ld_ge(partial + row * chunks + c));
+  acc = block_sum_ge_128(acc);
+  if (threadIdx.x == 0) st_ge(out + row, acc);
+}
+__global__ void __launch_bounds__(32) k_msm_reduce_small(ge* out, const ge* __restrict__ partial, int chunks) {   // chunks <= 32: one warp per row
+  const size_t row = blockIdx.x;
+  ge acc = (int)threadIdx.x < chunks ? ld_ge(partial + row * chunks + threadIdx.x) : ge_identity();
+  for (int d = 16; d > 0; d >>= 1) if (d < 2 * chunks) acc = ge_add(acc, shfl_down_ge(acc, d));
   if (threadIdx.x == 0) st_ge(out + row, acc);
 }
 static int msm_pick_groups(size_t L, size_t R) {
@@ -570,20 +581,34 @@ static int msm_pick_groups(size_t L, size_t R) {
   if (cols * 4 >= target) return 4;
   return 8;
 }
-static size_t msm_chunks(size_t R1, int groups) { size_t cols = 128 / groups; return (R1 + cols - 1) / cols; }
-size_t msm_scratch_bytes(size_t L, size_t R) { return L * msm_chunks(R + 1, 8) * sizeof(ge); }
+static int msm_pick_cpt(size_t L, size_t ncols, int groups) {
+  // several column passes per thread amortise the block reduction, as long as the grid still oversubscribes the chip
+  size_t cols = 128 / groups;
+  size_t blocks4 = L * ((ncols + 4 * cols - 1) / (4 * cols));
+  return (ncols >= 4 * cols && blocks4 >= (size_t)sm_count() * 4) ? 4 : 1;
+}
+static size_t msm_chunks(size_t R1, int groups, int cpt) { size_t cols = (128 / groups) * (size_t)cpt; return (R1 + cols - 1) / cols; }
+size_t msm_scratch_bytes(size_t L, size_t R) { return L * msm_chunks(R + 1, 8, 1) * sizeof(ge); }
+template <int WBITS, int GROUPS>
+static void msm_launch2(int cpt, dim3 grid, cudaStream_t s, ge* pp, const ge_niels* table, const u256* sc, size_t stride, size_t R, const u256* bl,
+                        size_t blind_base) {
+  if (cpt == 4) k_msm_rows<WBITS, GROUPS, 4><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
+  else k_msm_rows<WBITS, GROUPS, 1><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
+}
 template <int WBITS>
-static void msm_launch(int groups, dim3 grid, cudaStream_t s, ge* pp, const ge_niels* table, const u256* sc, size_t stride, size_t R, const u256* bl,
+static void msm_launch(int groups, int cpt, dim3 grid, cudaStream_t s, ge* pp, const ge_niels* table, const u256* sc, size_t stride, size_t R, const u256* bl,
                        size_t blind_base) {
-  if (groups == 1) k_msm_rows<WBITS, 1><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
-  else if (groups == 4) k_msm_rows<WBITS, 4><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
-  else k_msm_rows<WBITS, 8><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
+  if (groups == 1) msm_launch2<WBITS, 1>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
+  else if (groups == 4) msm_launch2<WBITS, 4>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
+  else msm_launch2<WBITS, 8>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
 }
 void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
               void* scratch, cudaStream_t s) {
   ProfScope ps("msm_rows", 32.0 * (double)L * (double)R + 32.0 * (double)R, s);
+  const size_t ncols = R + (blinds ? 1 : 0);
   int groups = msm_pick_groups(L, R);
-  size_t chunks = msm_chunks(R + (blinds ? 1 : 0), groups);
+  int cpt = msm_pick_cpt(L, ncols, groups);
+  size_t chunks = msm_chunks(ncols, groups, cpt);
   ge* partial = (ge*)scratch;
   for (size_t row0 = 0; row0 < L; row0 += 32768) {   // gridDim.y limit 65535
     size_t rows = L - row0 < 32768 ? L - row0 : 32768;
@@ -591,12 +616,13 @@ void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, si
     const u256* sc = scalars + row0 * stride;
     const u256* bl = blinds ? blinds + row0 : nullptr;
     ge* pp = partial + row0 * chunks;
-    if (wbits == 8) msm_launch<8>(groups, grid, s, pp, table, sc, stride, R, bl, blind_base);
-    else if (wbits == 13) msm_launch<13>(groups, grid, s, pp, table, sc, stride, R, bl, blind_base);
+    if (wbits == 8) msm_launch<8>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
+    else if (wbits == 13) msm_launch<13>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
     else throw std::runtime_error("spartan_b200: unsupported MSM window width");
     SP_LAUNCHED();
   }
-  k_msm_reduce<<<(unsigned)L, 32, 0, s>>>(out, partial, (int)chunks);
+  if (chunks <= 32) k_msm_reduce_small<<<(unsigned)L, 32, 0, s>>>(out, partial, (int)chunks);
+  else k_msm_reduce<<<(unsigned)L, 128, 0, s>>>(out, partial, (int)chunks);
   SP_LAUNCHED(); check("msm_rows");
 }
 
