@@ -499,8 +499,8 @@ def prof_report():
     out = {}
     for item in buf.value.decode().split(";"):
         if item:
-            name, n, ms, by = item.split(":")
-            out[name] = {"launches": int(n), "ms": float(ms), "bytes": float(by)}
+            name, n, ms, by, bb, bms = item.split(":")
+            out[name] = {"launches": int(n), "ms": float(ms), "bytes": float(by), "largest_bytes": float(bb), "largest_ms": float(bms)}
     return out
 
 

@@ -43,10 +43,10 @@ void prof_enable(bool on) {
   for (auto& r : g_recs) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
   g_recs.clear();
 }
-// "name:launches:total_ms:total_algorithmic_bytes;" per family, after a device synchronise
+// "name:launches:total_ms:total_algorithmic_bytes:largest_launch_bytes:largest_launch_ms;" per family, after a device synchronise
 std::string prof_report() {
   cudaDeviceSynchronize();
-  struct Agg { double ms = 0, bytes = 0; unsigned long long n = 0; };
+  struct Agg { double ms = 0, bytes = 0, big_bytes = 0, big_ms = 0; unsigned long long n = 0; };
   std::vector<std::pair<std::string, Agg>> aggs;
   for (auto& r : g_recs) {
     float ms = 0;
@@ -55,9 +55,12 @@ std::string prof_report() {
     for (; k < aggs.size(); k++) if (aggs[k].first == r.name) break;
     if (k == aggs.size()) aggs.push_back({r.name, Agg()});
     aggs[k].second.ms += ms; aggs[k].second.bytes += r.bytes; aggs[k].second.n++;
+    if (r.bytes > aggs[k].second.big_bytes) { aggs[k].second.big_bytes = r.bytes; aggs[k].second.big_ms = ms; }
   }
   std::string out;
-  for (auto& a : aggs) out += a.first + ":" + std::to_string(a.second.n) + ":" + std::to_string(a.second.ms) + ":" + std::to_string(a.second.bytes) + ";";
+  for (auto& a : aggs)
+    out += a.first + ":" + std::to_string(a.second.n) + ":" + std::to_string(a.second.ms) + ":" + std::to_string(a.second.bytes) + ":" +
+           std::to_string(a.second.big_bytes) + ":" + std::to_string(a.second.big_ms) + ";";
   return out;
 }
 

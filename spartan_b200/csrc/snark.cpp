@@ -415,11 +415,16 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   {
     std::vector<ProdCircuit*> prods = {&S[0].read[0], &S[0].read[1], &S[0].read[2], &S[0].write[0], &S[0].write[1], &S[0].write[2],
                                        &S[1].read[0], &S[1].read[1], &S[1].read[2], &S[1].write[0], &S[1].write[1], &S[1].write[2]};
+    auto tq = std::chrono::steady_clock::now();
     batched_prove(ctx, prods, dotps, T, pl.proof_ops, rand_ops);
+    mark("  product_layer_ops(12 trees + 6 dotp)", tq);
+    tq = std::chrono::steady_clock::now();
     std::vector<ProdCircuit*> mems = {&S[0].init, &S[0].audit, &S[1].init, &S[1].audit};
     std::vector<DotpCircuit> none;
     batched_prove(ctx, mems, none, T, pl.proof_mem, rand_mem);
+    mark("  product_layer_mem(4 trees)", tq);
   }
+  auto th = std::chrono::steady_clock::now();
 
   // ---- HashLayerProof::prove (sparse_mlpoly.rs:722-835)
   HashLayerProof& hl = ep.proof_hash_layer;
@@ -453,6 +458,8 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
     hl.eval_val.assign(ev.begin() + 18, ev.begin() + 21);
     hl.row_audit_ts = ev[21]; hl.col_audit_ts = ev[22];
   }
+  mark("  hash_layer_evaluations", th);
+  th = std::chrono::steady_clock::now();
   Cp dummy;
   {  // DerefsEvalProof::prove (sparse_mlpoly.rs:125-149, prove_single :80-123)
     T.append_protocol_name("Derefs evaluation proof");
@@ -467,6 +474,8 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
     T.append_scalar("joint_claim_eval", joint);
     polyeval_prove(ctx, derefs.p, nullptr, r_joint, joint, nullptr, gens.gens_derefs, T, tape, hl.proof_derefs, dummy);
   }
+  mark("  polyeval_derefs(2^23)", th);
+  th = std::chrono::steady_clock::now();
   {  // ops decommitment (sparse_mlpoly.rs:766-797)
     std::vector<Fq> evals;
     for (auto* v : {&hl.row_addr, &hl.row_read_ts, &hl.col_addr, &hl.col_read_ts, &hl.eval_val}) evals.insert(evals.end(), v->begin(), v->end());
@@ -479,6 +488,8 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
     T.append_scalar("joint_claim_eval_ops", joint);
     polyeval_prove(ctx, enc.comb_ops.p, nullptr, r_joint, joint, nullptr, gens.gens_ops, T, tape, hl.proof_ops, dummy);
   }
+  mark("  polyeval_ops(2^24)", th);
+  th = std::chrono::steady_clock::now();
   {  // mem decommitment (sparse_mlpoly.rs:799-824)
     std::vector<Fq> evals = {hl.row_audit_ts, hl.col_audit_ts};
     T.append_scalars("claim_evals_mem", evals);
@@ -489,6 +500,7 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
     T.append_scalar("joint_claim_eval_mem", joint);
     polyeval_prove(ctx, enc.comb_mem.p, nullptr, r_joint, joint, nullptr, gens.gens_mem, T, tape, hl.proof_mem, dummy);
   }
+  mark("  polyeval_mem(2^22)", th);
   mark("evalproof_layered_network", tn);
   mark("R1CSEvalProof::prove", t_eval);
   mark("SNARK::prove", t_start);
