@@ -231,10 +231,23 @@ def run_b200(args):
         if roof:
             roof["note"] = ("algorithmic bytes = 48 B x len per table per launch (read len*32, write len/2*32); CUDA-event time per launch on the prover stream; "
                             "ncu --set full of the same kernel: profiles/ (dram bytes ~0.78x algorithmic on the first ZK round: tables partly L2-resident)")
+        if roof:
+            # ncu --set full of the first (largest single-instance) launch of this kernel in the step: profiles/r01_ncu_full_sc_fold_eval.txt
+            roof["traffic"] = 156.3e6
+            roof["traffic_note"] = "dram__bytes_read+write of the captured first ZK-sumcheck launch (algorithmic 201.3e6 B: half of the tables are still L2-resident)"
         roof_msm = rl(dom[0], dom[1], "hbm")
         roof_msm["note"] = ("dominant kernel by time; fixed-base ristretto255 comb, INTEGER-ALU bound (20 table lookups x 7 field multiplications per term): its "
                             "algorithmic bytes are only scalars + bases, so the HBM fraction is honestly tiny")
         kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
+        # BASELINE.json's second metric: MSM point additions per second, on the largest MSM of the step (the 2048 x 4096 commitment to the
+        # dereferenced values, 2^23 terms with 253-bit scalars): reference-equivalent adds (33 per term, dalek Pippenger w=8) and executed table additions
+        m = rep.get("msm_rows")
+        msm_rate = None
+        if m and m["largest_ms"]:
+            terms = m["largest_bytes"] / 32.0
+            msm_rate = {"terms": terms, "ms": m["largest_ms"], "Mpoint_adds_per_s_reference_equivalent": 33.0 * terms / (m["largest_ms"] / 1e3) / 1e6,
+                        "Mpoint_adds_per_s_executed": 20.0 * terms / (m["largest_ms"] / 1e3) / 1e6, "Mterms_per_s": terms / (m["largest_ms"] / 1e3) / 1e6,
+                        "what": "largest msm_rows launch of the step: commit_nondet_witness, 2048 rows x 4096 generators (sparse_mlpoly.rs:64-67)"}
     if rank != 0:
         sd.finalize()
         return
@@ -251,7 +264,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": (d1 - d0) // args.steps, "api": "spartan_b200.SNARK.prove -> sp_snark_prove (C ABI), assignment in pinned host memory"},
         "gpu_launches": launches,
         "proof_bytes": len(proof.bytes),
-        "roofline": roof, "roofline_dominant_kernel": roof_msm, "kernels_ms_per_step": kernels,
+        "roofline": roof, "roofline_dominant_kernel": roof_msm, "msm": msm_rate, "kernels_ms_per_step": kernels,
         "phases_ms": {k: round(v, 3) for k, v in ctx.timings().items()},
         "cpu_baseline": cpu,
         "reference_published": {"value": 2 ** 20 / 39.1297568, "unit": UNIT, "what": "README.md:375 SNARK::prove 2^20 on one core of an i7-1065G7 (other hardware)"},
