@@ -22,6 +22,14 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the CPU arm's OpenMP loops are short: spinning worker threads on every logical CPU slow it down 10x on the 2 x 32-core / 128-thread host
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
+
+def host_threads():
+    """threads for the CPU arm: one per physical core (the oracle's loops do not profit from SMT siblings)"""
+    n = os.cpu_count() or 1
+    return max(1, n // 2) if n >= 4 else n
 
 METRIC = "R1CS constraints/sec (SNARK::prove, synthetic R1CS)"
 UNIT = "constraints/s"
@@ -95,7 +103,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle.spartan_ref import core as oc, r1cs, spark
-    cores = int(oc.lib.oracle_max_threads())
+    cores = host_threads()
     oc.lib.oracle_set_threads(cores)
     n = 1 << CPU_SAMPLE_LOG
     inst, vars_arr, inputs = r1cs.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, 0)
@@ -126,7 +134,7 @@ def run_reference(args):
 def cpu_baseline_leg(budget_s=20.0):
     """bounded oracle run on the box's host cores, reported beside the GPU number (rank 0, N = 1 only)"""
     from oracle.spartan_ref import core as oc, r1cs, spark
-    cores = int(oc.lib.oracle_max_threads())
+    cores = host_threads()
     oc.lib.oracle_set_threads(cores)
     n = 1 << CPU_SAMPLE_LOG
     inst, vars_arr, inputs = r1cs.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, 0)
@@ -230,11 +238,11 @@ def run_b200(args):
         roof = rl("sc_fold_eval", fold) if fold else None
         if roof:
             roof["note"] = ("algorithmic bytes = 48 B x len per table per launch (read len*32, write len/2*32); CUDA-event time per launch on the prover stream; "
-                            "ncu --set full of the same kernel: profiles/ (dram bytes ~0.78x algorithmic on the first ZK round: tables partly L2-resident)")
+                            "ncu --set full of the same kernel: profiles/r01_ncu_full_sc_fold_eval.txt")
         if roof:
             # ncu --set full of the first (largest single-instance) launch of this kernel in the step: profiles/r01_ncu_full_sc_fold_eval.txt
-            roof["traffic"] = 156.3e6
-            roof["traffic_note"] = "dram__bytes_read+write of the captured first ZK-sumcheck launch (algorithmic 201.3e6 B: half of the tables are still L2-resident)"
+            roof["traffic"] = 170.3e6
+            roof["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of the captured first ZK-sumcheck launch of the step (4 tables of 2^20: algorithmic 201.3e6 B; part of the tables is still L2-resident from the SpMV that produced them)"
         roof_msm = rl(dom[0], dom[1], "hbm")
         roof_msm["note"] = ("dominant kernel by time; fixed-base ristretto255 comb, INTEGER-ALU bound (20 table lookups x 7 field multiplications per term): its "
                             "algorithmic bytes are only scalars + bases, so the HBM fraction is honestly tiny")

@@ -82,6 +82,7 @@ void hadamard_many(u256* const* outs, const u256* const* as, const u256* const* 
 void from_u64(u256* out, const uint64_t* v, size_t n, cudaStream_t s);
 void from_bytes_wide(u256* out, const uint8_t* in64, size_t n, cudaStream_t s);
 void batch_invert_elems(u256* inout, size_t n, cudaStream_t s);
+void to_canonical(u256* out, const u256* in, size_t n, cudaStream_t s);   // Montgomery -> canonical little-endian integers (transcript bytes)
 void gather(u256* out, const u256* mem, const uint32_t* idx, size_t n, cudaStream_t s);
 // hash layer of the SPARK memory check: out = ts*r^2 + val*r + addr - g  (sparse_mlpoly.rs:545-600)
 // addr == null: addr = index i;  ts == null: ts = 0;  ts_plus_one adds one.   d_rg = [r_hash, r_multiset]

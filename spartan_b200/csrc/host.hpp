@@ -158,7 +158,13 @@ class Transcript {  // merlin::Transcript + ProofTranscript (transcript.rs:5-37)
   }
   void absorb(const uint8_t* d, size_t n) {
     uint8_t* b = bytes();
-    for (size_t i = 0; i < n; i++) { b[pos_] ^= d[i]; if (++pos_ == R) run_f(); }
+    while (n) {   // block-wise: up to the rate boundary at a time
+      size_t room = (size_t)R - pos_, take = n < room ? n : room;
+      uint8_t* dst = b + pos_;
+      for (size_t i = 0; i < take; i++) dst[i] ^= d[i];
+      pos_ = (uint8_t)(pos_ + take); d += take; n -= take;
+      if (pos_ == R) run_f();
+    }
   }
   void begin_op(uint8_t flags, bool more) {
     if (more) return;

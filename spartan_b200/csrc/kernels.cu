@@ -313,6 +313,13 @@ void from_bytes_wide(u256* out, const uint8_t* in64, size_t n, cudaStream_t s) {
   k_from_wide<<<grid_for(n, 256, 8), 256, 0, s>>>(out, in64, n);
   SP_LAUNCHED(); check("from_bytes_wide");
 }
+__global__ void k_to_canonical(u256* out, const u256* __restrict__ in, size_t n) {   // Scalar::to_bytes (ristretto255.rs:419) for a whole vector
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st256(out + i, fq_from_mont(ld256_ro(in + i)));
+}
+void to_canonical(u256* out, const u256* in, size_t n, cudaStream_t s) {
+  k_to_canonical<<<grid_for(n, 128, 8), 128, 0, s>>>(out, in, n);
+  SP_LAUNCHED(); check("to_canonical");
+}
 __global__ void k_invert(u256* x, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st256(x + i, fq_inv(ld256(x + i)));
 }

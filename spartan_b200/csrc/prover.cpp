@@ -429,10 +429,11 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
 }
 
 // DotProductProofLog::prove (nizk/mod.rs:440-525).  d_x: device x_vec (n, consumed); a_vec on the host (it is absorbed by the transcript).
+// d_x: device x_vec (n, consumed); d_avec: device a_vec (n, consumed); a_canon: the canonical bytes of a_vec, which the transcript absorbs
 static void dotproduct_log_prove(Ctx& ctx, const PolyCommitmentGens& gens, Transcript& T, RandomTape& tape, u256* d_x, const Fq& blind_x,
-                                 const std::vector<Fq>& a_vec, const Fq& y, const Fq& blind_y, DotProductProofLog& proof, Cp& Cy_out) {
+                                 u256* d_avec, const std::vector<uint8_t>& a_canon, const Fq& y, const Fq& blind_y, DotProductProofLog& proof, Cp& Cy_out) {
   T.append_protocol_name("dot product proof (log)");
-  size_t n = a_vec.size();
+  size_t n = a_canon.size() / 32;
   if (gens.n != n) throw std::runtime_error("spartan_b200: DotProductProofLog size mismatch");
   const GenSet& gs = *gens.gens_n.set;
   Fq d = tape.random_scalar("d");
@@ -448,14 +449,12 @@ static void dotproduct_log_prove(Ctx& ctx, const PolyCommitmentGens& gens, Trans
   T.append_point("Cx", cx[0].b);
   Cy_out = commit1(gens.gens_1, y, blind_y);
   T.append_point("Cy", Cy_out.b);
-  T.append_scalars("a", a_vec);
+  T.append_scalar_bytes("a", a_canon.data(), n);
   Fq r = T.challenge_scalar("r");
   Fq blind_Gamma = blind_x + r * blind_y;
-  DevBuf<u256> d_b(n);
-  dev::h2d(d_b.p, a_vec.data(), n * sizeof(u256), ctx.stream);
   Fq x_hat, a_hat, rhat_Gamma;
   ge g_hat;
-  bullet_prove(ctx, T, gens, r, d_x, d_b.p, n, blind_Gamma, blinds_vec, proof.bullet_reduction_proof, x_hat, a_hat, g_hat, rhat_Gamma);
+  bullet_prove(ctx, T, gens, r, d_x, d_avec, n, blind_Gamma, blinds_vec, proof.bullet_reduction_proof, x_hat, a_hat, g_hat, rhat_Gamma);
   Fq y_hat = x_hat * a_hat;
   // delta = d*g_hat + r_delta*h (gens_hat, nizk/mod.rs:497-505)
   Term th[1] = {{gens.gens_1.h, r_delta}};
@@ -475,15 +474,23 @@ void polyeval_prove(Ctx& ctx, const u256* d_Z, const std::vector<Fq>* blinds_opt
   T.append_protocol_name("polynomial evaluation proof");
   size_t ell = r.size(), lv = ell / 2;
   size_t L_size = (size_t)1 << lv, R_size = (size_t)1 << (ell - lv);
-  std::vector<Fq> Lr(r.begin(), r.begin() + lv), Rr(r.begin() + lv, r.end());
-  std::vector<Fq> Lev = host_eq_evals(Lr), Rev = host_eq_evals(Rr);  // compute_factored_evals (dense_mlpoly.rs:90-98)
-  Fq LZ_blind = Fq::zero();
-  if (blinds_opt) for (size_t i = 0; i < L_size; i++) LZ_blind += (*blinds_opt)[i] * Lev[i];
-  Fq blind_Zr = blind_Zr_opt ? *blind_Zr_opt : Fq::zero();
-  DevBuf<u256> d_L(L_size), d_LZ(R_size), tmp(64 * R_size);
-  dev::h2d(d_L.p, Lev.data(), L_size * sizeof(u256), ctx.stream);
+  // compute_factored_evals (dense_mlpoly.rs:90-98) on the device; the R half is also needed as canonical bytes (the transcript absorbs a_vec)
+  DevBuf<u256> d_r(r.size() + 1), d_L(L_size), d_R(R_size), d_Rc(R_size), d_LZ(R_size), tmp(64 * R_size), eqs(2 * ((size_t)1 << ((ell - lv + 1) / 2)) + 8);
+  dev::h2d(d_r.p, r.data(), r.size() * sizeof(u256), ctx.stream);
+  dev::eq_evals(d_L.p, d_r.p, (int)lv, eqs.p, ctx.stream);
+  dev::eq_evals(d_R.p, d_r.p + lv, (int)(ell - lv), eqs.p, ctx.stream);
+  dev::to_canonical(d_Rc.p, d_R.p, R_size, ctx.stream);
+  std::vector<uint8_t> a_canon(32 * R_size);
+  dev::d2h(a_canon.data(), d_Rc.p, 32 * R_size, ctx.stream);
   dev::bound_rows(d_LZ.p, d_Z, d_L.p, L_size, R_size, tmp.p, ctx.stream);  // DensePolynomial::bound (dense_mlpoly.rs:206-213)
-  dotproduct_log_prove(ctx, gens, T, tape, d_LZ.p, LZ_blind, Rev, Zr, blind_Zr, proof.proof, C_Zr);
+  Fq LZ_blind = Fq::zero();
+  if (blinds_opt) {
+    std::vector<Fq> Lev = ctx.download(d_L.p, L_size);
+    for (size_t i = 0; i < L_size; i++) LZ_blind += (*blinds_opt)[i] * Lev[i];
+  }
+  ctx.sync();
+  Fq blind_Zr = blind_Zr_opt ? *blind_Zr_opt : Fq::zero();
+  dotproduct_log_prove(ctx, gens, T, tape, d_LZ.p, LZ_blind, d_R.p, a_canon, Zr, blind_Zr, proof.proof, C_Zr);
 }
 
 // ================================================================================================ instance
