@@ -30,10 +30,12 @@ extern "C" {
 #define SP_ERR_INVALID_SCALAR 5    /* R1CSError::InvalidScalar */
 #define SP_ERR_INVALID_INPUTS 6    /* R1CSError::InvalidNumberOfInputs */
 #define SP_ERR_INTERNAL 7
+#define SP_ERR_INVALID_POINT 8     /* CompressedRistretto::decompress() == None (ProofVerifyError::DecompressionError, src/errors.rs:10) */
 
 typedef struct sp_ctx sp_ctx;
 typedef struct sp_poly sp_poly;           /* DensePolynomial.Z on the device          src/dense_mlpoly.rs:18-22 */
 typedef struct sp_gens sp_gens;           /* MultiCommitGens + fixed-base tables      src/commitments.rs:8-12 */
+typedef struct sp_points sp_points;       /* a caller-supplied &[GroupElement] on the device   src/group.rs:8-9 */
 typedef struct sp_instance sp_instance;   /* Instance (R1CSShape + digest)            src/lib.rs:111-114 */
 typedef struct sp_nizk_gens sp_nizk_gens; /* NIZKGens                                 src/lib.rs:468-486 */
 typedef struct sp_snark_gens sp_snark_gens;     /* SNARKGens                          src/lib.rs:277-309 */
@@ -95,6 +97,19 @@ int sp_msm(sp_ctx* ctx, const sp_gens* g, const uint64_t* scalars_mont, size_t n
 int sp_commit_rows(sp_ctx* ctx, const sp_gens* g, const sp_poly* p, size_t L, size_t R, const uint64_t* blinds_mont, uint8_t* out32);
 int sp_point_decompress_check(sp_ctx* ctx, const uint8_t* in32, size_t n, int* ok);        /* CompressedRistretto::decompress */
 int sp_point_roundtrip(sp_ctx* ctx, const uint8_t* in32, size_t n, uint8_t* out32);        /* decompress().compress() on the device */
+
+/* ---- variable-base MSM on caller-supplied points (bucket method; no precomputed tables — for point sets that are used once or are too
+ * large for window tables, e.g. the 2^24-point standalone MSM of BASELINE.json).                                   group.rs:98-117 */
+/* points cross as n 32-byte encodings; SP_ERR_INVALID_POINT if any fails to decompress */
+int sp_points_upload(sp_ctx* ctx, const uint8_t* compressed32, size_t n, sp_points** out);
+/* MultiCommitGens::new(n, label).G (the h generator is not kept)                                                   commitments.rs:15-33 */
+int sp_points_derive(sp_ctx* ctx, const uint8_t* label, size_t label_len, size_t n, sp_points** out);
+size_t sp_points_len(const sp_points* p);
+void sp_points_free(sp_points* p);
+int sp_points_export(sp_ctx* ctx, const sp_points* p, size_t offset, size_t n, uint8_t* out32);
+/* GroupElement::vartime_multiscalar_mul(scalars[0..n), points[offset..offset+n)).compress() */
+int sp_msm_var(sp_ctx* ctx, const sp_points* p, size_t offset, const uint64_t* scalars_mont, size_t n, uint8_t out32[32]);
+int sp_msm_var_resident(sp_ctx* ctx, const sp_points* p, size_t offset, const sp_poly* scalars, uint8_t out32[32]);
 
 /* ---- instances                                                                           lib.rs:111-274 */
 /* Instance::new: entries are (row, col, canonical 32-byte value); rows < num_cons, cols < num_vars + 1 + num_inputs */

@@ -30,6 +30,7 @@ lib = _load()
 lib.sp_last_error.restype = C.c_char_p
 lib.sp_kernel_launches.restype = C.c_ulonglong
 lib.sp_poly_len.restype = C.c_size_t
+lib.sp_points_len.restype = C.c_size_t
 _vp, _sz = C.c_void_p, C.c_size_t
 
 
@@ -246,6 +247,54 @@ class MultiCommitGens:
         try:
             if getattr(self, "h", None):
                 lib.sp_gens_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Points:
+    """A caller-supplied `&[GroupElement]` (group.rs:8-9) resident on the device, for the variable-base MSM (bucket method, no tables)."""
+
+    def __init__(self, compressed, ctx=None):
+        """compressed: list of 32-byte ristretto255 encodings; raises if any does not decompress"""
+        self.ctx = ctx or default_context()
+        h = _vp()
+        self.ctx.check(lib.sp_points_upload(self.ctx.h, C.c_char_p(b"".join(compressed)), _sz(len(compressed)), C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def derive(cls, n, label, ctx=None):
+        """MultiCommitGens::new(n, label).G without window tables (commitments.rs:15-33)"""
+        o = cls.__new__(cls)
+        o.ctx = ctx or default_context()
+        h = _vp()
+        o.ctx.check(lib.sp_points_derive(o.ctx.h, C.c_char_p(label), _sz(len(label)), _sz(n), C.byref(h)))
+        o.h = h
+        return o
+
+    def __len__(self):
+        return int(lib.sp_points_len(self.h))
+
+    def export(self, offset=0, n=None):
+        n = len(self) - offset if n is None else n
+        out = C.create_string_buffer(32 * n + 1)
+        self.ctx.check(lib.sp_points_export(self.ctx.h, self.h, _sz(offset), _sz(n), out))
+        return [out.raw[32 * i:32 * i + 32] for i in range(n)]
+
+    def msm(self, scalars, offset=0):
+        """GroupElement::vartime_multiscalar_mul(scalars, points[offset:offset+len(scalars)]).compress()  (group.rs:98-117)"""
+        out = C.create_string_buffer(32)
+        if isinstance(scalars, DensePolynomial):
+            self.ctx.check(lib.sp_msm_var_resident(self.ctx.h, self.h, _sz(offset), scalars.h, out))
+        else:
+            s = _limbs(scalars)
+            self.ctx.check(lib.sp_msm_var(self.ctx.h, self.h, _sz(offset), _p(s), _sz(len(s)), out))
+        return out.raw
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib.sp_points_free(self.h)
                 self.h = None
         except Exception:
             pass

@@ -11,6 +11,7 @@ using namespace sp;
 struct sp_ctx { Ctx c; explicit sp_ctx(int d) : c(d) {} };
 struct sp_poly { Ctx* ctx; DevBuf<u256> d; size_t len; };
 struct sp_gens { std::unique_ptr<GenSet> set; size_t n; };
+struct sp_points { Ctx* ctx; DevBuf<ge_niels> pts; size_t n; mutable DevBuf<uint8_t> scratch; mutable size_t scratch_bytes = 0; };
 struct sp_instance { Instance inst; };
 struct sp_nizk_gens { std::unique_ptr<R1CSGens> g; };
 struct sp_snark_gens { std::unique_ptr<SnarkGens> g; };
@@ -269,6 +270,101 @@ int sp_point_roundtrip(sp_ctx* ctx, const uint8_t* in32, size_t n, uint8_t* out3
   dev::compress_batch(d_out.p, pts.p, n, ctx->c.stream);
   dev::d2h(out32, d_out.p, 32 * n, ctx->c.stream);
   ctx->c.sync();
+  SP_CATCH(ctx)
+}
+
+// ---- variable-base MSM (kernels_pip.cu)
+static void points_from_ge(sp_ctx* ctx, sp_points* P, const ge* d_ge, size_t n) {
+  P->ctx = &ctx->c; P->n = n;
+  P->pts.alloc(n ? n : 1);
+  dev::points_to_niels(P->pts.p, d_ge, n, ctx->c.stream);
+}
+int sp_points_upload(sp_ctx* ctx, const uint8_t* in32, size_t n, sp_points** out) {
+  SP_TRY(ctx)
+  DevBuf<uint8_t> d_in(32 * n + 1);
+  DevBuf<ge> g(n + 1);
+  DevBuf<int> ok(n + 1);
+  dev::h2d(d_in.p, in32, 32 * n, ctx->c.stream);
+  dev::decompress_batch(g.p, ok.p, d_in.p, n, ctx->c.stream);
+  std::vector<int> h_ok(n);
+  dev::d2h(h_ok.data(), ok.p, sizeof(int) * n, ctx->c.stream);
+  ctx->c.sync();
+  for (size_t i = 0; i < n; i++)
+    if (!h_ok[i]) throw SpError(SP_ERR_INVALID_POINT, "points_upload: encoding " + std::to_string(i) + " is not a ristretto255 point");
+  std::unique_ptr<sp_points> P(new sp_points);
+  points_from_ge(ctx, P.get(), g.p, n);
+  ctx->c.sync();
+  *out = P.release();
+  SP_CATCH(ctx)
+}
+int sp_points_derive(sp_ctx* ctx, const uint8_t* label, size_t label_len, size_t n, sp_points** out) {
+  SP_TRY(ctx)
+  // the same SHAKE256(label || basepoint) stream as MultiCommitGens::new, squeezed and mapped in slabs so 2^24 points need no 1 GiB staging buffer
+  static const uint8_t basepoint[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+                                        0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
+  std::vector<uint8_t> seed(label, label + label_len);
+  seed.insert(seed.end(), basepoint, basepoint + 32);
+  Shake256 xof(seed.data(), seed.size());
+  std::unique_ptr<sp_points> P(new sp_points);
+  P->ctx = &ctx->c; P->n = n;
+  P->pts.alloc(n ? n : 1);
+  const size_t slab = (size_t)1 << 18;
+  std::vector<uint8_t> uni(64 * std::min(slab, n ? n : 1));
+  DevBuf<uint8_t> d_uni(uni.size());
+  DevBuf<ge> g(std::min(slab, n ? n : 1));
+  for (size_t i0 = 0; i0 < n; i0 += slab) {
+    size_t m = std::min(slab, n - i0);
+    xof.squeeze(uni.data(), 64 * m);
+    dev::h2d(d_uni.p, uni.data(), 64 * m, ctx->c.stream);
+    dev::gens_from_uniform(g.p, d_uni.p, m, ctx->c.stream);
+    dev::points_to_niels(P->pts.p + i0, g.p, m, ctx->c.stream);
+    ctx->c.sync();
+  }
+  *out = P.release();
+  SP_CATCH(ctx)
+}
+size_t sp_points_len(const sp_points* p) { return p->n; }
+void sp_points_free(sp_points* p) { delete p; }
+int sp_points_export(sp_ctx* ctx, const sp_points* p, size_t offset, size_t n, uint8_t* out32) {
+  SP_TRY(ctx)
+  if (offset + n > p->n) throw SpError(SP_ERR_INVALID_ARG, "points_export: range outside the point set");
+  // 1 * P_i through the MSM path's own mixed addition, then compress
+  DevBuf<ge> g(n + 1);
+  DevBuf<uint8_t> comp(32 * n + 1);
+  dev::niels_to_ge(g.p, p->pts.p + offset, n, ctx->c.stream);
+  dev::compress_batch(comp.p, g.p, n, ctx->c.stream);
+  dev::d2h(out32, comp.p, 32 * n, ctx->c.stream);
+  ctx->c.sync();
+  SP_CATCH(ctx)
+}
+static void msm_var_run(sp_ctx* ctx, const sp_points* p, size_t offset, const u256* d_scalars, size_t n, uint8_t out32[32]) {
+  if (offset + n > p->n) throw SpError(SP_ERR_INVALID_ARG, "msm_var: range outside the point set");
+  DevBuf<ge> out(1);
+  DevBuf<uint8_t> comp(32);
+  if (n == 0) {
+    ge id = ge_identity();
+    dev::h2d(out.p, &id, sizeof(ge), ctx->c.stream);
+  } else {
+    const char* cenv = getenv("SP_PIP_WINDOW");
+    dev::PipPlan plan = dev::pip_plan(n, cenv ? atoi(cenv) : 0);
+    const size_t need = dev::pip_scratch_bytes(plan);
+    if (need > p->scratch_bytes) { p->scratch.alloc(need); p->scratch_bytes = need; }   // the sort workspace stays with the point set
+    dev::msm_var(out.p, p->pts.p + offset, d_scalars, plan, p->scratch.p, ctx->c.stream);
+  }
+  dev::compress_batch(comp.p, out.p, 1, ctx->c.stream);
+  dev::d2h(out32, comp.p, 32, ctx->c.stream);
+  ctx->c.sync();
+}
+int sp_msm_var(sp_ctx* ctx, const sp_points* p, size_t offset, const uint64_t* scalars, size_t n, uint8_t out32[32]) {
+  SP_TRY(ctx)
+  DevBuf<u256> d(n ? n : 1);
+  dev::h2d(d.p, scalars, n * 32, ctx->c.stream);
+  msm_var_run(ctx, p, offset, d.p, n, out32);
+  SP_CATCH(ctx)
+}
+int sp_msm_var_resident(sp_ctx* ctx, const sp_points* p, size_t offset, const sp_poly* scalars, uint8_t out32[32]) {
+  SP_TRY(ctx)
+  msm_var_run(ctx, p, offset, scalars->d.p, scalars->len, out32);
   SP_CATCH(ctx)
 }
 

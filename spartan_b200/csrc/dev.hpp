@@ -112,5 +112,14 @@ size_t msm_scratch_bytes(size_t L, size_t R);
 void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
               void* scratch, cudaStream_t s);
 
+// ---- variable-base MSM on arbitrary points (bucket method; kernels_pip.cu).  pts: affine-niels form of the caller's points.
+struct PipPlan { size_t n = 0; int c = 0, nwin = 0, G = 32; uint32_t nb = 0; size_t tile = 0, ntiles = 0, S = 0, max_items = 0; };
+PipPlan pip_plan(size_t n, int c_override);   // c_override = 0: pick the window width from n
+size_t pip_scratch_bytes(const PipPlan& p);
+void points_to_niels(ge_niels* out, const ge* in, size_t n, cudaStream_t s);
+void niels_to_ge(ge* out, const ge_niels* in, size_t n, cudaStream_t s);
+// out = sum_i scalars[i] * pts[i]   (scalars Montgomery-form, device-resident; scratch >= pip_scratch_bytes(p))
+void msm_var(ge* out, const ge_niels* pts, const u256* scalars, const PipPlan& p, void* scratch, cudaStream_t s);
+
 }  // namespace dev
 }  // namespace sp

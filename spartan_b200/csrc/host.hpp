@@ -87,6 +87,29 @@ class Keccak {
   }
 };
 
+struct Shake256 {  // streaming SHAKE256 XOF (sha3's Shake256 + XofReader as used by commitments.rs:16-24): absorb once, squeeze in pieces
+  uint64_t st[25];
+  size_t pos = 0;
+  Shake256(const uint8_t* in, size_t inlen) {
+    memset(st, 0, sizeof st);
+    uint8_t* sb = reinterpret_cast<uint8_t*>(st);
+    const size_t rate = 136;
+    while (inlen >= rate) { for (size_t i = 0; i < rate; i++) sb[i] ^= in[i]; Keccak::f1600(st); in += rate; inlen -= rate; }
+    for (size_t i = 0; i < inlen; i++) sb[i] ^= in[i];
+    sb[inlen] ^= 0x1f; sb[rate - 1] ^= 0x80;
+    Keccak::f1600(st);
+  }
+  void squeeze(uint8_t* out, size_t n) {
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(st);
+    while (n) {
+      if (pos == 136) { Keccak::f1600(st); pos = 0; }
+      size_t m = n < 136 - pos ? n : 136 - pos;
+      memcpy(out, sb + pos, m);
+      out += m; n -= m; pos += m;
+    }
+  }
+};
+
 class Transcript {  // merlin::Transcript + ProofTranscript (transcript.rs:5-37)
  public:
   explicit Transcript(const std::string& label) {
