@@ -384,7 +384,7 @@ SP_HD u256 fp_sub(const u256& a, const u256& b) {
 }
 SP_HD u256 fp_neg(const u256& a) { return fp_sub(fp_zero(), a); }
 
-#if defined(__CUDA_ARCH__) && defined(SP_NI_FP)
+#if defined(__CUDA_ARCH__)
 static __device__ __noinline__ u256 fp_mul_ni(u256 a, u256 b);
 #endif
 SP_HD u256 fp_mul_impl(const u256& a, const u256& b);
@@ -427,10 +427,20 @@ SP_HD u256 fp_mul_impl(const u256& a, const u256& b) {
   return r;
 #endif
 }
-#if defined(__CUDA_ARCH__) && defined(SP_NI_FP)
+#if defined(__CUDA_ARCH__)
 static __device__ __noinline__ u256 fp_mul_ni(u256 a, u256 b) { return fp_mul_impl(a, b); }
 #endif
 SP_HD u256 fp_sqr(const u256& a) { return fp_mul(a, a); }
+// out-of-line multiplication for the long exponentiation chains (inversion, square roots: ~265 multiplications each): there the call
+// overhead is irrelevant and one shared body keeps compress/decompress kernels small
+SP_HD u256 fp_mulc(const u256& a, const u256& b) {
+#if defined(__CUDA_ARCH__)
+  return fp_mul_ni(a, b);
+#else
+  return fp_mul_impl(a, b);
+#endif
+}
+SP_HD u256 fp_sqrc(const u256& a) { return fp_mulc(a, a); }
 SP_HD u256 fp_mul_small(const u256& a, uint32_t k) {
   u256 r;
   uint64_t c = 0;
@@ -474,33 +484,34 @@ SP_HD bool fp_eq(const u256& a, const u256& b) { return fq_eq(fp_canon(a), fp_ca
 SP_HD bool fp_is_neg(const u256& a) { return (fp_canon(a).v[0] & 1u) != 0; }
 SP_HD u256 fp_abs(const u256& a) { return fp_is_neg(a) ? fp_neg(a) : a; }
 SP_HD u256 fp_sqn(u256 a, int n) {
-  for (int i = 0; i < n; i++) a = fp_sqr(a);
+#pragma unroll 1
+  for (int i = 0; i < n; i++) a = fp_sqrc(a);
   return a;
 }
 
 // z^(2^250-1) and z^11, shared by inversion and the square-root exponent
 SP_HD void fp_pow250(const u256& z, u256& t250, u256& z11) {
-  u256 z2 = fp_sqr(z);
-  u256 z9 = fp_mul(fp_sqn(z2, 2), z);
-  z11 = fp_mul(z9, z2);
-  u256 z_5_0 = fp_mul(fp_sqr(z11), z9);
-  u256 z_10_0 = fp_mul(fp_sqn(z_5_0, 5), z_5_0);
-  u256 z_20_0 = fp_mul(fp_sqn(z_10_0, 10), z_10_0);
-  u256 z_40_0 = fp_mul(fp_sqn(z_20_0, 20), z_20_0);
-  u256 z_50_0 = fp_mul(fp_sqn(z_40_0, 10), z_10_0);
-  u256 z_100_0 = fp_mul(fp_sqn(z_50_0, 50), z_50_0);
-  u256 z_200_0 = fp_mul(fp_sqn(z_100_0, 100), z_100_0);
-  t250 = fp_mul(fp_sqn(z_200_0, 50), z_50_0);
+  u256 z2 = fp_sqrc(z);
+  u256 z9 = fp_mulc(fp_sqn(z2, 2), z);
+  z11 = fp_mulc(z9, z2);
+  u256 z_5_0 = fp_mulc(fp_sqrc(z11), z9);
+  u256 z_10_0 = fp_mulc(fp_sqn(z_5_0, 5), z_5_0);
+  u256 z_20_0 = fp_mulc(fp_sqn(z_10_0, 10), z_10_0);
+  u256 z_40_0 = fp_mulc(fp_sqn(z_20_0, 20), z_20_0);
+  u256 z_50_0 = fp_mulc(fp_sqn(z_40_0, 10), z_10_0);
+  u256 z_100_0 = fp_mulc(fp_sqn(z_50_0, 50), z_50_0);
+  u256 z_200_0 = fp_mulc(fp_sqn(z_100_0, 100), z_100_0);
+  t250 = fp_mulc(fp_sqn(z_200_0, 50), z_50_0);
 }
 SP_HD u256 fp_inv(const u256& z) {
   u256 t250, z11;
   fp_pow250(z, t250, z11);
-  return fp_mul(fp_sqn(t250, 5), z11);
+  return fp_mulc(fp_sqn(t250, 5), z11);
 }
 SP_HD u256 fp_pow22523(const u256& z) {
   u256 t250, z11;
   fp_pow250(z, t250, z11);
-  return fp_mul(fp_sqn(t250, 2), z);
+  return fp_mulc(fp_sqn(t250, 2), z);
 }
 
 // curve / ristretto constants (RFC 9496 section 4.1)
