@@ -116,11 +116,8 @@ SP_HD void u256_to_bytes(uint8_t* b, const u256& a) {
 }
 
 // RFC 9496 4.3.2 Encode -> canonical field element s (caller stores its 32 little-endian bytes)
-SP_HD u256 ristretto_encode(const ge& p) {
-  u256 u1 = fp_mul(fp_add(p.Z, p.Y), fp_sub(p.Z, p.Y));
-  u256 u2 = fp_mul(p.X, p.Y);
-  u256 invsqrt;
-  (void)fp_sqrt_ratio_i(invsqrt, fp_one(), fp_mul(u1, fp_sqr(u2)));
+// RFC 9496 4.3.2 Encode, split around the inverse square root (see fp_sqrt_ratio_pre/post)
+SP_HD u256 ristretto_encode_post(const ge& p, const u256& u1, const u256& u2, const u256& invsqrt) {
   u256 den1 = fp_mul(invsqrt, u1), den2 = fp_mul(invsqrt, u2);
   u256 z_inv = fp_mul(fp_mul(den1, den2), p.T);
   u256 ix0 = fp_mul(p.X, fp_SQRT_M1()), iy0 = fp_mul(p.Y, fp_SQRT_M1());
@@ -132,6 +129,13 @@ SP_HD u256 ristretto_encode(const ge& p) {
   if (fp_is_neg(fp_mul(x, z_inv))) y = fp_neg(y);
   u256 s = fp_abs(fp_mul(den_inv, fp_sub(p.Z, y)));
   return fp_canon(s);
+}
+SP_HD u256 ristretto_encode(const ge& p) {
+  u256 u1 = fp_mul(fp_add(p.Z, p.Y), fp_sub(p.Z, p.Y));
+  u256 u2 = fp_mul(p.X, p.Y);
+  u256 invsqrt;
+  (void)fp_sqrt_ratio_i(invsqrt, fp_one(), fp_mul(u1, fp_sqr(u2)));
+  return ristretto_encode_post(p, u1, u2, invsqrt);
 }
 
 // RFC 9496 4.3.1 Decode; false on a non-canonical / invalid encoding

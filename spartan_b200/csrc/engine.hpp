@@ -1,5 +1,8 @@
 // spartan_b200 — device context, buffers and generator sets shared by the host prover.
 #pragma once
+#include <chrono>
+#include <cstdlib>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -41,6 +44,7 @@ struct Ctx {
   std::string last_error;
   // per-phase timers (profile feature of the reference, src/timer.rs): label -> milliseconds of the last prove
   std::vector<std::pair<std::string, double>> timings;
+  std::map<std::string, double> fine;   // accumulated sub-phase timers (SP_FINE_TIMERS=1), flushed into `timings` by the prove entry points
 
   explicit Ctx(int dev);
   ~Ctx();
@@ -62,6 +66,14 @@ struct Ctx {
 
 // One SHAKE256 generator stream (a `label` of MultiCommitGens::new, commitments.rs:15-33) expanded to `nbases` points,
 // with the fixed-base window table on the device and host copies of the tables of a few named bases.
+struct FineTimer {  // host wall-clock accumulator for latency hunting; a no-op unless SP_FINE_TIMERS is set
+  Ctx& ctx; const char* name; std::chrono::steady_clock::time_point t0; bool on;
+  static bool enabled() { static const bool e = getenv("SP_FINE_TIMERS") != nullptr; return e; }
+  FineTimer(Ctx& c, const char* n) : ctx(c), name(n), on(enabled()) { if (on) t0 = std::chrono::steady_clock::now(); }
+  void stop() { if (on) { ctx.fine[name] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); on = false; } }
+  ~FineTimer() { stop(); }
+};
+
 struct GenSet {
   Ctx* ctx;
   std::string label;
@@ -77,7 +89,7 @@ struct GenSet {
     if (it == host_tab.end()) throw std::runtime_error("spartan_b200: no host table for generator " + std::to_string(base));
     return it->second;
   }
-  ge host_point(size_t base) const;  // 1 * G_base from the host table
+  hge host_point(size_t base) const;  // 1 * G_base from the host table
 };
 
 // A MultiCommitGens view (commitments.rs:8-12): G = set.G[off .. off+n), h = set.G[h]
@@ -88,7 +100,7 @@ struct CommitKey {
 
 struct Term { size_t base; Fq k; };
 // sum of k_i * G_{base_i} over host tables
-ge host_commit(const GenSet& gs, const Term* terms, size_t nterms);
+hge host_commit(const GenSet& gs, const Term* terms, size_t nterms);
 inline Cp host_commit_c(const GenSet& gs, const std::vector<Term>& t) { return compress(host_commit(gs, t.data(), t.size())); }
 
 }  // namespace sp

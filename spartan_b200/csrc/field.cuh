@@ -523,11 +523,15 @@ SP_HD u256 fp_INVSQRT_A_MINUS_D() { u256 r = {{0x805d40eau, 0x99c8fdaau, 0x5a417
 SP_HD u256 fp_ONE_MINUS_D_SQ() { u256 r = {{0x945fc176u, 0xe27c09c1u, 0xcd5e350fu, 0x2c81a138u, 0xbe70dfe4u, 0x9994abddu, 0xb2b3e0d7u, 0x029072a8u}}; return r; }
 SP_HD u256 fp_D_MINUS_ONE_SQ() { u256 r = {{0x44ed4d20u, 0x31ad5aaau, 0xb01e1999u, 0xd29e4a2cu, 0x529b4eebu, 0x4cdcd32fu, 0xf66c2241u, 0x5968b37au}}; return r; }
 
-// RFC 9496 4.2 SQRT_RATIO_M1
-SP_HD bool fp_sqrt_ratio_i(u256& out, const u256& u, const u256& v) {
+// RFC 9496 4.2 SQRT_RATIO_M1, split around its one exponentiation so that callers can run several exponentiations side by side
+SP_HD u256 fp_sqrt_ratio_pre(const u256& u, const u256& v, u256& uv3) {   // returns u*v^7 (to be raised to (p-5)/8), sets uv3 = u*v^3
   u256 v3 = fp_mul(fp_sqr(v), v);
   u256 v7 = fp_mul(fp_sqr(v3), v);
-  u256 r = fp_mul(fp_mul(u, v3), fp_pow22523(fp_mul(u, v7)));
+  uv3 = fp_mul(u, v3);
+  return fp_mul(u, v7);
+}
+SP_HD bool fp_sqrt_ratio_post(u256& out, const u256& u, const u256& v, const u256& uv3, const u256& pw) {
+  u256 r = fp_mul(uv3, pw);
   u256 check = fp_mul(v, fp_sqr(r));
   u256 neg_u = fp_neg(u);
   bool correct = fp_eq(check, u);
@@ -536,6 +540,11 @@ SP_HD bool fp_sqrt_ratio_i(u256& out, const u256& u, const u256& v) {
   if (flipped || flipped_i) r = fp_mul(r, fp_SQRT_M1());
   out = fp_abs(r);
   return correct || flipped;
+}
+SP_HD bool fp_sqrt_ratio_i(u256& out, const u256& u, const u256& v) {
+  u256 uv3;
+  u256 base = fp_sqrt_ratio_pre(u, v, uv3);
+  return fp_sqrt_ratio_post(out, u, v, uv3, fp_pow22523(base));
 }
 
 #if SP_HOST_FAST

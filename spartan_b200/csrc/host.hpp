@@ -12,6 +12,7 @@
 #include <vector>
 #include "curve.cuh"
 #include "field.cuh"
+#include "host_fe51.hpp"
 
 namespace sp {
 
@@ -217,13 +218,22 @@ struct Cp {  // CompressedGroup (group.rs:7)
   uint8_t b[32];
   bool operator==(const Cp& o) const { return memcmp(b, o.b, 32) == 0; }
 };
-inline Cp compress(const ge& p) { Cp c; u256_to_bytes(c.b, ristretto_encode(p)); return c; }
+inline Cp compress(const hge& p) { Cp c; uint8_t o[1][32]; hge_encode_n<1>(&p, o); memcpy(c.b, o[0], 32); return c; }
+inline Cp compress(const ge& p) { return compress(to_hge(p)); }
+// two encodings at once: the two 252-squaring exponentiations run in lockstep, so the CPU overlaps their dependency chains
+inline void compress2(const hge& p, const hge& q, Cp& cp, Cp& cq) {
+  hge pq[2] = {p, q};
+  uint8_t o[2][32];
+  hge_encode_n<2>(pq, o);
+  memcpy(cp.b, o[0], 32); memcpy(cq.b, o[1], 32);
+}
+inline void compress2(const ge& p, const ge& q, Cp& cp, Cp& cq) { compress2(to_hge(p), to_hge(q), cp, cq); }
 
 // 8-bit signed fixed-base windows for one generator: 32 windows x 128 affine-niels entries (copied from the device table)
 struct HostBaseTable {
-  std::vector<ge_niels> e;  // [w*128 + d-1]
+  std::vector<hniels> e;  // [w*128 + d-1], radix-2^51 limbs (host_fe51.hpp)
 };
-inline void host_fixed_mul_acc(ge& acc, const HostBaseTable& tb, const Fq& k) {
+inline void host_fixed_mul_acc(hge& acc, const HostBaseTable& tb, const Fq& k) {
   if (k.is_zero()) return;
   u256 c = k.canonical();
   uint32_t carry = 0;
@@ -233,7 +243,7 @@ inline void host_fixed_mul_acc(ge& acc, const HostBaseTable& tb, const Fq& k) {
     if (v > 128u) { d = (int)v - 256; carry = 1; } else { d = (int)v; carry = 0; }
     if (d == 0) continue;
     int ad = d < 0 ? -d : d;
-    acc = ge_madd(acc, tb.e[(size_t)w * 128 + ad - 1], d < 0);
+    acc = hge_madd(acc, tb.e[(size_t)w * 128 + ad - 1], d < 0);
   }
 }
 

@@ -51,6 +51,15 @@ int spt_dbl(const uint8_t* a32, uint8_t* out32) {
   out256(out32, ristretto_encode(ge_dbl(a)));
   return 1;
 }
+// compress2 (host.hpp): two encodings with interleaved exponentiations, of a+b and 2a (non-trivial Z)
+int spt_compress2(const uint8_t* a32, const uint8_t* b32, uint8_t* out64) {
+  ge a, b;
+  if (!ristretto_decode(a, in256(a32)) || !ristretto_decode(b, in256(b32))) return 0;
+  sp::Cp c1, c2;
+  sp::compress2(ge_add(a, b), ge_dbl(a), c1, c2);   // the ge overload converts to radix 2^51 and encodes there
+  memcpy(out64, c1.b, 32); memcpy(out64 + 32, c2.b, 32);
+  return 1;
+}
 int spt_scalarmul(const uint8_t* k_canonical, const uint8_t* a32, uint8_t* out32) {
   ge a;
   if (!ristretto_decode(a, in256(a32))) return 0;
@@ -65,13 +74,33 @@ int spt_fixed_base_mul(const uint8_t* k_mont, const uint8_t* a32, uint8_t* out32
   tb.e.resize(32 * 128);
   for (int w = 0; w < 32; w++) {
     ge acc = P;
-    for (int d = 0; d < 128; d++) { tb.e[(size_t)w * 128 + d] = ge_to_niels(acc); acc = ge_add(acc, P); }
+    for (int d = 0; d < 128; d++) { tb.e[(size_t)w * 128 + d] = to_hniels(ge_to_niels(acc)); acc = ge_add(acc, P); }
     for (int k = 0; k < 8; k++) P = ge_dbl(P);
   }
-  ge acc = ge_identity();
+  hge acc = hge_identity();
   Fq k; memcpy(&k.m, k_mont, 32);
   host_fixed_mul_acc(acc, tb, k);
-  out256(out32, ristretto_encode(acc));
+  Cp c = compress(acc);
+  memcpy(out32, c.b, 32);
+  return 1;
+}
+// radix-2^51 host arithmetic (host_fe51.hpp) against the 8x32-limb field code: mul, sqr, add, sub, freeze on raw 256-bit inputs
+void spt_fe51_ops(const uint8_t* a32, const uint8_t* b32, uint8_t* out160) {
+  fe51 a = fe_from_u256(in256(a32)), b = fe_from_u256(in256(b32));
+  fe_to_bytes(out160, fe_mul(a, b));
+  fe_to_bytes(out160 + 32, fe_sqr(a));
+  fe_to_bytes(out160 + 64, fe_add(a, b));
+  fe_to_bytes(out160 + 96, fe_sub(a, b));
+  fe_to_bytes(out160 + 128, fe_mul(fe_sub(fe_add(a, b), fe_neg(a)), fe_add(fe_add(a, a), fe_add(b, b))));   // lazily-reduced operands
+}
+// hge (host_fe51.hpp): k*A by signed 4-bit windows, A+B, 2A -> encodings
+int spt_hge_ops(const uint8_t* k_canonical, const uint8_t* a32, const uint8_t* b32, uint8_t* out96) {
+  ge a, b;
+  if (!ristretto_decode(a, in256(a32)) || !ristretto_decode(b, in256(b32))) return 0;
+  Cp c1 = compress(hge_scalarmul(in256(k_canonical), to_hge(a)));
+  Cp c2, c3;
+  compress2(hge_add(to_hge(a), to_hge(b)), hge_dbl(to_hge(a)), c2, c3);
+  memcpy(out96, c1.b, 32); memcpy(out96 + 32, c2.b, 32); memcpy(out96 + 64, c3.b, 32);
   return 1;
 }
 // transcript

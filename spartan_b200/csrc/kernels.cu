@@ -230,6 +230,50 @@ void dot_many(u256* out, const u256* const* a_list, int count, const u256* b, si
   SP_LAUNCHED(); check("dot_many");
 }
 
+// out[k] = <a_k, b_k> for up to 8 independent pairs in one launch; the results can also be published to the host (HostSig)
+struct DotPairs { const u256* a[8]; const u256* b[8]; };
+__global__ void __launch_bounds__(256) k_dot_pairs(DotPairs dp, size_t n, u256* partials, unsigned int* counters, u256* out, HostSig sig) {
+  const u256* a = dp.a[blockIdx.y];
+  const u256* b = dp.b[blockIdx.y];
+  u256 acc[1] = {fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc[0] = fq_add(acc[0], fq_mul(ld256_ro(a + i), ld256_ro(b + i)));
+  block_reduce_finish<1>(acc, partials, counters, out, 1, sig);
+}
+void dot_pairs(u256* out, const u256* const* a_list, const u256* const* b_list, int count, size_t n, void* scratch, cudaStream_t s, HostSig sig) {
+  ProfScope ps("dot", 64.0 * (double)n * count, s);
+  if (count > 8) throw std::runtime_error("spartan_b200: dot_pairs supports at most 8 pairs");
+  DotPairs dp;
+  for (int i = 0; i < count; i++) { dp.a[i] = a_list[i]; dp.b[i] = b_list[i]; }
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(n, 256, 1), count);
+  k_dot_pairs<<<grid, 256, 0, s>>>(dp, n, partials, counters, out, sig);
+  SP_LAUNCHED(); check("dot_pairs");
+}
+
+// first elements of up to 64 tables -> one contiguous array (+ the host, through HostSig): the layer claims of the batched product proofs
+struct HeadBatch { const u256* p[64]; };
+__global__ void __launch_bounds__(64) k_heads(HeadBatch hb, int count, u256* out, HostSig sig) {
+  if ((int)threadIdx.x < count) {
+    u256 v = ld256(hb.p[threadIdx.x]);
+    st256(out + threadIdx.x, v);
+    if (sig.host_out) st256(sig.host_out + threadIdx.x, v);
+  }
+  if (sig.flag) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
+  }
+}
+void heads(u256* out, const u256* const* tables, int count, cudaStream_t s, HostSig sig) {
+  if (count > 64) throw std::runtime_error("spartan_b200: heads supports at most 64 tables");
+  HeadBatch hb;
+  for (int i = 0; i < count; i++) hb.p[i] = tables[i];
+  k_heads<<<1, 64, 0, s>>>(hb, count, out, sig);
+  SP_LAUNCHED(); check("heads");
+}
+
 // DensePolynomial::bound (dense_mlpoly.rs:206-213): out[i] = sum_j L[j]*Z[j*R+i].  Column-per-thread (coalesced over i),
 // rows split into gridDim.y slabs whose partial sums land in scratch and are combined by a second tiny kernel.
 __global__ void __launch_bounds__(128) k_bound_rows_partial(u256* part, const u256* __restrict__ Z, const u256* __restrict__ L, size_t L_size,

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 
 namespace sp {
 
@@ -106,21 +107,23 @@ GenSet::GenSet(Ctx* c, const std::string& label_, size_t nbases_, const std::vec
     DevBuf<ge_niels> small(dev::table_entries(hb.size(), 8));
     dev::build_tables(small.p, sel.p, hb.size(), 8, ctx->stream);
     for (size_t i = 0; i < hb.size(); i++) {
+      std::vector<ge_niels> raw(32 * 128);
+      dev::d2h(raw.data(), small.p + i * 32 * 128, sizeof(ge_niels) * 32 * 128, ctx->stream);
+      ctx->sync();
       HostBaseTable t;
       t.e.resize(32 * 128);
-      dev::d2h(t.e.data(), small.p + i * 32 * 128, sizeof(ge_niels) * 32 * 128, ctx->stream);
-      ctx->sync();
+      for (size_t e = 0; e < raw.size(); e++) t.e[e] = to_hniels(raw[e]);
       host_tab[hb[i]] = std::move(t);
     }
   }
   ctx->sync();
 }
-ge GenSet::host_point(size_t base) const {
-  ge acc = ge_identity();
-  return ge_madd(acc, tab(base).e[0], false);
+hge GenSet::host_point(size_t base) const {
+  hge acc = hge_identity();
+  return hge_madd(acc, tab(base).e[0], false);
 }
-ge host_commit(const GenSet& gs, const Term* terms, size_t nterms) {
-  ge acc = ge_identity();
+hge host_commit(const GenSet& gs, const Term* terms, size_t nterms) {
+  hge acc = hge_identity();
   for (size_t i = 0; i < nterms; i++) host_fixed_mul_acc(acc, gs.tab(terms[i].base), terms[i].k);
   return acc;
 }
@@ -197,7 +200,7 @@ static ProductProof product_prove(const CommitKey& g, Transcript& T, RandomTape&
 }
 // DotProductProof::prove (nizk/mod.rs:311-370); Cx is passed in when the caller already holds commit(x_vec; blind_x)
 // `pre` (optional): tape draws made ahead of time in the reference's order, with the commitments that depend on the tape only
-struct DotPre { std::vector<Fq> d_vec; Fq r_delta, r_beta; Cp delta; ge r_beta_h; };
+struct DotPre { std::vector<Fq> d_vec; Fq r_delta, r_beta; Cp delta; hge r_beta_h; };
 static DotProductProof dotproduct_prove(const CommitKey& g1, const CommitKey& gn, Transcript& T, RandomTape& tape, const std::vector<Fq>& x_vec,
                                         const Fq& blind_x, const std::vector<Fq>& a_vec, const Fq& y, const Fq& blind_y, const Cp* Cx_known,
                                         const DotPre* pre = nullptr) {
@@ -215,7 +218,7 @@ static DotProductProof dotproduct_prove(const CommitKey& g1, const CommitKey& gn
   T.append_point("delta", p.delta.b);
   Fq dot = Fq::zero();
   for (size_t i = 0; i < n; i++) dot += a_vec[i] * d_vec[i];
-  if (pre) { Term t1[1] = {{g1.off, dot}}; p.beta = compress(ge_add(host_commit(*g1.set, t1, 1), pre->r_beta_h)); }
+  if (pre) { Term t1[1] = {{g1.off, dot}}; p.beta = compress(hge_add(host_commit(*g1.set, t1, 1), pre->r_beta_h)); }
   else p.beta = commit1(g1, dot, r_beta);
   T.append_point("beta", p.beta.b);
   Fq c = T.challenge_scalar("c");
@@ -258,7 +261,7 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
   //   delta_j = commit(d_vec_j; r_delta_j) and the blind halves blinds_poly[j]*h, blinds_evals[j]*h, r_beta_j*h.
   const size_t nco = (size_t)degree + 1;
   std::vector<DotPre> pre(num_rounds);
-  std::vector<ge> bp_h(num_rounds), be_h(num_rounds);
+  std::vector<hge> bp_h(num_rounds), be_h(num_rounds);
   {
     std::vector<Fq> dmat(num_rounds * nco), rdel(num_rounds), rbet(num_rounds);
     for (size_t j = 0; j < num_rounds; j++) {
@@ -288,12 +291,12 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
     dev::d2h(deltas.data(), d_c.p, 32 * num_rounds, ctx.stream);
     dev::d2h(pts.data(), d_pts.p + num_rounds, 3 * num_rounds * sizeof(ge), ctx.stream);
     ctx.sync();
-    for (size_t j = 0; j < num_rounds; j++) { pre[j].delta = deltas[j]; pre[j].r_beta_h = pts[j]; bp_h[j] = pts[num_rounds + j]; be_h[j] = pts[2 * num_rounds + j]; }
+    for (size_t j = 0; j < num_rounds; j++) { pre[j].delta = deltas[j]; pre[j].r_beta_h = to_hge(pts[j]); bp_h[j] = to_hge(pts[num_rounds + j]); be_h[j] = to_hge(pts[2 * num_rounds + j]); }
   }
   auto commit_poly_pre = [&](const std::vector<Fq>& coeffs, size_t j) {   // commit(coeffs; blinds_poly[j]; gens_n) = sum coeff_i*G_i + (blinds_poly[j]*h)
     std::vector<Term> t;
     for (size_t i = 0; i < coeffs.size(); i++) t.push_back({gn.off + i, coeffs[i]});
-    return compress(ge_add(host_commit(*gn.set, t.data(), t.size()), bp_h[j]));
+    return compress(hge_add(host_commit(*gn.set, t.data(), t.size()), bp_h[j]));
   };
   dev::ScInst inst;
   for (int t = 0; t < 4; t++) inst.t[t] = t < nt ? tables[t] : nullptr;
@@ -305,7 +308,10 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
   dev::sc_eval(kind, &inst, 1, len, d_out, ctx.red.p, ctx.stream, sig);
   for (size_t j = 0; j < num_rounds; j++) {
     Fq e[3];
+    FineTimer fw(ctx, "zk wait evals");
     ctx.wait_sig(sig);
+    fw.stop();
+    FineTimer fh(ctx, "zk host commit_poly+challenge");
     memcpy(e, ctx.host_res, sizeof e);
     std::vector<Fq> evals = {e[0], claim_per_round - e[0], e[1]};
     if (degree == 3) evals.push_back(e[2]);
@@ -319,10 +325,12 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
     if (j + 1 < num_rounds) { sig = ctx.next_sig(); dev::sc_fold_eval(kind, &inst, 1, len, r_j.m, d_out, ctx.red.p, ctx.stream, sig); }
     else dev::fold_top(tables, nt, len, r_j.m, ctx.stream);
     len >>= 1;
+    fh.stop();
+    FineTimer fs(ctx, "zk host sigma (overlaps kernel)");
 
     Fq eval = poly.evaluate(r_j);
     Term te[1] = {{g1.off, eval}};
-    Cp comm_eval = compress(ge_add(host_commit(*g1.set, te, 1), be_h[j]));   // eval*G + blinds_evals[j]*h
+    Cp comm_eval = compress(hge_add(host_commit(*g1.set, te, 1), be_h[j]));   // eval*G + blinds_evals[j]*h
     T.append_point("comm_claim_per_round", comm_claim_per_round.b);
     T.append_point("comm_eval", comm_eval.b);
     std::vector<Fq> w = T.challenge_vector("combine_two_claims_to_one", 2);
@@ -377,49 +385,77 @@ void append_poly_commitment(Transcript& T, const char* label, const PolyCommitme
 
 // BulletReductionProof::prove (nizk/bullet.rs:32-132) with Q = r*G1 and H = h folded into host fixed-base terms, and the
 // generator vector left unfolded (see k_ipa_lr in kernels.cu).  d_a / d_b are consumed (folded in place).
-static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens, const Fq& r_scale, u256* d_a, u256* d_b, size_t n, const Fq& blind,
-                         const std::vector<std::pair<Fq, Fq>>& blinds_vec, BulletReductionProof& proof, Fq& a_hat, Fq& b_hat, ge& g_hat, Fq& blind_final) {
+static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens, const std::function<Fq()>& get_r_scale, u256* d_a, u256* d_b, size_t n,
+                         const Fq& blind, const std::vector<std::pair<Fq, Fq>>& blinds_vec, BulletReductionProof& proof, Fq& a_hat, Fq& b_hat, ge& g_hat,
+                         Fq& blind_final) {
   const GenSet& gs = *gens.gens_n.set;
-  DevBuf<u256> svec(n), lr(2 * n);
-  DevBuf<ge> pts(2);
+  const size_t rounds = blinds_vec.size();
+  DevBuf<u256> svec(n), lr(2 * n), d_bl(2 * rounds + 1);
+  DevBuf<ge> pts(2), d_bh(2 * rounds + 1);
   dev::fill_one(svec.p, n, ctx.stream);
-  ctx.ensure_scratch(dev::msm_scratch_bytes(2, n) + 64);
+  ctx.ensure_scratch(dev::msm_scratch_bytes(2 * rounds + 2, n) + 64);
+  // blind_L[k]*H and blind_R[k]*H depend on the tape only: one batched launch up front (rows with no generator terms, just the blind)
+  std::vector<ge> bh(2 * rounds);
+  if (rounds) {
+    std::vector<Fq> bl(2 * rounds);
+    for (size_t k = 0; k < rounds; k++) { bl[2 * k] = blinds_vec[k].first; bl[2 * k + 1] = blinds_vec[k].second; }
+    dev::h2d(d_bl.p, bl.data(), bl.size() * sizeof(u256), ctx.stream);
+    dev::msm_rows(d_bh.p, gs.table.p, gs.wbits, lr.p, 0, 2 * rounds, 0, d_bl.p, gens.gens_n.h, ctx.scratch.p, ctx.stream);
+    dev::d2h(bh.data(), d_bh.p, bh.size() * sizeof(ge), ctx.stream);   // pageable target: completes before the call returns
+  }
   u256* d_c = ctx.small.p + 16;  // c_L, c_R
   blind_final = blind;
+  Fq r_scale = Fq::zero();
   size_t cur = n, k = 0;
   while (cur != 1) {
     size_t half = cur / 2;
-    dev::dot(d_c, d_a, d_b + half, half, ctx.red.p, ctx.stream);          // c_L = <a_L, b_R>   bullet.rs:78
-    dev::dot(d_c + 1, d_a + half, d_b, half, ctx.red.p, ctx.stream);      // c_R = <a_R, b_L>   bullet.rs:79
+    FineTimer f1(ctx, "ipa launch");
+    const u256* da[2] = {d_a, d_a + half};
+    const u256* db[2] = {d_b + half, d_b};
+    dev::HostSig sig = ctx.next_sig();
+    dev::dot_pairs(d_c, da, db, 2, half, ctx.red.p, ctx.stream, sig);     // c_L = <a_L, b_R>, c_R = <a_R, b_L>   bullet.rs:78-79
     dev::ipa_lr_scalars(lr.p, lr.p + n, d_a, svec.p, cur, n, ctx.stream);
     dev::msm_rows(pts.p, gs.table.p, gs.wbits, lr.p, n, 2, n, nullptr, 0, ctx.scratch.p, ctx.stream);
-    dev::d2h(ctx.pinned, d_c, 64, ctx.stream);
     dev::d2h(ctx.pinned + 64, pts.p, 2 * sizeof(ge), ctx.stream);
-    ctx.sync();
+    f1.stop();
+    // the transcript work that precedes the first round (absorbing a_vec, deriving r) runs while the device computes round 0
+    if (k == 0) r_scale = get_r_scale();
+    FineTimer f2(ctx, "ipa wait c");
+    ctx.wait_sig(sig);
+    f2.stop();
+    FineTimer f3(ctx, "ipa host c*Q (overlaps MSM)");
     Fq c_L, c_R;
-    memcpy(&c_L, ctx.pinned, 32); memcpy(&c_R, ctx.pinned + 32, 32);
+    memcpy(&c_L, ctx.host_res, 32); memcpy(&c_R, ctx.host_res + 1, 32);
+    // + c_L*Q + blind_L*H with Q = r*G1 (nizk/mod.rs:479-480), H = gens_n.h   (bullet.rs:83-97)
+    Term tl[1] = {{gens.gens_1.off, c_L * r_scale}};
+    Term tr[1] = {{gens.gens_1.off, c_R * r_scale}};
+    hge hl = hge_add(host_commit(gs, tl, 1), to_hge(bh[2 * k]));
+    hge hr = hge_add(host_commit(gs, tr, 1), to_hge(bh[2 * k + 1]));
+    f3.stop();
+    FineTimer f4(ctx, "ipa wait MSM");
+    ctx.sync();
+    f4.stop();
+    FineTimer f5(ctx, "ipa host compress+transcript");
     ge Lg, Rg;
     memcpy(&Lg, ctx.pinned + 64, sizeof(ge)); memcpy(&Rg, ctx.pinned + 64 + sizeof(ge), sizeof(ge));
-    const Fq& blind_L = blinds_vec[k].first;
-    const Fq& blind_R = blinds_vec[k].second;
-    // + c_L*Q + blind_L*H with Q = r*G1 (nizk/mod.rs:479-480), H = gens_n.h   (bullet.rs:83-97)
-    Term tl[2] = {{gens.gens_1.off, c_L * r_scale}, {gens.gens_n.h, blind_L}};
-    Term tr[2] = {{gens.gens_1.off, c_R * r_scale}, {gens.gens_n.h, blind_R}};
-    Cp Lc = compress(ge_add(Lg, host_commit(gs, tl, 2)));
-    Cp Rc = compress(ge_add(Rg, host_commit(gs, tr, 2)));
+    Cp Lc, Rc;
+    compress2(hge_add(to_hge(Lg), hl), hge_add(to_hge(Rg), hr), Lc, Rc);
     T.append_point("L", Lc.b);
     T.append_point("R", Rc.b);
     Fq u = T.challenge_scalar("u");
     Fq u_inv = u.inv();
+    f5.stop();
     dev::ipa_fold_ab(d_a, d_b, half, u.m, u_inv.m, ctx.stream);
     dev::ipa_update_s(svec.p, half, n, u.m, u_inv.m, ctx.stream);
-    blind_final = blind_final + blind_L * u * u + blind_R * u_inv * u_inv;  // bullet.rs:111
+    blind_final = blind_final + blinds_vec[k].first * u * u + blinds_vec[k].second * u_inv * u_inv;  // bullet.rs:111
     proof.L_vec.push_back(Lc);
     proof.R_vec.push_back(Rc);
     cur = half;
     k++;
   }
+  if (k == 0) r_scale = get_r_scale();
   // g_hat = G_final[0] = <s, G>
+  FineTimer f6(ctx, "ipa final");
   dev::msm_rows(pts.p, gs.table.p, gs.wbits, svec.p, n, 1, n, nullptr, 0, ctx.scratch.p, ctx.stream);
   dev::d2h(ctx.pinned, d_a, 32, ctx.stream);
   dev::d2h(ctx.pinned + 32, d_b, 32, ctx.stream);
@@ -433,6 +469,7 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
 static void dotproduct_log_prove(Ctx& ctx, const PolyCommitmentGens& gens, Transcript& T, RandomTape& tape, u256* d_x, const Fq& blind_x,
                                  u256* d_avec, const std::vector<uint8_t>& a_canon, const Fq& y, const Fq& blind_y, DotProductProofLog& proof, Cp& Cy_out) {
   T.append_protocol_name("dot product proof (log)");
+  FineTimer f0(ctx, "dotlog pre-ipa");
   size_t n = a_canon.size() / 32;
   if (gens.n != n) throw std::runtime_error("spartan_b200: DotProductProofLog size mismatch");
   const GenSet& gs = *gens.gens_n.set;
@@ -449,16 +486,23 @@ static void dotproduct_log_prove(Ctx& ctx, const PolyCommitmentGens& gens, Trans
   T.append_point("Cx", cx[0].b);
   Cy_out = commit1(gens.gens_1, y, blind_y);
   T.append_point("Cy", Cy_out.b);
-  T.append_scalar_bytes("a", a_canon.data(), n);
-  Fq r = T.challenge_scalar("r");
-  Fq blind_Gamma = blind_x + r * blind_y;
+  Fq r = Fq::zero();
+  auto absorb_a = [&]() {   // called by bullet_prove once round 0 is in flight on the device (same transcript order as nizk/mod.rs:475-477)
+    T.append_scalar_bytes("a", a_canon.data(), n);
+    r = T.challenge_scalar("r");
+    return r;
+  };
   Fq x_hat, a_hat, rhat_Gamma;
   ge g_hat;
-  bullet_prove(ctx, T, gens, r, d_x, d_avec, n, blind_Gamma, blinds_vec, proof.bullet_reduction_proof, x_hat, a_hat, g_hat, rhat_Gamma);
+  f0.stop();
+  // blind_Gamma = blind_x + r*blind_y enters the reduction only through the final blind, which is linear in it: pass blind_x and add r*blind_y after
+  bullet_prove(ctx, T, gens, absorb_a, d_x, d_avec, n, blind_x, blinds_vec, proof.bullet_reduction_proof, x_hat, a_hat, g_hat, rhat_Gamma);
+  rhat_Gamma = rhat_Gamma + r * blind_y;
+  FineTimer f6(ctx, "dotlog post-ipa");
   Fq y_hat = x_hat * a_hat;
   // delta = d*g_hat + r_delta*h (gens_hat, nizk/mod.rs:497-505)
   Term th[1] = {{gens.gens_1.h, r_delta}};
-  proof.delta = compress(ge_add(ge_scalarmul(d.canonical(), g_hat), host_commit(gs, th, 1)));
+  proof.delta = compress(hge_add(hge_scalarmul(d.canonical(), to_hge(g_hat)), host_commit(gs, th, 1)));
   T.append_point("delta", proof.delta.b);
   // beta = d*(r*G1) + r_beta*h (gens_1_scaled, nizk/mod.rs:507)
   proof.beta = commit1(gens.gens_1, d * r, r_beta);
@@ -472,6 +516,7 @@ static void dotproduct_log_prove(Ctx& ctx, const PolyCommitmentGens& gens, Trans
 void polyeval_prove(Ctx& ctx, const u256* d_Z, const std::vector<Fq>* blinds_opt, const std::vector<Fq>& r, const Fq& Zr, const Fq* blind_Zr_opt,
                            const PolyCommitmentGens& gens, Transcript& T, RandomTape& tape, PolyEvalProof& proof, Cp& C_Zr) {
   T.append_protocol_name("polynomial evaluation proof");
+  FineTimer fp(ctx, "polyeval pre (eq, bound_rows)");
   size_t ell = r.size(), lv = ell / 2;
   size_t L_size = (size_t)1 << lv, R_size = (size_t)1 << (ell - lv);
   // compute_factored_evals (dense_mlpoly.rs:90-98) on the device; the R half is also needed as canonical bytes (the transcript absorbs a_vec)
@@ -490,6 +535,7 @@ void polyeval_prove(Ctx& ctx, const u256* d_Z, const std::vector<Fq>* blinds_opt
   }
   ctx.sync();
   Fq blind_Zr = blind_Zr_opt ? *blind_Zr_opt : Fq::zero();
+  fp.stop();
   dotproduct_log_prove(ctx, gens, T, tape, d_LZ.p, LZ_blind, d_R.p, a_canon, Zr, blind_Zr, proof.proof, C_Zr);
 }
 

@@ -148,6 +148,7 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
   DevBuf<u256> cpar0(std::max<size_t>(max_half, 1));
   std::vector<Fq> rand;
   u256* d_out = ctx.small.p + 64;   // ninst * 3 scalars
+  DevBuf<u256> d_heads(64);
   for (size_t layer_id = num_layers; layer_id-- > 0;) {
     const size_t len = prods[0]->layer_len(layer_id);  // left + right
     const size_t half = len / 2;                       // table length of this layer's sumcheck
@@ -191,7 +192,10 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     int flip = 0;
     for (size_t j = 0; j < num_rounds; j++) {
       std::vector<Fq> ev(3 * ninst);
+      FineTimer fw(ctx, "batched wait evals");
       ctx.wait_sig(sig);
+      fw.stop();
+      FineTimer fh(ctx, "batched host round");
       memcpy(ev.data(), ctx.host_res, 3 * ninst * sizeof(u256));
       Fq c0 = Fq::zero(), c2 = Fq::zero(), c3 = Fq::zero();
       for (size_t i = 0; i < ninst; i++) { c0 += ev[3 * i] * coeff_vec[i]; c2 += ev[3 * i + 1] * coeff_vec[i]; c3 += ev[3 * i + 2] * coeff_vec[i]; }  // sumcheck.rs:359-361
@@ -215,14 +219,17 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
       lp.proof.compressed_polys.push_back(poly.compress());
     }
     // final claims: first element of every A / B (and C for the dot-product circuits)
-    for (size_t i = 0; i < ninst; i++) {
-      dev::d2h(ctx.pinned + 96 * i, insts[i].t[0], 32, ctx.stream);
-      dev::d2h(ctx.pinned + 96 * i + 32, insts[i].t[1], 32, ctx.stream);
-      if (i >= np) dev::d2h(ctx.pinned + 96 * i + 64, insts[i].t[2], 32, ctx.stream);
+    FineTimer fl(ctx, "batched layer tail (claims d2h + transcript)");
+    {  // one gather kernel that also publishes the values to the host (instead of 2-3 tiny copies per instance and a stream synchronise)
+      std::vector<const u256*> hp(3 * ninst);
+      for (size_t i = 0; i < ninst; i++) { hp[3 * i] = insts[i].t[0]; hp[3 * i + 1] = insts[i].t[1]; hp[3 * i + 2] = i >= np ? insts[i].t[2] : insts[i].t[0]; }
+      dev::HostSig hs = ctx.next_sig();
+      dev::heads(d_heads.p, hp.data(), (int)hp.size(), ctx.stream, hs);
+      ctx.wait_sig(hs);
     }
-    ctx.sync();
+    const uint8_t* heads_h = reinterpret_cast<const uint8_t*>(ctx.host_res);
     lp.claims_prod_left.resize(np); lp.claims_prod_right.resize(np);
-    for (size_t i = 0; i < np; i++) { memcpy(&lp.claims_prod_left[i], ctx.pinned + 96 * i, 32); memcpy(&lp.claims_prod_right[i], ctx.pinned + 96 * i + 32, 32); }
+    for (size_t i = 0; i < np; i++) { memcpy(&lp.claims_prod_left[i], heads_h + 96 * i, 32); memcpy(&lp.claims_prod_right[i], heads_h + 96 * i + 32, 32); }
     for (size_t i = 0; i < np; i++) {
       T.append_scalar("claim_prod_left", lp.claims_prod_left[i]);
       T.append_scalar("claim_prod_right", lp.claims_prod_right[i]);
@@ -230,9 +237,9 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     if (with_dotp) {
       out.dotp_left.resize(nd); out.dotp_right.resize(nd); out.dotp_weight.resize(nd);
       for (size_t i = 0; i < nd; i++) {
-        memcpy(&out.dotp_left[i], ctx.pinned + 96 * (np + i), 32);
-        memcpy(&out.dotp_right[i], ctx.pinned + 96 * (np + i) + 32, 32);
-        memcpy(&out.dotp_weight[i], ctx.pinned + 96 * (np + i) + 64, 32);
+        memcpy(&out.dotp_left[i], heads_h + 96 * (np + i), 32);
+        memcpy(&out.dotp_right[i], heads_h + 96 * (np + i) + 32, 32);
+        memcpy(&out.dotp_weight[i], heads_h + 96 * (np + i) + 64, 32);
         T.append_scalar("claim_dotp_left", out.dotp_left[i]);
         T.append_scalar("claim_dotp_right", out.dotp_right[i]);
         T.append_scalar("claim_dotp_weight", out.dotp_weight[i]);
@@ -504,6 +511,8 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   mark("evalproof_layered_network", tn);
   mark("R1CSEvalProof::prove", t_eval);
   mark("SNARK::prove", t_start);
+  for (auto& f : ctx.fine) ctx.timings.push_back({"fine:" + f.first, f.second});
+  ctx.fine.clear();
 
   // bincode(SNARK { r1cs_sat_proof, inst_evals, r1cs_eval_proof }) (lib.rs:313-317)
   sat.ser(w);

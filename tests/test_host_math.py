@@ -98,6 +98,19 @@ def test_fp_against_python_ints(lib):
             assert int.from_bytes(call1(lib, "spt_fp_inv", b32(a)), "little") == pow(a, -1, P)
 
 
+def test_fe51_against_python_ints(lib):
+    """host_fe51.hpp: radix-2^51 arithmetic mod 2^255-19 on arbitrary 256-bit inputs (incl. non-canonical ones), results frozen to [0, p)"""
+    rng = np.random.default_rng(51)
+    out = C.create_string_buffer(160)
+    edge = [0, 1, 2, 19, P - 1, P, P + 1, 2**255 - 1, 2**255, 2**256 - 1, 2**256 - 38, 2**51 - 1, 2**51, 2**102 - 1]
+    vals = edge + [int.from_bytes(rng.bytes(32), "little") for _ in range(200)]
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        lib.spt_fe51_ops(C.c_char_p(b32(a)), C.c_char_p(b32(b)), out)
+        got = [int.from_bytes(out.raw[32 * k:32 * k + 32], "little") for k in range(5)]
+        assert got == [a * b % P, a * a % P, (a + b) % P, (a - b) % P, (2 * a + b) * (2 * a + 2 * b) % P], (a, b)
+
+
 def test_group_against_oracle(lib):
     out = C.create_string_buffer(32)
     pts = []
@@ -116,7 +129,18 @@ def test_group_against_oracle(lib):
         assert out.raw == (a + b).compress()
         assert lib.spt_dbl(C.c_char_p(a.compress()), out) == 1 and out.raw == (a + a).compress()
         assert lib.spt_add(C.c_char_p(a.compress()), C.c_char_p(ident), out) == 1 and out.raw == a.compress()
+    o64 = C.create_string_buffer(64)
+    for i in range(0, 24, 2):     # the two-at-a-time encoder used on the prover's host side gives the same bytes
+        a, b = pts[i], pts[i + 1]
+        assert lib.spt_compress2(C.c_char_p(a.compress()), C.c_char_p(b.compress()), o64) == 1
+        assert o64.raw == (a + b).compress() + (a + a).compress()
+    assert lib.spt_compress2(C.c_char_p(ident), C.c_char_p(ident), o64) == 1 and o64.raw == ident + ident
     rng = np.random.default_rng(9)
+    o96 = C.create_string_buffer(96)
+    for i, k in enumerate([0, 1, 8, 9, 15, 16, 2**252 + 9, Q - 1, 2**255 - 1] + [int.from_bytes(rng.bytes(32), "little") % Q for _ in range(6)]):
+        a, b = pts[i % 24], pts[(i + 5) % 24]      # host radix-2^51 point arithmetic: windowed scalar mult, add, double
+        assert lib.spt_hge_ops(C.c_char_p(b32(k)), C.c_char_p(a.compress()), C.c_char_p(b.compress()), o96) == 1
+        assert o96.raw == (a * (k % Q)).compress() + (a + b).compress() + (a + a).compress(), k
     for i in range(6):
         k = int.from_bytes(rng.bytes(32), "little") % Q
         assert lib.spt_scalarmul(C.c_char_p(b32(k)), C.c_char_p(pts[i].compress()), out) == 1
