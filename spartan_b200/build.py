@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         o = os.path.join(HERE, "build" + TAG, f + ".o")
         objs.append(o)
         if force or _stale(o, [os.path.join(CSRC, f)] + hdrs):
-            cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-c", os.path.join(CSRC, f), "-o", o]
+            cmd = [CXX, "-O3", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-c", os.path.join(CSRC, f), "-o", o]
             procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:

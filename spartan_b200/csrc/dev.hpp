@@ -114,6 +114,11 @@ size_t msm_scratch_bytes(size_t L, size_t R);
 void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
               void* scratch, cudaStream_t s);
 
+// both MSMs of an inner-product round (L, R -> out[0], out[1]) over unfolded generators: scalar of generator j is a[.]*svec[j].
+// scratch >= 2 * ceil(n_full/32) points; ticket: one zero-initialised word (self-resetting)
+void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
+             cudaStream_t s, HostSig sig = HostSig());
+
 // ---- variable-base MSM on arbitrary points (bucket method; kernels_pip.cu).  pts: affine-niels form of the caller's points.
 struct PipPlan { size_t n = 0; int c = 0, nwin = 0, G = 32; uint32_t nb = 0; size_t tile = 0, ntiles = 0, S = 0, max_items = 0; };
 PipPlan pip_plan(size_t n, int c_override);   // c_override = 0: pick the window width from n

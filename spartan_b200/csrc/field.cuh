@@ -14,6 +14,7 @@
 // formulation of a 256-bit modular product.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define SP_HD __host__ __device__ __forceinline__
@@ -548,27 +549,39 @@ SP_HD bool fp_sqrt_ratio_i(u256& out, const u256& u, const u256& v) {
 }
 
 #if SP_HOST_FAST
-inline u256 host_fq_mul(const u256& a, const u256& b) {
+inline u256 host_fq_mul(const u256& a, const u256& b) {   // CIOS Montgomery multiplication on 4x64-bit limbs (q has a zero limb: one product fewer per row)
   typedef unsigned __int128 u128;
-  const uint64_t q[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL};
+  const uint64_t q0 = 0x5812631a5cf5d3edULL, q1 = 0x14def9dea2f79cd6ULL, q3 = 0x1000000000000000ULL;
   const uint64_t inv = 0xd2b51da312547e1bULL;
-  uint64_t x[4], y[4], t[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < 4; i++) { x[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32); y[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32); }
+  uint64_t x[4], y[4];
+  memcpy(x, a.v, 32); memcpy(y, b.v, 32);   // little-endian host: the 8x32-bit limbs are the 4x64-bit limbs
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+#pragma GCC unroll 4
   for (int i = 0; i < 4; i++) {
-    u128 c = 0;
-    for (int j = 0; j < 4; j++) { c += (u128)x[j] * y[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
-    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
-    uint64_t m = t[0] * inv;
-    c = ((u128)m * q[0] + t[0]) >> 64;
-    c += (u128)m * q[1] + t[1]; t[0] = (uint64_t)c; c >>= 64;
-    c += t[2]; t[1] = (uint64_t)c; c >>= 64;
-    c += (u128)m * q[3] + t[3]; t[2] = (uint64_t)c; c >>= 64;
-    c += t[4]; t[3] = (uint64_t)c; c >>= 64;
-    t[4] = t[5] + (uint64_t)c;
+    const uint64_t yi = y[i];
+    u128 c = (u128)x[0] * yi + t0; t0 = (uint64_t)c; c >>= 64;
+    c += (u128)x[1] * yi + t1; t1 = (uint64_t)c; c >>= 64;
+    c += (u128)x[2] * yi + t2; t2 = (uint64_t)c; c >>= 64;
+    c += (u128)x[3] * yi + t3; t3 = (uint64_t)c; c >>= 64;
+    c += t4; t4 = (uint64_t)c; const uint64_t t5 = (uint64_t)(c >> 64);
+    const uint64_t m = t0 * inv;
+    c = ((u128)m * q0 + t0) >> 64;
+    c += (u128)m * q1 + t1; t0 = (uint64_t)c; c >>= 64;
+    c += t2; t1 = (uint64_t)c; c >>= 64;
+    c += (u128)m * q3 + t3; t2 = (uint64_t)c; c >>= 64;
+    c += t4; t3 = (uint64_t)c; c >>= 64;
+    t4 = t5 + (uint64_t)c;
   }
-  u256 r;
-  for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)t[i]; r.v[2 * i + 1] = (uint32_t)(t[i] >> 32); }
-  return fq_cond_sub_q(r);
+  // result < 2q: subtract q once if needed
+  u128 d = (u128)t0 - q0; uint64_t r0 = (uint64_t)d; uint64_t bw = (uint64_t)(d >> 64) & 1;
+  d = (u128)t1 - q1 - bw; uint64_t r1 = (uint64_t)d; bw = (uint64_t)(d >> 64) & 1;
+  d = (u128)t2 - bw; uint64_t r2 = (uint64_t)d; bw = (uint64_t)(d >> 64) & 1;
+  d = (u128)t3 - q3 - bw; uint64_t r3 = (uint64_t)d; bw = (uint64_t)(d >> 64) & 1;
+  const bool keep = bw && !t4;   // borrow out and no carry word: t < q
+  uint64_t r[4] = {keep ? t0 : r0, keep ? t1 : r1, keep ? t2 : r2, keep ? t3 : r3};
+  u256 o;
+  memcpy(o.v, r, 32);
+  return o;
 }
 inline u256 host_fp_mul(const u256& a, const u256& b) {
   typedef unsigned __int128 u128;

@@ -627,6 +627,95 @@ __global__ void __launch_bounds__(32) k_msm_reduce_small(ge* out, const ge* __re
   for (int d = 16; d > 0; d >>= 1) if (d < 2 * chunks) acc = ge_add(acc, shfl_down_ge(acc, d));
   if (threadIdx.x == 0) st_ge(out + row, acc);
 }
+// ---- the two MSMs of one inner-product round in a single launch (bullet.rs:83-97 with unfolded generators, see k_ipa_lr):
+// every generator j carries exactly one non-zero scalar, a[.]*s[j], for L (j in the right half of its n_cur-block) or for R (left half).
+// grid = (chunks, 2 sides); the last block to finish sums the partial points of both sides and publishes L, R to the host.
+template <int WBITS, int GROUPS>
+__global__ void __launch_bounds__(128, SP_MSM_LB) k_ipa_msm(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ a, const u256* __restrict__ sv,
+                                                           size_t n_cur, size_t n_full, unsigned int* ticket, ge* out, HostSig sig) {
+  constexpr int NWIN = (253 + WBITS - 1) / WBITS;
+  constexpr int WPT = (NWIN + GROUPS - 1) / GROUPS;
+  constexpr int COLS = 128 / GROUPS;
+  constexpr uint32_t HALF = 1u << (WBITS - 1);
+  constexpr size_t DEPTH = (size_t)1 << (WBITS - 1);
+  const int side = blockIdx.y;
+  const size_t half = n_cur >> 1, total = n_full >> 1;
+  const int g = threadIdx.x % GROUPS;
+  const size_t t = (size_t)blockIdx.x * COLS + threadIdx.x / GROUPS;
+  ge acc = ge_identity();
+  if (t < total) {
+    const size_t blk = t / half, off = t - blk * half;
+    const size_t j = blk * n_cur + off + (side == 0 ? half : 0);
+    u256 k = fq_mul(ld256_ro(a + (side == 0 ? off : off + half)), ld256_ro(sv + j));
+    if (!fq_is_zero(k)) {
+      k = fq_from_mont(k);
+      uint32_t carry = 0;
+      for (int w = 0; w < g * WPT; w++) carry = (msm_window<WBITS>(k, w) + carry) > HALF ? 1u : 0u;
+      const int w_end = (g + 1) * WPT < NWIN ? (g + 1) * WPT : NWIN;
+      const ge_niels* tb = table + (j * NWIN + (size_t)g * WPT) * DEPTH;
+#pragma unroll 1
+      for (int w = g * WPT; w < w_end; w++, tb += DEPTH) {
+        uint32_t v = msm_window<WBITS>(k, w) + carry;
+        int d;
+        if (v > HALF) { d = (int)v - (int)(2 * HALF); carry = 1; } else { d = (int)v; carry = 0; }
+        if (d == 0) continue;
+        int ad = d < 0 ? -d : d;
+        const ge_niels* e = tb + (ad - 1);
+        ge_niels nl;
+        nl.ypx = ld256_ro(&e->ypx); nl.ymx = ld256_ro(&e->ymx); nl.t2d = ld256_ro(&e->t2d);
+        acc = ge_madd(acc, nl, d < 0);
+      }
+    }
+  }
+  acc = block_sum_ge_128(acc);
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    st_ge(partial + (size_t)side * gridDim.x + blockIdx.x, acc);
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == 2 * gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int s2 = threadIdx.x >> 6, tt = threadIdx.x & 63;   // threads 0..63 finish L, 64..127 finish R
+  ge r = ge_identity();
+  for (unsigned int c = tt; c < gridDim.x; c += 64) {
+    const ge* p = partial + (size_t)s2 * gridDim.x + c;
+    ge x;
+    x.X = ld256_cg(&p->X); x.Y = ld256_cg(&p->Y); x.Z = ld256_cg(&p->Z); x.T = ld256_cg(&p->T);
+    r = ge_add(r, x);
+  }
+#pragma unroll 1
+  for (int d = 16; d > 0; d >>= 1) r = ge_add(r, shfl_down_ge(r, d));
+  __shared__ ge fin[4];
+  if ((threadIdx.x & 31) == 0) fin[threadIdx.x >> 5] = r;
+  __syncthreads();
+  if (tt == 0) {
+    r = ge_add(fin[2 * s2], fin[2 * s2 + 1]);
+    st_ge(out + s2, r);
+    if (sig.host_out) {
+      st256(sig.host_out + 4 * s2, r.X); st256(sig.host_out + 4 * s2 + 1, r.Y); st256(sig.host_out + 4 * s2 + 2, r.Z); st256(sig.host_out + 4 * s2 + 3, r.T);
+      __threadfence_system();
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *ticket = 0;
+    if (sig.flag) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
+  }
+}
+void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
+             cudaStream_t s, HostSig sig) {
+  ProfScope ps("msm_rows", 64.0 * (double)n_full, s);
+  constexpr int GROUPS = 8;
+  const size_t cols = 128 / GROUPS, total = n_full / 2;
+  dim3 grid((unsigned)((total + cols - 1) / cols), 2);
+  if (wbits == 8) k_ipa_msm<8, GROUPS><<<grid, 128, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+  else if (wbits == 13) k_ipa_msm<13, GROUPS><<<grid, 128, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+  else throw std::runtime_error("spartan_b200: unsupported MSM window width");
+  SP_LAUNCHED(); check("ipa_msm");
+}
+
 static int msm_pick_groups(size_t L, size_t R) {
   // enough threads to fill the chip: one thread per scalar once L*R is large (least reduction work), else split the windows
   size_t cols = L * (R + 1);

@@ -55,10 +55,10 @@ void Ctx::wait_sig(const dev::HostSig& s) {
   volatile unsigned int* f = s.flag;
   auto t0 = std::chrono::steady_clock::now();
   unsigned long spins = 0;
-  while (*f != s.seq) {
+  while ((int)(*f - s.seq) < 0) {   // sequence numbers only grow (one stream): a later signal also satisfies an earlier wait
     if ((++spins & 0xffff) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
       sync();   // throws on a CUDA error; otherwise the kernel has finished and the flag must be visible
-      if (*f != s.seq) throw std::runtime_error("spartan_b200: kernel completed without publishing its result flag");
+      if ((int)(*f - s.seq) < 0) throw std::runtime_error("spartan_b200: kernel completed without publishing its result flag");
     }
   }
   std::atomic_thread_fence(std::memory_order_acquire);
@@ -414,9 +414,10 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
     const u256* db[2] = {d_b + half, d_b};
     dev::HostSig sig = ctx.next_sig();
     dev::dot_pairs(d_c, da, db, 2, half, ctx.red.p, ctx.stream, sig);     // c_L = <a_L, b_R>, c_R = <a_R, b_L>   bullet.rs:78-79
-    dev::ipa_lr_scalars(lr.p, lr.p + n, d_a, svec.p, cur, n, ctx.stream);
-    dev::msm_rows(pts.p, gs.table.p, gs.wbits, lr.p, n, 2, n, nullptr, 0, ctx.scratch.p, ctx.stream);
-    dev::d2h(ctx.pinned + 64, pts.p, 2 * sizeof(ge), ctx.stream);
+    // L = <a_L, G_R>, R = <a_R, G_L> over the unfolded generators (scalars a[.]*s[j] formed inside the kernel), results published to the host
+    dev::HostSig sig2 = ctx.next_sig();
+    sig2.host_out = ctx.host_res + 8;
+    dev::ipa_msm(pts.p, gs.table.p, gs.wbits, d_a, svec.p, cur, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sig2);
     f1.stop();
     // the transcript work that precedes the first round (absorbing a_vec, deriving r) runs while the device computes round 0
     if (k == 0) r_scale = get_r_scale();
@@ -433,11 +434,11 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
     hge hr = hge_add(host_commit(gs, tr, 1), to_hge(bh[2 * k + 1]));
     f3.stop();
     FineTimer f4(ctx, "ipa wait MSM");
-    ctx.sync();
+    ctx.wait_sig(sig2);
     f4.stop();
     FineTimer f5(ctx, "ipa host compress+transcript");
     ge Lg, Rg;
-    memcpy(&Lg, ctx.pinned + 64, sizeof(ge)); memcpy(&Rg, ctx.pinned + 64 + sizeof(ge), sizeof(ge));
+    memcpy(&Lg, ctx.host_res + 8, sizeof(ge)); memcpy(&Rg, ctx.host_res + 12, sizeof(ge));
     Cp Lc, Rc;
     compress2(hge_add(to_hge(Lg), hl), hge_add(to_hge(Rg), hr), Lc, Rc);
     T.append_point("L", Lc.b);
