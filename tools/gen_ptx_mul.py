@@ -73,6 +73,8 @@ def run(prog, regs):
             res = v[0] >> v[1]
         elif op == "mov":
             res = v[0]
+        elif op == "and":
+            res = v[0] & v[1]
         else:
             raise ValueError(op)
         regs[dst] = res
@@ -170,6 +172,12 @@ def gen_fq_mul():
         dst = p.r("c%d" % k)
         p.emit("addc", dst, C[k], 0)
         C[k] = dst
+    # Reduction rows are chained through a value that is always zero but that ptxas cannot prove zero (the word each row has just cleared,
+    # and-ed with the last word it wrote; for row 0 the top bit of T[15], clear because a, b < 2^255): m_i = T[i]*QINV + dep_i.  Without it
+    # ptxas overlaps all eight rows (and the 8x8 product), keeps ~20 carry predicates live and spills them bit by bit into a register
+    # (120 LOP3 per multiplication on sm_100a); with it at most one row's chains are in flight and no predicate is spilled.
+    dep = p.r("dep0")
+    p.emit("shr", dep, T[15], 31)
     for i in range(8):
         if i > 0 and C[i] != 0:
             d = p.r("u%d" % i)
@@ -177,13 +185,16 @@ def gen_fq_mul():
             T[i] = d
             bump(i + 1)
         m = p.r("m%d" % i)
-        p.emit("mul.lo", m, T[i], QINV32)
+        p.emit("mad.lo", m, T[i], QINV32, dep)
+        zeroed = None
         # chain A: q0 at (i, i+1), q2 at (i+2, i+3)
         for k, (ql, part) in enumerate([(0, "lo"), (0, "hi"), (2, "lo"), (2, "hi")]):
             d = p.r("x%d_%d" % (i, k))
             op = "mad.lo.cc" if k == 0 else ("madc.%s.cc" % part)
             p.emit(op, d, m, QL[ql], T[i + k])
             T[i + k] = d
+            if k == 0:
+                zeroed = d      # T[i] + lo(m*q0) == 0 mod 2^32 by construction
         bump(i + 4)
         # chain B: q1 at (i+1, i+2), q3 at (i+3, i+4)
         for k, (ql, part) in enumerate([(1, "lo"), (1, "hi"), (3, "lo"), (3, "hi")]):
@@ -199,6 +210,9 @@ def gen_fq_mul():
         d = p.r("z%d_0" % i); p.emit("add.cc", d, T[i + 7], lo); T[i + 7] = d
         d = p.r("z%d_1" % i); p.emit("addc.cc", d, T[i + 8], hi); T[i + 8] = d
         bump(i + 9)
+        if i < 7:
+            dep = p.r("dep%d" % (i + 1))
+            p.emit("and", dep, d, zeroed)
     r = [p.r("r%d" % i) for i in range(8)]
     for k in range(8):
         p.emit("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), r[k], T[8 + k], C[8 + k])
@@ -241,7 +255,7 @@ def emit_c(name, prog, a, b, r, comment):
         if x in b:
             return "%%%d" % (16 + b.index(x))
         return x
-    ptxop = {"mul.lo": "mul.lo.u32", "mul.hi": "mul.hi.u32", "shl": "shl.b32", "shr": "shr.u32", "mov": "mov.u32"}
+    ptxop = {"mul.lo": "mul.lo.u32", "mul.hi": "mul.hi.u32", "shl": "shl.b32", "shr": "shr.u32", "mov": "mov.u32", "and": "and.b32"}
     for ins in prog.ins:
         op, dst, src = ins[0], ins[1], ins[2:]
         o = ptxop.get(op, op + ".u32")
