@@ -1,4 +1,5 @@
 // spartan_b200 — sumcheck-round kernels (K1/K2 of SURVEY.md §2b), their own translation unit so the two .cu files build in parallel.
+#include <cstdlib>
 #include "kcommon.cuh"
 
 #ifndef SP_SC_LB
@@ -88,6 +89,85 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, s
   block_reduce_finish<3>(acc, partials, counters, out, 3, sig);
 }
 
+// Small tables (len/4 <= SC_SMALL_MAX): the round's latency, not its throughput, is what the prover waits for, so the work of one index is
+// spread over 2*NT threads for the bind step (one multiplication deep) and 3 threads for the evaluations (two deep), exchanging the bound
+// values through shared memory, instead of one thread running all 14 multiplications back to back.  Same arithmetic, same results.
+#define SC_SMALL_Q 64
+#define SC_SMALL_MAX 1024
+template <int KIND>
+__global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch batch, size_t len, const u256 r, u256* partials, unsigned int* counters,
+                                                                     u256* out, HostSig sig) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  constexpr int NP = KIND == SC_QUAD ? 2 : 3;   // evaluation points 0, 2 (, 3)
+  __shared__ u256 sh[NT][2][SC_SMALL_Q];
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1, quarter = len >> 2;
+  const int e = threadIdx.x % SC_SMALL_Q, th = threadIdx.x / SC_SMALL_Q;
+  const size_t i = (size_t)blockIdx.x * SC_SMALL_Q + e;
+  const bool valid = i < quarter;
+  if (valid && th < 2 * NT) {
+    const int t = th >> 1, h = th & 1;
+    const size_t idx = i + (h ? quarter : 0);
+    u256 x0 = ld256(in.t[t] + idx), x1 = ld256(in.t[t] + idx + half);
+    u256 v = fq_add(x0, fq_mul(r, fq_sub(x1, x0)));   // dense_mlpoly.rs:218
+    if (t == 2) { if (in.write_c) st256(in.c_out + idx, v); }
+    else st256(in.t[t] + idx, v);
+    sh[t][h][e] = v;
+  }
+  __syncthreads();
+  u256 val = fq_zero();
+  if (valid && th < NP) {
+    u256 x[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) x[t] = fq_zero();
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      u256 lo = sh[t][0][e], hi = sh[t][1][e];
+      if (th == 0) x[t] = lo;                                            // t = 0
+      else {
+        u256 dl = fq_sub(hi, lo);
+        x[t] = fq_add(hi, dl);                                           // t = 2: 2*hi - lo
+        if (th == 2) x[t] = fq_add(x[t], dl);                            // t = 3
+      }
+    }
+    val = sc_comb<KIND>(x[0], x[1], x[2], x[3]);
+  }
+  // Reduction: point p lives in warps 2p, 2p+1 (SC_SMALL_Q = 64), so one value per thread; blocks of one instance meet through the
+  // ticket counter as in block_reduce_finish, and the last block of the last instance publishes the flag.
+  __shared__ u256 ws[8];
+  __shared__ bool is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (warp < 2 * NP) { u256 v = warp_sum_fq(val); if (lane == 0) ws[warp] = v; }
+  __syncthreads();
+  u256 res = fq_zero();
+  if (tid < NP) res = fq_add(ws[2 * tid], ws[2 * tid + 1]);
+  if (gridDim.x > 1) {
+    if (tid < 3) { st256(&partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + tid], res); __threadfence(); }
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(&counters[blockIdx.y], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid < 3) {
+      res = fq_zero();
+      for (unsigned int b = 0; b < gridDim.x; b++) res = fq_add(res, ld256_cg(&partials[((size_t)blockIdx.y * gridDim.x + b) * 3 + tid]));
+    }
+  }
+  if (tid < 3) {
+    st256(&out[(size_t)blockIdx.y * 3 + tid], res);
+    if (sig.host_out) { st256(&sig.host_out[(size_t)blockIdx.y * 3 + tid], res); __threadfence_system(); }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (gridDim.x > 1) counters[blockIdx.y] = 0;
+    if (sig.flag) {
+      __threadfence_system();
+      unsigned int done = atomicAdd(sig.done, 1u) + 1;
+      if (done == gridDim.y) { *sig.done = 0; __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
+    }
+  }
+}
+
 struct FoldBatch {
   u256* t[64];
 };
@@ -128,6 +208,17 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
+  static const bool small_ok = getenv("SP_SC_NO_SMALL") == nullptr;
+  if (small_ok && len / 4 <= SC_SMALL_MAX && len >= 4) {
+    dim3 grid((unsigned)((len / 4 + SC_SMALL_Q - 1) / SC_SMALL_Q), ninst);
+    switch (kind) {
+      case SC_QUAD: k_sc_fold_eval_small<SC_QUAD><<<grid, SC_SMALL_Q * 4, 0, s>>>(b, len, r, partials, counters, out, sig); break;
+      case SC_CUBIC3: k_sc_fold_eval_small<SC_CUBIC3><<<grid, SC_SMALL_Q * 6, 0, s>>>(b, len, r, partials, counters, out, sig); break;
+      default: k_sc_fold_eval_small<SC_CUBIC4><<<grid, SC_SMALL_Q * 8, 0, s>>>(b, len, r, partials, counters, out, sig); break;
+    }
+    SP_LAUNCHED(); check("sc_fold_eval_small");
+    return;
+  }
   dim3 grid(grid_for(len / 4, 256, 2), ninst);
   if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
   switch (kind) {
