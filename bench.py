@@ -149,6 +149,30 @@ def cpu_baseline_leg(budget_s=20.0):
             "sample": "SNARK::prove at 2^%d (oracle = CPU restatement of the reference; %d reps, %.2f s each)" % (CPU_SAMPLE_LOG, reps, dt)}
 
 
+def msm_var_leg(sb, api, ctx, logn=24):
+    """BASELINE.json configs[2]: standalone variable-base MSM, N = 2^24 ristretto255 points (MultiCommitGens::new(N, b"msm-bench").G, no
+    precomputed tables), uniformly random scalars below q; bucket method of spartan_b200/csrc/kernels_pip.cu through sp_msm_var_resident."""
+    import numpy as np
+    n = 1 << logn
+    P = api.Points.derive(n, b"msm-bench", ctx=ctx)
+    rng = np.random.default_rng(0)
+    t = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64)
+    t[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)          # < 2^252 < q: valid Montgomery residues, i.e. uniformly random field elements
+    S = sb.DensePolynomial(t, ctx=ctx)
+    del t
+    out = P.msm(S)
+    ts = []
+    for _ in range(3):
+        api.timer_start(ctx)
+        out2 = P.msm(S)
+        ts.append(api.timer_stop_ms(ctx))
+    assert out == out2
+    ms = min(ts)
+    return {"points": n, "ms": ms, "Mpoint_adds_per_s_reference_equivalent": 33.0 * n / (ms / 1e3) / 1e6, "Mpoints_per_s": n / (ms / 1e3) / 1e6,
+            "what": "sp_msm_var_resident: 2^%d caller-supplied points, 253-bit scalars, scalars and points resident in HBM; 33 adds/point = dalek Pippenger w=8 (SURVEY.md 8d)" % logn,
+            "result_prefix": out.hex()[:16]}
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -260,6 +284,12 @@ def run_b200(args):
         sd.finalize()
         return
     cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
+    msm_var = None
+    if world == 1 and not args.no_msm_var:
+        try:
+            msm_var = msm_var_leg(sb, api, ctx)
+        except Exception as ex:   # an extra, never the headline: report instead of failing the bench line
+            msm_var = {"error": str(ex)}
     out = {
         "metric": METRIC, "value": sd.aggregate_throughput(n * args.steps, world, t_res), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -272,7 +302,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": (d1 - d0) // args.steps, "api": "spartan_b200.SNARK.prove -> sp_snark_prove (C ABI), assignment in pinned host memory"},
         "gpu_launches": launches,
         "proof_bytes": len(proof.bytes),
-        "roofline": roof, "roofline_dominant_kernel": roof_msm, "msm": msm_rate, "kernels_ms_per_step": kernels,
+        "roofline": roof, "roofline_dominant_kernel": roof_msm, "msm": msm_rate, "msm_var_2p24": msm_var, "kernels_ms_per_step": kernels,
         "phases_ms": {k: round(v, 3) for k, v in ctx.timings().items()},
         "cpu_baseline": cpu,
         "reference_published": {"value": 2 ** 20 / 39.1297568, "unit": UNIT, "what": "README.md:375 SNARK::prove 2^20 on one core of an i7-1065G7 (other hardware)"},
@@ -288,6 +318,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-msm-var", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
