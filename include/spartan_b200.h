@@ -80,6 +80,12 @@ int sp_fold_top(sp_ctx* ctx, sp_poly* const* polys, int k, const uint64_t r_mont
 int sp_sumcheck_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, uint64_t out[3][4]);
 /* fused: bind the top variable of every table to r, then evaluate the next round on the folded tables */
 int sp_sumcheck_fold_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, const uint64_t r_mont[4], uint64_t out[3][4]);
+/* SumcheckInstanceProof::prove_cubic_batched evaluation loops (sumcheck.rs:290-357): ninst instances of comb = A*B*C (product_tree.rs:283-286).
+ * out = ninst x [e0, e2, e3] Montgomery limbs.  The same sp_poly may be passed as C of several instances (poly_C_par); A and B must be distinct. */
+int sp_sumcheck_batched_eval(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly* const* B, sp_poly* const* C, uint64_t* out /* ninst*3*4 */);
+/* bound_poly_var_top(r) on every table (each shared C once) fused with the next round's evaluations */
+int sp_sumcheck_batched_fold_eval(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly* const* B, sp_poly* const* C, const uint64_t r_mont[4],
+                                  uint64_t* out /* ninst*3*4 */);
 int sp_eq_evals(sp_ctx* ctx, const uint64_t* r_mont, size_t ell, sp_poly** out);           /* EqPolynomial::evals   dense_mlpoly.rs:68-84 */
 int sp_poly_evaluate(sp_ctx* ctx, const sp_poly* p, const uint64_t* r_mont, size_t ell, uint64_t out[4]); /* DensePolynomial::evaluate :236 */
 int sp_poly_bound_rows(sp_ctx* ctx, const sp_poly* p, const uint64_t* L_mont, size_t L_size, sp_poly** out); /* DensePolynomial::bound :206 */
@@ -88,6 +94,8 @@ int sp_dot(sp_ctx* ctx, const sp_poly* a, const sp_poly* b, uint64_t out[4]);   
 /* ---- Pedersen generators and commitments */
 /* MultiCommitGens::new(n, label): G[0..n), h = G[n]  (n+1 points drawn)                    commitments.rs:15-33 */
 int sp_gens_create(sp_ctx* ctx, const uint8_t* label, size_t label_len, size_t n, sp_gens** out);
+/* the caller's own MultiCommitGens (e.g. after `scale`, commitments.rs:43-49): n+1 encodings, G[0..n) then h; SP_ERR_INVALID_POINT if one fails */
+int sp_gens_upload(sp_ctx* ctx, const uint8_t* compressed32, size_t n, sp_gens** out);
 void sp_gens_free(sp_gens* g);
 int sp_gens_export(sp_ctx* ctx, const sp_gens* g, uint8_t* out32 /* (n+1)*32: G then h */);
 /* GroupElement::vartime_multiscalar_mul(scalars, G[0..n)) compressed                       group.rs:98-117 */

@@ -215,6 +215,26 @@ def sumcheck_fold_eval(kind, polys, r):
     return out
 
 
+def _handles(polys):
+    return (_vp * len(polys))(*[p.h for p in polys])
+
+
+def sumcheck_batched_eval(As, Bs, Cs):
+    """prove_cubic_batched evaluation loops (sumcheck.rs:290-357) for len(As) instances of A*B*C; returns (ninst, 3, 4) limbs [e0, e2, e3]"""
+    ctx = As[0].ctx
+    out = np.zeros((len(As), 3, 4), dtype=np.uint64)
+    ctx.check(lib.sp_sumcheck_batched_eval(ctx.h, C.c_int(len(As)), _handles(As), _handles(Bs), _handles(Cs), _p(out)))
+    return out
+
+
+def sumcheck_batched_fold_eval(As, Bs, Cs, r):
+    """bind the top variable of every table with r (a C shared by several instances once) and evaluate the next round"""
+    ctx = As[0].ctx
+    out = np.zeros((len(As), 3, 4), dtype=np.uint64)
+    ctx.check(lib.sp_sumcheck_batched_fold_eval(ctx.h, C.c_int(len(As)), _handles(As), _handles(Bs), _handles(Cs), _p(np.ascontiguousarray(r, dtype=np.uint64)), _p(out)))
+    return out
+
+
 def fold_top(polys, r):
     ctx = polys[0].ctx
     arr = (_vp * len(polys))(*[p.h for p in polys])
@@ -230,6 +250,17 @@ class MultiCommitGens:
         h = _vp()
         self.ctx.check(lib.sp_gens_create(self.ctx.h, C.c_char_p(label), _sz(len(label)), _sz(n), C.byref(h)))
         self.h = h
+
+    @classmethod
+    def from_points(cls, compressed, ctx=None):
+        """the caller's own generators: n+1 ristretto255 encodings, G[0..n) then h (e.g. a `scale`d MultiCommitGens, commitments.rs:43-49)"""
+        o = cls.__new__(cls)
+        o.ctx = ctx or default_context()
+        o.n = len(compressed) - 1
+        h = _vp()
+        o.ctx.check(lib.sp_gens_upload(o.ctx.h, C.c_char_p(b"".join(compressed)), _sz(o.n), C.byref(h)))
+        o.h = h
+        return o
 
     def export(self):
         out = C.create_string_buffer(32 * (self.n + 1))

@@ -165,6 +165,67 @@ int sp_sumcheck_fold_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, const ui
   for (int i = 0; i < nt; i++) polys[i]->len /= 2;
   SP_CATCH(ctx)
 }
+// prove_cubic_batched's evaluation loops (sumcheck.rs:290-357): ninst instances of A*B*C; an sp_poly may serve as C of several instances
+// (the shared eq table poly_C_par) — it is then bound once, through a temporary, and copied back
+static void batched_insts(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly* const* B, sp_poly* const* Cc, std::vector<dev::ScInst>& insts,
+                          std::vector<std::pair<sp_poly*, std::unique_ptr<DevBuf<u256>>>>& shared, bool fold) {
+  if (ninst < 1 || ninst > 24) throw SpError(SP_ERR_INVALID_ARG, "batched sumcheck: 1..24 instances");
+  const size_t len = A[0]->len;
+  if (len < 2 || (len & (len - 1))) throw SpError(SP_ERR_INVALID_ARG, "length must be a power of two >= 2");
+  for (int i = 0; i < ninst; i++) {
+    if (A[i]->len != len || B[i]->len != len || Cc[i]->len != len) throw SpError(SP_ERR_INVALID_ARG, "polynomials differ in length");
+    for (int j = 0; j < ninst; j++)
+      if (A[i] == B[j] || A[i] == Cc[j] || B[i] == Cc[j] || (i != j && (A[i] == A[j] || B[i] == B[j])))
+        throw SpError(SP_ERR_INVALID_ARG, "batched sumcheck: only the C table may be shared between instances");
+  }
+  insts.resize(ninst);
+  for (int i = 0; i < ninst; i++) {
+    dev::ScInst& in = insts[i];
+    in.t[0] = A[i]->d.p; in.t[1] = B[i]->d.p; in.t[2] = Cc[i]->d.p; in.t[3] = nullptr;
+    in.c_out = in.t[2]; in.write_c = 1;
+    if (!fold) continue;
+    int users = 0, first = -1;
+    for (int j = 0; j < ninst; j++) if (Cc[j] == Cc[i]) { users++; if (first < 0) first = j; }
+    if (users > 1) {
+      DevBuf<u256>* tmp = nullptr;
+      for (auto& sh : shared) if (sh.first == Cc[i]) tmp = sh.second.get();
+      if (!tmp) { shared.push_back({Cc[i], std::unique_ptr<DevBuf<u256>>(new DevBuf<u256>(len / 2))}); tmp = shared.back().second.get(); }
+      in.c_out = tmp->p;
+      in.write_c = first == i;
+    }
+  }
+  (void)ctx;
+}
+int sp_sumcheck_batched_eval(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly* const* B, sp_poly* const* Cc, uint64_t* out) {
+  SP_TRY(ctx)
+  std::vector<dev::ScInst> insts;
+  std::vector<std::pair<sp_poly*, std::unique_ptr<DevBuf<u256>>>> shared;
+  batched_insts(ctx, ninst, A, B, Cc, insts, shared, false);
+  DevBuf<u256> d_out(3 * ninst);
+  dev::sc_eval(dev::SC_CUBIC3, insts.data(), ninst, A[0]->len, d_out.p, ctx->c.red.p, ctx->c.stream);
+  dev::d2h(out, d_out.p, 96 * (size_t)ninst, ctx->c.stream);
+  ctx->c.sync();
+  SP_CATCH(ctx)
+}
+int sp_sumcheck_batched_fold_eval(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly* const* B, sp_poly* const* Cc, const uint64_t r[4], uint64_t* out) {
+  SP_TRY(ctx)
+  if (A[0]->len < 4) throw SpError(SP_ERR_INVALID_ARG, "fold_eval needs length >= 4");
+  std::vector<dev::ScInst> insts;
+  std::vector<std::pair<sp_poly*, std::unique_ptr<DevBuf<u256>>>> shared;
+  batched_insts(ctx, ninst, A, B, Cc, insts, shared, true);
+  Fq rr = fq_in(r);
+  DevBuf<u256> d_out(3 * ninst);
+  const size_t len = A[0]->len;
+  dev::sc_fold_eval(dev::SC_CUBIC3, insts.data(), ninst, len, rr.m, d_out.p, ctx->c.red.p, ctx->c.stream);
+  for (auto& sh : shared) dev::d2d(sh.first->d.p, sh.second->p, (len / 2) * sizeof(u256), ctx->c.stream);
+  dev::d2h(out, d_out.p, 96 * (size_t)ninst, ctx->c.stream);
+  ctx->c.sync();
+  std::vector<sp_poly*> seen;
+  for (int i = 0; i < ninst; i++)
+    for (sp_poly* p : {A[i], B[i], Cc[i]})
+      if (std::find(seen.begin(), seen.end(), p) == seen.end()) { seen.push_back(p); p->len /= 2; }
+  SP_CATCH(ctx)
+}
 int sp_eq_evals(sp_ctx* ctx, const uint64_t* r, size_t ell, sp_poly** out) {
   SP_TRY(ctx)
   size_t n = (size_t)1 << ell;
@@ -217,6 +278,24 @@ int sp_gens_create(sp_ctx* ctx, const uint8_t* label, size_t label_len, size_t n
   g->n = n;
   g->set.reset(new GenSet(&ctx->c, std::string((const char*)label, label_len), n + 1, {}));
   *out = g;
+  SP_CATCH(ctx)
+}
+int sp_gens_upload(sp_ctx* ctx, const uint8_t* compressed32, size_t n, sp_gens** out) {
+  SP_TRY(ctx)
+  DevBuf<uint8_t> d_in(32 * (n + 1));
+  DevBuf<ge> g(n + 1);
+  DevBuf<int> ok(n + 1);
+  dev::h2d(d_in.p, compressed32, 32 * (n + 1), ctx->c.stream);
+  dev::decompress_batch(g.p, ok.p, d_in.p, n + 1, ctx->c.stream);
+  std::vector<int> h_ok(n + 1);
+  dev::d2h(h_ok.data(), ok.p, sizeof(int) * (n + 1), ctx->c.stream);
+  ctx->c.sync();
+  for (size_t i = 0; i <= n; i++)
+    if (!h_ok[i]) throw SpError(SP_ERR_INVALID_POINT, "gens_upload: encoding " + std::to_string(i) + " is not a ristretto255 point");
+  sp_gens* G = new sp_gens;
+  G->n = n;
+  G->set.reset(new GenSet(&ctx->c, g.p, n + 1, {}));
+  *out = G;
   SP_CATCH(ctx)
 }
 void sp_gens_free(sp_gens* g) { delete g; }

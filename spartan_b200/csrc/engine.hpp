@@ -84,6 +84,8 @@ struct GenSet {
   std::map<size_t, HostBaseTable> host_tab;
   std::vector<Cp> compressed;  // lazily filled export
   GenSet(Ctx* c, const std::string& label, size_t nbases, const std::vector<size_t>& host_bases);
+  GenSet(Ctx* c, const ge* d_points, size_t nbases, const std::vector<size_t>& host_bases);   // caller-supplied generators (device array)
+  void finish(const std::vector<size_t>& host_bases);   // window tables + host copies, once G is filled
   const HostBaseTable& tab(size_t base) const {
     auto it = host_tab.find(base);
     if (it == host_tab.end()) throw std::runtime_error("spartan_b200: no host table for generator " + std::to_string(base));

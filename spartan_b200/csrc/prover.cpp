@@ -92,6 +92,14 @@ GenSet::GenSet(Ctx* c, const std::string& label_, size_t nbases_, const std::vec
   dev::h2d(d_uni.p, uni.data(), uni.size(), ctx->stream);
   G.alloc(nbases);
   dev::gens_from_uniform(G.p, d_uni.p, nbases, ctx->stream);
+  finish(host_bases);
+}
+GenSet::GenSet(Ctx* c, const ge* d_points, size_t nbases_, const std::vector<size_t>& host_bases) : ctx(c), label("<uploaded>"), nbases(nbases_) {
+  G.alloc(nbases);
+  dev::d2d(G.p, d_points, nbases * sizeof(ge), ctx->stream);
+  finish(host_bases);
+}
+void GenSet::finish(const std::vector<size_t>& host_bases) {
   // large generator sets get 13-bit windows (20 additions per term instead of 32; 7.9 MB of table per generator)
   const char* wenv = getenv("SP_MSM_WINDOW");
   wbits = wenv ? atoi(wenv) : (nbases >= 512 ? 13 : 8);

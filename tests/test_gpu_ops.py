@@ -148,3 +148,52 @@ def test_commit_rows(sb, L, R):
     cs = sb.DensePolynomial(Zs).commit(g, rows, R)
     for a, b, s in zip(ca, cb, cs):
         assert (oc.Point.decompress(a) + oc.Point.decompress(b)).compress() == s
+
+
+def test_gens_upload(sb):
+    """sp_gens_upload: caller-supplied generators (here: the oracle's MultiCommitGens::scale output, commitments.rs:43-49) behave like derived ones"""
+    from spartan_b200 import api
+    n = 37
+    ref = oc.MultiCommitGens.new(n, b"upload-test")
+    k = 0x1234567890abcdef
+    enc = [(ref.g(i) * k).compress() for i in range(n)] + [ref.h.compress()]
+    g = sb.MultiCommitGens.from_points(enc)
+    assert g.export() == enc
+    sc = edge_table(n, "up")
+    G = np.stack([oc.Point.decompress(e).buf for e in enc[:n]])
+    assert g.msm(sc) == oc.msm(sc, G).compress()
+    p = sb.DensePolynomial(edge_table(4 * 8, "upc"))
+    blinds = oc.prg_scalars("upb", 4, 1)
+    want = [(oc.msm(p.to_numpy()[8 * i:8 * i + 8], G) + oc.Point.decompress(enc[n]) * oc.to_ints(blinds)[i]).compress() for i in range(4)]
+    assert p.commit(g, 4, 8, blinds) == want
+    bad = list(enc)
+    bad[3] = hashlib.sha256(b"bad0").digest()
+    with pytest.raises(api.SpartanB200Error, match="error 8"):
+        sb.MultiCommitGens.from_points(bad)
+
+
+@pytest.mark.parametrize("logn", [2, 5, 11, 14])
+def test_sumcheck_batched(sb, logn):
+    """prove_cubic_batched's loops (sumcheck.rs:290-357): 5 instances, three of them sharing one C table (poly_C_par), whole chain of rounds"""
+    from spartan_b200 import api
+    n = 1 << logn
+    A = [edge_table(n, "ba%d" % i) for i in range(5)]
+    B = [edge_table(n, "bb%d" % i) for i in range(5)]
+    Cs = [edge_table(n, "bc%d" % i) for i in range(3)]
+    cmap = [0, 0, 1, 0, 2]
+    dA, dB = [sb.DensePolynomial(t) for t in A], [sb.DensePolynomial(t) for t in B]
+    dC = [sb.DensePolynomial(t) for t in Cs]
+    got = api.sumcheck_batched_eval(dA, dB, [dC[k] for k in cmap])
+    for i in range(5):
+        assert oc.to_ints(got[i]) == oc.sc_eval_cubic(A[i], B[i], Cs[cmap[i]], None)
+    for j in range(logn - 1):
+        r = oc.arr_get(oc.prg_scalars("br", 1, j), 0)
+        A = [oc.bound_top(t, r) for t in A]; B = [oc.bound_top(t, r) for t in B]; Cs = [oc.bound_top(t, r) for t in Cs]
+        got = api.sumcheck_batched_fold_eval(dA, dB, [dC[k] for k in cmap], oc.to_arr([r])[0])
+        for i in range(5):
+            assert oc.to_ints(got[i]) == oc.sc_eval_cubic(A[i], B[i], Cs[cmap[i]], None), (j, i)
+        assert all(p.len() == len(A[0]) for p in dA + dB + dC)
+    for t, p in zip(A + B + Cs, dA + dB + dC):
+        assert np.array_equal(p.to_numpy(), t)
+    with pytest.raises(api.SpartanB200Error):
+        api.sumcheck_batched_eval([dA[0], dA[0]], dB[:2], dC[:2])
