@@ -148,22 +148,31 @@ __global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch b
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (tid < 3) {
-      res = fq_zero();
-      for (unsigned int b = 0; b < gridDim.x; b++) res = fq_add(res, ld256_cg(&partials[((size_t)blockIdx.y * gridDim.x + b) * 3 + tid]));
+    if (warp < 3) {   // warp k sums value k over the blocks (gridDim.x <= 16 here: one load per lane)
+      u256 v = fq_zero();
+      for (unsigned int b = lane; b < gridDim.x; b += 32) v = fq_add(v, ld256_cg(&partials[((size_t)blockIdx.y * gridDim.x + b) * 3 + warp]));
+      v = warp_sum_fq(v);
+      if (lane == 0) ws[warp] = v;
     }
+    __syncthreads();
+    if (tid < 3) res = ws[tid];
   }
   if (tid < 3) {
     st256(&out[(size_t)blockIdx.y * 3 + tid], res);
-    if (sig.host_out) { st256(&sig.host_out[(size_t)blockIdx.y * 3 + tid], res); __threadfence_system(); }
+    if (sig.host_out) st256(&sig.host_out[(size_t)blockIdx.y * 3 + tid], res);
   }
   __syncthreads();
   if (tid == 0) {
     if (gridDim.x > 1) counters[blockIdx.y] = 0;
     if (sig.flag) {
-      __threadfence_system();
-      unsigned int done = atomicAdd(sig.done, 1u) + 1;
-      if (done == gridDim.y) { *sig.done = 0; __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
+      __threadfence_system();   // cumulative: orders the three stores above (joined through the barrier) before the flag
+      bool publish = true;
+      if (gridDim.y > 1) {
+        unsigned int done = atomicAdd(sig.done, 1u) + 1;
+        publish = done == gridDim.y;
+        if (publish) { *sig.done = 0; __threadfence_system(); }
+      }
+      if (publish) *((volatile unsigned int*)sig.flag) = sig.seq;
     }
   }
 }
