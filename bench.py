@@ -265,7 +265,7 @@ def run_b200(args):
                             "ncu --set full of the same kernel: profiles/r01_ncu_full_sc_fold_eval.txt")
         if roof:
             # ncu --set full of the first (largest single-instance) launch of this kernel in the step: profiles/r01_ncu_full_sc_fold_eval.txt
-            roof["traffic"] = 170.3e6
+            roof["traffic"] = 167.7e6
             roof["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of the captured first ZK-sumcheck launch of the step (4 tables of 2^20: algorithmic 201.3e6 B; part of the tables is still L2-resident from the SpMV that produced them)"
         roof_msm = rl(dom[0], dom[1], "hbm")
         roof_msm["note"] = ("dominant kernel by time; fixed-base ristretto255 comb, INTEGER-ALU bound (20 table lookups x 7 field multiplications per term): its "
