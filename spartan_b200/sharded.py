@@ -8,6 +8,9 @@
 * row commitments (DensePolynomial::commit_inner): rows are independent MSMs over the same generators -> rank r commits rows
   [r*L/W, (r+1)*L/W) and the 32-byte compressed commitments are all-gathered.
 
+* variable-base MSM (`sharded_msm_var`): the points (and their scalars) are partitioned by index range, every rank runs the bucket MSM on its
+  slice, and the W partial results meet in a "point-add allreduce": an all-gather of the 32-byte encodings followed by a W-term sum.
+
 The Fiat-Shamir transcript is deterministic, so every rank replays it on identical bytes and derives identical challenges: no broadcast.
 
 `backend` supplies the local device operations (the GPU API in production — `GpuBackend` below; the CPU tests inject an oracle-backed
@@ -43,6 +46,21 @@ class GpuBackend:
 
     def commit_rows(self, table, gens, L, R, blinds):
         return self.api.DensePolynomial(table, ctx=self.ctx).commit(gens, L, R, blinds)
+
+    def points_derive(self, label, lo, hi):
+        """MultiCommitGens::new(hi, label).G[lo:hi] on this rank's GPU (the SHAKE stream is sequential: the prefix is squeezed and dropped)"""
+        full = self.api.Points.derive(hi, label, ctx=self.ctx)
+        return full, lo
+
+    def msm_var(self, points, scalars):
+        pts, off = points
+        return pts.msm(scalars, offset=off)
+
+    def sum_points(self, encodings):
+        """sum of a few points given by their encodings: an MSM with all scalars one"""
+        P = self.api.Points(list(encodings), ctx=self.ctx)
+        ones = np.tile(self.api.scalar_from_bytes(b"\x01" + bytes(31)), (len(encodings), 1))
+        return P.msm(ones)
 
     def add(self, a, b):
         import ctypes as C
@@ -154,3 +172,20 @@ def sharded_commit_rows(backend, coll, table, gens, L, R, blinds=None):
     for p in parts:
         out += [p[32 * i:32 * i + 32] for i in range(L // W)]
     return out
+
+
+def sharded_msm_var(backend, coll, points, scalars_slice):
+    """GroupElement::vartime_multiscalar_mul over a point set split by index range: `points` / `scalars_slice` are this rank's slice
+    (backend-specific handle, (m,4) Montgomery limbs).  Returns the 32-byte encoding of the full sum on every rank."""
+    mine = backend.msm_var(points, scalars_slice)
+    parts = coll.all_gather_bytes(mine)
+    if coll.world == 1:
+        return parts[0]
+    return backend.sum_points(parts)
+
+
+def index_range(n, rank, world):
+    """contiguous slice [lo, hi) of n items for `rank` (sizes differ by at most one)"""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)

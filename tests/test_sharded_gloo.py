@@ -35,6 +35,12 @@ WORKER = textwrap.dedent("""
         def commit_rows(self, table, gens, L, R, blinds):
             bl = [0] * L if blinds is None else oc.to_ints(blinds)
             return oc.commit_rows(np.ascontiguousarray(table), L, R, bl, gens)
+        def msm_var(self, points, scalars):
+            return oc.msm(np.ascontiguousarray(scalars), points).compress()
+        def sum_points(self, encodings):
+            acc = oc.Point.identity()
+            for e in encodings: acc = acc + oc.Point.decompress(e)
+            return acc.compress()
         def add(self, a, b):
             return oc.to_arr([(oc.from_mont_bytes(a.tobytes()) + oc.from_mont_bytes(b.tobytes())) %% oc.Q])[0]
 
@@ -60,6 +66,14 @@ WORKER = textwrap.dedent("""
     bl = oc.prg_scalars("b", L)
     got = sharded.sharded_commit_rows(be, coll, Z, gens, L, R, bl)
     assert got == oc.commit_rows(Z, L, R, oc.to_ints(bl), gens)
+    # variable-base MSM split by index range (uneven: 1001 points over 2 ranks), partial results met by a point-add allreduce
+    n = 1001
+    pts = oc.MultiCommitGens.new(n, b"shard-msm").G
+    sc = oc.prg_scalars("ms", n)
+    lo, hi = sharded.index_range(n, rank, world)
+    assert sharded.index_range(n, 0, world)[0] == 0 and sharded.index_range(n, world - 1, world)[1] == n
+    got = sharded.sharded_msm_var(be, coll, pts[lo:hi], sc[lo:hi])
+    assert got == oc.msm(sc, pts).compress()
     sd.finalize()
     print("rank", rank, "ok")
 """)
