@@ -30,6 +30,8 @@ extern "C" {
 #define SP_ERR_INVALID_SCALAR 5    /* R1CSError::InvalidScalar */
 #define SP_ERR_INVALID_INPUTS 6    /* R1CSError::InvalidNumberOfInputs */
 #define SP_ERR_INTERNAL 7
+#define SP_ERR_VERIFY 9            /* ProofVerifyError::InternalError: the proof was rejected                    src/errors.rs:5-12 */
+#define SP_ERR_DECOMPRESS 10       /* ProofVerifyError::DecompressionError: a point of the proof does not decompress */
 #define SP_ERR_INVALID_POINT 8     /* CompressedRistretto::decompress() == None (ProofVerifyError::DecompressionError, src/errors.rs:10) */
 
 typedef struct sp_ctx sp_ctx;
@@ -166,6 +168,16 @@ int sp_snark_prove(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding
 int sp_snark_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const sp_poly* vars, const uint64_t* inputs_mont,
                             size_t ninputs, const sp_snark_gens* gens, const uint8_t* transcript_label, size_t label_len,
                             const uint64_t tape_seed_mont[4], uint8_t** proof, size_t* proof_len);
+
+/* ---- verifiers: SP_OK = accepted; SP_ERR_VERIFY / SP_ERR_DECOMPRESS = rejected (sp_last_error names the failing check).  `proof` is
+ * bincode::serialize(&NIZK) / (&SNARK), as produced by sp_*_prove or by the reference. */
+/* NIZK::verify(&self, &Instance, &InputsAssignment, &mut Transcript, &NIZKGens)                         lib.rs:549-591 */
+int sp_nizk_verify(sp_ctx* ctx, const sp_instance* inst, const uint64_t* inputs_mont, size_t ninputs, const sp_nizk_gens* gens, const uint8_t* label,
+                   size_t label_len, const uint8_t* proof, size_t proof_len);
+/* SNARK::verify(&self, &ComputationCommitment, &InputsAssignment, &mut Transcript, &SNARKGens)          lib.rs:423-465
+ * (the commitment is taken from the encoding handle; the decommitment part of the handle is not used) */
+int sp_snark_verify(sp_ctx* ctx, const sp_snark_encoding* comm, const uint64_t* inputs_mont, size_t ninputs, const sp_snark_gens* gens, const uint8_t* label,
+                    size_t label_len, const uint8_t* proof, size_t proof_len);
 
 void sp_free(void* p);
 

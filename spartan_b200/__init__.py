@@ -6,6 +6,6 @@ SNARKGens, SNARK — same names, argument meaning and error behaviour.  There is
 without a GPU every entry point raises.
 """
 from .api import (  # noqa: F401
-    Assignment, Context, DensePolynomial, InputsAssignment, Instance, MultiCommitGens, NIZK, NIZKGens, R1CSError, SNARK, SNARKGens,
+    Assignment, Context, DensePolynomial, InputsAssignment, Instance, MultiCommitGens, NIZK, NIZKGens, ProofVerifyError, R1CSError, SNARK, SNARKGens,
     SpartanB200Error, VarsAssignment, default_context, kernel_launches, lib, scalar_from_bytes, scalar_to_bytes, tape_seed, prg_scalars,
 )

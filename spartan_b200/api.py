@@ -16,6 +16,10 @@ class SpartanB200Error(RuntimeError):
     pass
 
 
+class ProofVerifyError(SpartanB200Error):
+    """errors.rs:5-12: InternalError (a check failed) or DecompressionError (a point of the proof does not decompress)"""
+
+
 class R1CSError(SpartanB200Error):
     """errors.rs:28-41: InvalidIndex / InvalidScalar / InvalidNumberOfInputs"""
 
@@ -69,6 +73,10 @@ class Context:
             raise R1CSError("InvalidScalar: " + msg)
         if rc == SP_ERR_INVALID_INPUTS:
             raise R1CSError("InvalidNumberOfInputs: " + msg)
+        if rc == 9:
+            raise ProofVerifyError("InternalError: " + msg)
+        if rc == 10:
+            raise ProofVerifyError("DecompressionError: " + msg)
         raise SpartanB200Error("spartan_b200 error %d: %s" % (rc, msg))
 
     def timings(self):
@@ -490,6 +498,12 @@ class NIZK:
                                         C.c_char_p(transcript_label), _sz(len(transcript_label)), _p(seed), C.byref(out), C.byref(n)))
         return NIZK(_take_bytes(out, n))
 
+    def verify(self, inst, inputs, transcript_label, gens):
+        """NIZK::verify(&self, &inst, &inputs, &mut Transcript::new(transcript_label), &gens): returns None, raises ProofVerifyError"""
+        ctx = inst.ctx
+        ctx.check(lib.sp_nizk_verify(ctx.h, inst.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, C.c_char_p(transcript_label), _sz(len(transcript_label)),
+                                     C.c_char_p(bytes(self.bytes)), _sz(len(self.bytes))))
+
 
 class SNARKGens:
     """lib.rs:277-309"""
@@ -559,6 +573,12 @@ class SNARK:
             ctx.check(lib.sp_snark_prove(ctx.h, inst.h, comm.h, _p(vars.limbs), _sz(len(vars)), _p(inputs.limbs), _sz(len(inputs)), gens.h,
                                          C.c_char_p(transcript_label), _sz(len(transcript_label)), _p(seed), C.byref(out), C.byref(n)))
         return SNARK(_take_bytes(out, n))
+
+    def verify(self, comm, inputs, transcript_label, gens):
+        """SNARK::verify(&self, &comm, &inputs, &mut Transcript::new(transcript_label), &gens): returns None, raises ProofVerifyError"""
+        ctx = comm.ctx
+        ctx.check(lib.sp_snark_verify(ctx.h, comm.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, C.c_char_p(transcript_label), _sz(len(transcript_label)),
+                                      C.c_char_p(bytes(self.bytes)), _sz(len(self.bytes))))
 
 
 # ----------------------------------------------------------------------------- measurement helpers (bench.py)

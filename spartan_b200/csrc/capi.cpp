@@ -678,6 +678,22 @@ int sp_snark_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_snark
   return snark_prove_common(ctx, inst, enc, vars->d.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
 }
 
+// ---- verifiers
+int sp_nizk_verify(sp_ctx* ctx, const sp_instance* inst, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens, const uint8_t* label, size_t label_len,
+                   const uint8_t* proof, size_t proof_len) {
+  SP_TRY(ctx)
+  Transcript T(std::string((const char*)label, label_len));
+  nizk_verify(ctx->c, inst->inst, fq_vec(inputs, ninputs), *gens->g, T, proof, proof_len);
+  SP_CATCH(ctx)
+}
+int sp_snark_verify(sp_ctx* ctx, const sp_snark_encoding* comm, const uint64_t* inputs, size_t ninputs, const sp_snark_gens* gens, const uint8_t* label,
+                    size_t label_len, const uint8_t* proof, size_t proof_len) {
+  SP_TRY(ctx)
+  Transcript T(std::string((const char*)label, label_len));
+  snark_verify(ctx->c, *comm->e, fq_vec(inputs, ninputs), *gens->g, T, proof, proof_len);
+  SP_CATCH(ctx)
+}
+
 void sp_free(void* p) { free(p); }
 
 }  // extern "C"

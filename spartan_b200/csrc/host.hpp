@@ -32,6 +32,7 @@ struct Fq {  // Montgomery-form element, same bytes as the reference's Scalar([u
   Fq operator*(const Fq& o) const { return Fq(fq_mul(m, o.m)); }
   Fq operator-() const { return Fq(fq_neg(m)); }
   Fq& operator+=(const Fq& o) { m = fq_add(m, o.m); return *this; }
+  Fq& operator-=(const Fq& o) { m = fq_sub(m, o.m); return *this; }
   Fq& operator*=(const Fq& o) { m = fq_mul(m, o.m); return *this; }
   bool operator==(const Fq& o) const { return fq_eq(m, o.m); }
   bool is_zero() const { return fq_is_zero(m); }
