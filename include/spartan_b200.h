@@ -169,13 +169,16 @@ int sp_snark_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_snark
                             size_t ninputs, const sp_snark_gens* gens, const uint8_t* transcript_label, size_t label_len,
                             const uint64_t tape_seed_mont[4], uint8_t** proof, size_t* proof_len);
 
+/* bincode(ComputationCommitment) (as written by sp_snark_commitment_bytes or by the reference) -> a commitment-only handle for sp_snark_verify */
+int sp_snark_commitment_load(sp_ctx* ctx, const uint8_t* bytes, size_t len, sp_snark_encoding** out);
+
 /* ---- verifiers: SP_OK = accepted; SP_ERR_VERIFY / SP_ERR_DECOMPRESS = rejected (sp_last_error names the failing check).  `proof` is
  * bincode::serialize(&NIZK) / (&SNARK), as produced by sp_*_prove or by the reference. */
 /* NIZK::verify(&self, &Instance, &InputsAssignment, &mut Transcript, &NIZKGens)                         lib.rs:549-591 */
 int sp_nizk_verify(sp_ctx* ctx, const sp_instance* inst, const uint64_t* inputs_mont, size_t ninputs, const sp_nizk_gens* gens, const uint8_t* label,
                    size_t label_len, const uint8_t* proof, size_t proof_len);
 /* SNARK::verify(&self, &ComputationCommitment, &InputsAssignment, &mut Transcript, &SNARKGens)          lib.rs:423-465
- * (the commitment is taken from the encoding handle; the decommitment part of the handle is not used) */
+ * (`comm`: a handle from sp_snark_encode or from sp_snark_commitment_load; only its commitment part is read) */
 int sp_snark_verify(sp_ctx* ctx, const sp_snark_encoding* comm, const uint64_t* inputs_mont, size_t ninputs, const sp_snark_gens* gens, const uint8_t* label,
                     size_t label_len, const uint8_t* proof, size_t proof_len);
 

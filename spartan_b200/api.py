@@ -533,6 +533,14 @@ class ComputationCommitment:
     def __init__(self, ctx, h):
         self.ctx, self.h = ctx, h
 
+    @classmethod
+    def from_bytes(cls, data, ctx=None):
+        """a verifier's view: bincode(ComputationCommitment) only (cannot be used to prove)"""
+        ctx = ctx or default_context()
+        h = _vp()
+        ctx.check(lib.sp_snark_commitment_load(ctx.h, C.c_char_p(bytes(data)), _sz(len(data)), C.byref(h)))
+        return cls(ctx, h)
+
     def commitment_bytes(self):
         out, n = C.POINTER(C.c_ubyte)(), _sz()
         lib.sp_snark_commitment_bytes(self.h, C.byref(out), C.byref(n))

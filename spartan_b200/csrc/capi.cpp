@@ -654,10 +654,31 @@ int sp_snark_commitment_bytes(const sp_snark_encoding* e, uint8_t** out, size_t*
   *out = dup_bytes(w.out); *len = w.out.size();
   return SP_OK;
 }
+// a verifier holds only the ComputationCommitment: bincode(ComputationCommitment) -> a handle usable with sp_snark_verify (not with sp_snark_prove)
+int sp_snark_commitment_load(sp_ctx* ctx, const uint8_t* bytes, size_t len, sp_snark_encoding** out) {
+  SP_TRY(ctx)
+  size_t pos = 0;
+  auto u64 = [&]() { if (len - pos < 8) throw SpError(SP_ERR_INVALID_ARG, "commitment truncated"); uint64_t x = 0; for (int i = 0; i < 8; i++) x |= (uint64_t)bytes[pos + i] << (8 * i); pos += 8; return x; };
+  auto pts = [&](PolyCommitment& c) {
+    uint64_t k = u64();
+    if (k > (len - pos) / 32) throw SpError(SP_ERR_INVALID_ARG, "commitment truncated");
+    c.C.resize(k);
+    for (auto& p : c.C) { memcpy(p.b, bytes + pos, 32); pos += 32; }
+  };
+  std::unique_ptr<sp_snark_encoding> E(new sp_snark_encoding);
+  E->e.reset(new SnarkEncoding);
+  SnarkEncoding& e = *E->e;
+  e.num_cons = u64(); e.num_vars = u64(); e.num_inputs = u64(); e.batch_size = u64(); e.num_ops = u64(); e.num_mem_cells = u64();
+  pts(e.comm_comb_ops); pts(e.comm_comb_mem);
+  if (pos != len) throw SpError(SP_ERR_INVALID_ARG, "trailing bytes after the commitment");
+  *out = E.release();
+  SP_CATCH(ctx)
+}
 static int snark_prove_common(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const u256* d_vars, const uint64_t* inputs, size_t ninputs,
                               const sp_snark_gens* gens, const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   SP_TRY(ctx)
   if (ninputs != inst->inst.num_inputs) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs");
+  if (!enc->e->comb_ops.p) throw SpError(SP_ERR_INVALID_ARG, "this handle holds a commitment only (sp_snark_commitment_load): proving needs sp_snark_encode");
   Transcript T(std::string((const char*)label, label_len));
   Writer w;
   snark_prove(ctx->c, inst->inst, *enc->e, d_vars, fq_vec(inputs, ninputs), *gens->g, T, fq_in(seed), w);

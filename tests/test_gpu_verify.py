@@ -62,6 +62,13 @@ def test_snark_verify(sb, num_cons, num_vars, num_inputs, seed):
     comm = sb.SNARK.encode(inst, gens)
     proof = sb.SNARK.prove(inst, comm, vars_, inputs, gens, b"snark_example", sb.tape_seed(seed))
     proof.verify(comm, inputs, b"snark_example", gens)
+    # a verifier that only holds the commitment bytes
+    from spartan_b200 import api
+    comm_only = api.ComputationCommitment.from_bytes(comm.commitment_bytes())
+    assert comm_only.commitment_bytes() == comm.commitment_bytes()
+    proof.verify(comm_only, inputs, b"snark_example", gens)
+    with pytest.raises(sb.SpartanB200Error):
+        sb.SNARK.prove(inst, comm_only, vars_, inputs, gens, b"snark_example", sb.tape_seed(seed))
     oi, ovars, oinputs = r1cs.Instance.produce_synthetic_r1cs(num_cons, num_vars, num_inputs, seed)
     ogens = spark.SNARKGens(num_cons, num_vars, num_inputs, nz)
     ocomm, odecomm = spark.SNARK.encode(oi, ogens)
