@@ -556,7 +556,9 @@ inline u256 host_fq_mul(const u256& a, const u256& b) {   // CIOS Montgomery mul
   uint64_t x[4], y[4];
   memcpy(x, a.v, 32); memcpy(y, b.v, 32);   // little-endian host: the 8x32-bit limbs are the 4x64-bit limbs
   uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+#if !defined(__CUDACC__)
 #pragma GCC unroll 4
+#endif
   for (int i = 0; i < 4; i++) {
     const uint64_t yi = y[i];
     u128 c = (u128)x[0] * yi + t0; t0 = (uint64_t)c; c >>= 64;
