@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libspartan_b200%s.so" % os.environ.get("SP_LIB_TAG", ""))  # SP_LIB_TAG: tuning builds only
 
 SP_OK, SP_ERR_NO_DEVICE, SP_ERR_CUDA, SP_ERR_INVALID_ARG, SP_ERR_INVALID_INDEX, SP_ERR_INVALID_SCALAR, SP_ERR_INVALID_INPUTS, SP_ERR_INTERNAL = range(8)
+SP_ERR_INVALID_POINT, SP_ERR_VERIFY, SP_ERR_DECOMPRESS = 8, 9, 10
 
 
 class SpartanB200Error(RuntimeError):
@@ -73,9 +74,9 @@ class Context:
             raise R1CSError("InvalidScalar: " + msg)
         if rc == SP_ERR_INVALID_INPUTS:
             raise R1CSError("InvalidNumberOfInputs: " + msg)
-        if rc == 9:
+        if rc == SP_ERR_VERIFY:
             raise ProofVerifyError("InternalError: " + msg)
-        if rc == 10:
+        if rc == SP_ERR_DECOMPRESS:
             raise ProofVerifyError("DecompressionError: " + msg)
         raise SpartanB200Error("spartan_b200 error %d: %s" % (rc, msg))
 

@@ -332,7 +332,6 @@ __global__ void __launch_bounds__(32) k_pip_final(ge* out, const ge* __restrict_
   if (threadIdx.x == 0) st_ge_p(out, acc);
 }
 
-static bool g_pip_attr = false;
 void msm_var(ge* out, const ge_niels* pts, const u256* scalars, const PipPlan& p, void* scratch, cudaStream_t s) {
   ProfScope ps("msm_var", 32.0 * (double)p.n + (double)p.nwin * 100.0 * (double)p.n, s);
   if (p.n >= ((size_t)1 << 31)) throw std::runtime_error("spartan_b200: msm_var supports at most 2^31-1 points");
@@ -349,10 +348,9 @@ void msm_var(ge* out, const ge_niels* pts, const u256* scalars, const PipPlan& p
   ge* partial = (ge*)(base + L.partial);
   ge* buckets = (ge*)(base + L.buckets);
   ge* wins = (ge*)(base + L.wins);
-  if (!g_pip_attr) {
+  if (p.nb * 4 > 48 * 1024) {   // per device and cheap: set whenever the histogram needs the opt-in shared-memory size
     cudaFuncSetAttribute(k_pip_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     cudaFuncSetAttribute(k_pip_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    g_pip_attr = true;
   }
   // C = sum_{w < nwin-1} 2^(c-1 + c*w)
   u256 C;

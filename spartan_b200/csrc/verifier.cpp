@@ -7,14 +7,15 @@
 // The multiexponentiations over generator vectors and over commitment vectors run on the device (fixed-base tables / bucket MSM); the
 // constant-size group checks run on the host in radix 2^51.  Failures map to ProofVerifyError::{InternalError, DecompressionError}.
 #include <algorithm>
+#include "../../include/spartan_b200.h"
 #include "snark.hpp"
 
 namespace sp {
 
 namespace {
 
-struct Reject : SpError { explicit Reject(const std::string& what) : SpError(9 /* SP_ERR_VERIFY */, "proof rejected: " + what) {} };
-struct BadPoint : SpError { explicit BadPoint(const std::string& what) : SpError(10 /* SP_ERR_DECOMPRESS */, "proof rejected: " + what + " does not decompress") {} };
+struct Reject : SpError { explicit Reject(const std::string& what) : SpError(SP_ERR_VERIFY, "proof rejected: " + what) {} };
+struct BadPoint : SpError { explicit BadPoint(const std::string& what) : SpError(SP_ERR_DECOMPRESS, "proof rejected: " + what + " does not decompress") {} };
 
 // ---- bincode reader (inverse of Writer in prover.hpp)
 struct Reader {
