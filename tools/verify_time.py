@@ -1,4 +1,4 @@
-"""wall time of the library's verifiers on one B200: NIZK::verify / SNARK::verify at 2^LOGN (the reference: 103.9 ms / 3.9 s? see README.md:380-420)"""
+"""wall time of the library's verifiers on one B200: NIZK::verify / SNARK::verify at 2^LOGN (reference README.md at 2^20: 414.5 ms / 103.05 ms on its CPU)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import spartan_b200 as sb
