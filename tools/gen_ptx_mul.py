@@ -278,6 +278,10 @@ def main():
         want = x * y * Rinv % Q
         assert got < 2 * Q and got % Q == want, (hex(x), hex(y), hex(got), hex(want))
     check(pfq, a, b, r, {"dom": lambda v: v % Q, "check": chk_fq})
+    # the same routine also accepts lazily reduced operands (sums / differences of two residues): a, b < 4q still give a result < 2q, because
+    # a*b/2^256 < 16 q^2 / 2^256 < q.  Not relied upon yet (every caller passes canonical residues); checked here so a lazy-reduction variant of
+    # the sumcheck kernels can build on it.
+    check(pfq, a, b, r, {"dom": lambda v: v % (4 * Q), "check": chk_fq}, nrand=5000)
     pfp, a2, b2, r2 = gen_fp_mul()
 
     def chk_fp(x, y, got):
