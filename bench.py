@@ -35,7 +35,8 @@ METRIC = "R1CS constraints/sec (SNARK::prove, synthetic R1CS)"
 UNIT = "constraints/s"
 LOG_N = int(os.environ.get("SP_BENCH_LOGN", "20"))
 NUM_INPUTS = 10
-CPU_SAMPLE_LOG = int(os.environ.get("SP_BENCH_CPU_LOGN", "16"))
+CPU_SAMPLE_LOG = int(os.environ.get("SP_BENCH_CPU_LOGN", str(LOG_N)))   # the CPU arm proves the SAME configuration as the GPU arm
+CPU_ARM_BUDGET_S = float(os.environ.get("SP_BENCH_CPU_BUDGET_S", "1200"))
 
 
 def peaks():
@@ -97,33 +98,49 @@ def dist_env():
     return rank, world, local
 
 
-def run_reference(args):
-    """CPU arm: the oracle's SNARK::prove (restatement of the reference; the Rust crate cannot be built here) on all host cores."""
-    rank, world, _ = dist_env()
-    if rank != 0:
-        return
+def _oracle_setup(n):
     from oracle.spartan_ref import core as oc, r1cs, spark
     cores = host_threads()
     oc.lib.oracle_set_threads(cores)
-    n = 1 << CPU_SAMPLE_LOG
     inst, vars_arr, inputs = r1cs.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, 0)
     gens = spark.SNARKGens(n, n, NUM_INPUTS, n)
     comm, decomm = spark.SNARK.encode(inst, gens)
 
     def step():
-        spark.SNARK.prove(inst, comm, decomm, vars_arr.copy(), inputs, gens, oc.Transcript(b"example"), r1cs.tape_seed(0))
-    for _ in range(args.warmup):
+        return spark.SNARK.prove(inst, comm, decomm, vars_arr.copy(), inputs, gens, oc.Transcript(b"example"), r1cs.tape_seed(0))
+    return step, cores
+
+
+def run_reference(args):
+    """CPU arm: the oracle's SNARK::prove (restatement of the reference; the Rust crate cannot be built here) on all host cores, on the SAME
+    configuration as the GPU arm (2^LOG_N constraints / variables / non-zeros, same instance seed, tape seed and transcript label): one step =
+    one whole proof.  A step takes tens of seconds, so at most one warm-up step is run and the timed loop stops early (reporting the steps it
+    actually timed) if it would exceed CPU_ARM_BUDGET_S."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    n = 1 << CPU_SAMPLE_LOG
+    step, cores = _oracle_setup(n)
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    done = 0
+    while done < args.steps:
         step()
-    dt = (time.perf_counter() - t0) / args.steps
+        done += 1
+        el = time.perf_counter() - t0
+        if done < args.steps and el / done * (done + 1) > CPU_ARM_BUDGET_S:
+            break
+    dt = (time.perf_counter() - t0) / done
     value = n / dt
-    sample = "SNARK::prove at 2^%d constraints/variables/non-zeros (bounded sample of the 2^%d workload), oracle C loops + Python protocol layer" % (CPU_SAMPLE_LOG, LOG_N)
+    sample = ("SNARK::prove at 2^%d constraints/variables/non-zeros = the GPU arm's configuration, whole proof per step; oracle (C loops under OpenMP, Python "
+              "protocol layer < 3%% of the time at this size); %d of %d requested steps timed (%.1f s each), %d warm-up" % (CPU_SAMPLE_LOG, done, args.steps, dt, warm))
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": "SNARK::prove synthetic R1CS 2^%d cons/vars, 2^%d non-zero" % (LOG_N, LOG_N), "sample": sample},
+        "config": {"workload": "SNARK::prove synthetic R1CS 2^%d cons/vars, 2^%d non-zero, %d inputs (BASELINE.json configs[1])" % (CPU_SAMPLE_LOG, CPU_SAMPLE_LOG, NUM_INPUTS),
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -131,22 +148,15 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
-def cpu_baseline_leg(budget_s=20.0):
-    """bounded oracle run on the box's host cores, reported beside the GPU number (rank 0, N = 1 only)"""
-    from oracle.spartan_ref import core as oc, r1cs, spark
-    cores = host_threads()
-    oc.lib.oracle_set_threads(cores)
+def cpu_baseline_leg():
+    """one whole oracle proof of the same configuration on the box's host cores, reported beside the GPU number (rank 0, N = 1 only)"""
     n = 1 << CPU_SAMPLE_LOG
-    inst, vars_arr, inputs = r1cs.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, 0)
-    gens = spark.SNARKGens(n, n, NUM_INPUTS, n)
-    comm, decomm = spark.SNARK.encode(inst, gens)
-    reps, t0 = 0, time.perf_counter()
-    while reps < 2 or (time.perf_counter() - t0 < budget_s and reps < 5):
-        spark.SNARK.prove(inst, comm, decomm, vars_arr.copy(), inputs, gens, oc.Transcript(b"example"), r1cs.tape_seed(0))
-        reps += 1
-    dt = (time.perf_counter() - t0) / reps
+    step, cores = _oracle_setup(n)
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "SNARK::prove at 2^%d (oracle = CPU restatement of the reference; %d reps, %.2f s each)" % (CPU_SAMPLE_LOG, reps, dt)}
+            "sample": "one SNARK::prove at 2^%d = the GPU arm's configuration (oracle = CPU restatement of the reference, OpenMP over its C loops; %.1f s)" % (CPU_SAMPLE_LOG, dt)}
 
 
 def msm_var_leg(sb, api, ctx, logn=24):

@@ -134,8 +134,16 @@ def prg_scalars(tag, n, seed=0):
 
 
 def tape_seed(seed=0):
-    """the scalar RandomTape::new draws from OsRng (random.rs:13-15), made an explicit input"""
+    """a DETERMINISTIC RandomTape seed (tests / benchmarks / byte-parity runs only): every blind of the proof becomes a public function
+    of `seed`, so a proof made with it is not zero-knowledge.  Real proofs use random_tape_seed() (the default of NIZK.prove / SNARK.prove)."""
     return prg_scalars("tape", 1, seed)[0]
+
+
+def random_tape_seed():
+    """the scalar RandomTape::new draws from OsRng (random.rs:13-15): 64 bytes of OS randomness -> Scalar::from_bytes_wide"""
+    out = np.zeros(4, dtype=np.uint64)
+    lib.sp_scalar_from_bytes_wide(C.c_char_p(os.urandom(64)), _p(out))
+    return out
 
 
 # ----------------------------------------------------------------------------- operator level
@@ -487,9 +495,10 @@ class NIZK:
 
     @staticmethod
     def prove(inst, vars, inputs, gens, transcript_label, seed=None):
-        """NIZK::prove(&inst, vars, &inputs, &gens, &mut Transcript::new(transcript_label)).  `seed`: RandomTape seed scalar limbs."""
+        """NIZK::prove(&inst, vars, &inputs, &gens, &mut Transcript::new(transcript_label)).  `seed`: RandomTape seed scalar limbs; None (the
+        default) draws it from the OS like the reference (random.rs:13-15).  Pass tape_seed(k) only for reproducible test / bench runs."""
         ctx = inst.ctx
-        seed = tape_seed(0) if seed is None else np.ascontiguousarray(seed, dtype=np.uint64)
+        seed = random_tape_seed() if seed is None else np.ascontiguousarray(seed, dtype=np.uint64)
         out, n = C.POINTER(C.c_ubyte)(), _sz()
         if isinstance(vars, DensePolynomial):
             ctx.check(lib.sp_nizk_prove_resident(ctx.h, inst.h, vars.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, C.c_char_p(transcript_label),
@@ -571,9 +580,10 @@ class SNARK:
 
     @staticmethod
     def prove(inst, comm, vars, inputs, gens, transcript_label, seed=None):
-        """SNARK::prove(&inst, &comm, &decomm, vars, &inputs, &gens, &mut Transcript::new(transcript_label))"""
+        """SNARK::prove(&inst, &comm, &decomm, vars, &inputs, &gens, &mut Transcript::new(transcript_label)).  `seed` as in NIZK.prove:
+        None = fresh OS randomness (zero-knowledge); tape_seed(k) = deterministic, for tests and benchmarks only."""
         ctx = inst.ctx
-        seed = tape_seed(0) if seed is None else np.ascontiguousarray(seed, dtype=np.uint64)
+        seed = random_tape_seed() if seed is None else np.ascontiguousarray(seed, dtype=np.uint64)
         out, n = C.POINTER(C.c_ubyte)(), _sz()
         if isinstance(vars, DensePolynomial):
             ctx.check(lib.sp_snark_prove_resident(ctx.h, inst.h, comm.h, vars.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, C.c_char_p(transcript_label),

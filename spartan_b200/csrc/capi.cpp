@@ -33,6 +33,11 @@ static std::string g_create_error;
 static Fq fq_in(const uint64_t l[4]) { Fq f; memcpy(&f.m, l, 32); return f; }
 static void fq_out(uint64_t l[4], const Fq& f) { memcpy(l, &f.m, 32); }
 static std::vector<Fq> fq_vec(const uint64_t* l, size_t n) { std::vector<Fq> v(n); if (n) memcpy(v.data(), l, 32 * n); return v; }
+// scalars that enter host arithmetic (public inputs, tape seed) must be reduced residues: limbs >= q are rejected at the boundary
+static void require_reduced(const uint64_t* l, size_t n, const char* what) {
+  for (size_t i = 0; i < n; i++)
+    if (!fq_bytes_canonical(reinterpret_cast<const uint8_t*>(l + 4 * i))) throw SpError(SP_ERR_INVALID_SCALAR, std::string(what) + ": scalar limbs are not reduced modulo q");
+}
 static uint8_t* dup_bytes(const std::vector<uint8_t>& v) { uint8_t* p = (uint8_t*)malloc(v.size() ? v.size() : 1); memcpy(p, v.data(), v.size()); return p; }
 
 extern "C" {
@@ -65,17 +70,19 @@ int sp_prof_report(char* buf, size_t buflen) {
   memcpy(buf, s.c_str(), s.size() + 1);
   return SP_OK;
 }
-static void* g_ev_a = nullptr; static void* g_ev_b = nullptr;
 int sp_timer_start(sp_ctx* ctx) {
   SP_TRY(ctx)
-  if (!g_ev_a) { g_ev_a = dev::event_create(); g_ev_b = dev::event_create(); }
-  dev::event_record(g_ev_a, ctx->c.stream);
+  if (!ctx->c.ev_a) { ctx->c.ev_a = dev::event_create(); ctx->c.ev_b = dev::event_create(); }   // events belong to the context (device)
+  dev::event_record(ctx->c.ev_a, ctx->c.stream);
+  ctx->c.timer_running = true;
   SP_CATCH(ctx)
 }
 int sp_timer_stop_ms(sp_ctx* ctx, float* ms) {
   SP_TRY(ctx)
-  dev::event_record(g_ev_b, ctx->c.stream);
-  *ms = dev::event_elapsed_ms(g_ev_a, g_ev_b);
+  if (!ctx->c.timer_running) throw SpError(SP_ERR_INVALID_ARG, "sp_timer_stop_ms without sp_timer_start");
+  dev::event_record(ctx->c.ev_b, ctx->c.stream);
+  *ms = dev::event_elapsed_ms(ctx->c.ev_a, ctx->c.ev_b);
+  ctx->c.timer_running = false;
   SP_CATCH(ctx)
 }
 
@@ -99,10 +106,10 @@ int sp_scalar_invert(const uint64_t a[4], uint64_t out[4]) {
 // ---- polys
 int sp_poly_upload(sp_ctx* ctx, const uint64_t* limbs, size_t len, sp_poly** out) {
   SP_TRY(ctx)
-  sp_poly* p = new sp_poly{&ctx->c, DevBuf<u256>(len), len};
+  std::unique_ptr<sp_poly> p(new sp_poly{&ctx->c, DevBuf<u256>(len), len});
   dev::h2d(p->d.p, limbs, len * 32, ctx->c.stream);
   ctx->c.sync();
-  *out = p;
+  *out = p.release();
   SP_CATCH(ctx)
 }
 int sp_poly_download(sp_ctx* ctx, const sp_poly* p, uint64_t* limbs, size_t len) {
@@ -121,7 +128,9 @@ static void check_same_len(sp_poly* const* polys, int k) {
 }
 int sp_fold_top(sp_ctx* ctx, sp_poly* const* polys, int k, const uint64_t r[4]) {
   SP_TRY(ctx)
+  if (k < 1) throw SpError(SP_ERR_INVALID_ARG, "fold_top: no polynomials");
   check_same_len(polys, k);
+  for (int i = 0; i < k; i++) for (int j = 0; j < i; j++) if (polys[i] == polys[j]) throw SpError(SP_ERR_INVALID_ARG, "fold_top: the same polynomial passed twice");
   Fq rr = fq_in(r);
   std::vector<u256*> t(k);
   for (int i = 0; i < k; i++) t[i] = polys[i]->d.p;
@@ -209,6 +218,7 @@ int sp_sumcheck_batched_eval(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly*
 }
 int sp_sumcheck_batched_fold_eval(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly* const* B, sp_poly* const* Cc, const uint64_t r[4], uint64_t* out) {
   SP_TRY(ctx)
+  if (ninst < 1 || ninst > 24) throw SpError(SP_ERR_INVALID_ARG, "batched sumcheck: 1..24 instances");
   if (A[0]->len < 4) throw SpError(SP_ERR_INVALID_ARG, "fold_eval needs length >= 4");
   std::vector<dev::ScInst> insts;
   std::vector<std::pair<sp_poly*, std::unique_ptr<DevBuf<u256>>>> shared;
@@ -229,12 +239,12 @@ int sp_sumcheck_batched_fold_eval(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_
 int sp_eq_evals(sp_ctx* ctx, const uint64_t* r, size_t ell, sp_poly** out) {
   SP_TRY(ctx)
   size_t n = (size_t)1 << ell;
-  sp_poly* p = new sp_poly{&ctx->c, DevBuf<u256>(n), n};
+  std::unique_ptr<sp_poly> p(new sp_poly{&ctx->c, DevBuf<u256>(n), n});
   DevBuf<u256> d_r(ell + 1), small(2 * ((size_t)1 << ((ell + 1) / 2)) + 8);
   dev::h2d(d_r.p, r, ell * 32, ctx->c.stream);
   dev::eq_evals(p->d.p, d_r.p, (int)ell, small.p, ctx->c.stream);
   ctx->c.sync();
-  *out = p;
+  *out = p.release();
   SP_CATCH(ctx)
 }
 int sp_poly_evaluate(sp_ctx* ctx, const sp_poly* p, const uint64_t* r, size_t ell, uint64_t out[4]) {
@@ -253,12 +263,12 @@ int sp_poly_bound_rows(sp_ctx* ctx, const sp_poly* p, const uint64_t* Lm, size_t
   SP_TRY(ctx)
   if (L_size == 0 || p->len % L_size) throw SpError(SP_ERR_INVALID_ARG, "bound: L does not divide the length");
   size_t R_size = p->len / L_size;
-  sp_poly* o = new sp_poly{&ctx->c, DevBuf<u256>(R_size), R_size};
+  std::unique_ptr<sp_poly> o(new sp_poly{&ctx->c, DevBuf<u256>(R_size), R_size});
   DevBuf<u256> d_L(L_size), tmp(64 * R_size);
   dev::h2d(d_L.p, Lm, L_size * 32, ctx->c.stream);
   dev::bound_rows(o->d.p, p->d.p, d_L.p, L_size, R_size, tmp.p, ctx->c.stream);
   ctx->c.sync();
-  *out = o;
+  *out = o.release();
   SP_CATCH(ctx)
 }
 int sp_dot(sp_ctx* ctx, const sp_poly* a, const sp_poly* b, uint64_t out[4]) {
@@ -274,10 +284,10 @@ int sp_dot(sp_ctx* ctx, const sp_poly* a, const sp_poly* b, uint64_t out[4]) {
 // ---- gens / commitments
 int sp_gens_create(sp_ctx* ctx, const uint8_t* label, size_t label_len, size_t n, sp_gens** out) {
   SP_TRY(ctx)
-  sp_gens* g = new sp_gens;
+  std::unique_ptr<sp_gens> g(new sp_gens);
   g->n = n;
   g->set.reset(new GenSet(&ctx->c, std::string((const char*)label, label_len), n + 1, {}));
-  *out = g;
+  *out = g.release();
   SP_CATCH(ctx)
 }
 int sp_gens_upload(sp_ctx* ctx, const uint8_t* compressed32, size_t n, sp_gens** out) {
@@ -292,10 +302,10 @@ int sp_gens_upload(sp_ctx* ctx, const uint8_t* compressed32, size_t n, sp_gens**
   ctx->c.sync();
   for (size_t i = 0; i <= n; i++)
     if (!h_ok[i]) throw SpError(SP_ERR_INVALID_POINT, "gens_upload: encoding " + std::to_string(i) + " is not a ristretto255 point");
-  sp_gens* G = new sp_gens;
+  std::unique_ptr<sp_gens> G(new sp_gens);
   G->n = n;
   G->set.reset(new GenSet(&ctx->c, g.p, n + 1, {}));
-  *out = G;
+  *out = G.release();
   SP_CATCH(ctx)
 }
 void sp_gens_free(sp_gens* g) { delete g; }
@@ -597,9 +607,9 @@ int sp_nizk_gens_create(sp_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
   SP_TRY(ctx)
   (void)num_cons;
   size_t num_vars_padded = next_pow2(std::max(num_vars, num_inputs + 1));  // lib.rs:475-481
-  sp_nizk_gens* g = new sp_nizk_gens;
+  std::unique_ptr<sp_nizk_gens> g(new sp_nizk_gens);
   g->g.reset(new R1CSGens(&ctx->c, "gens_r1cs_sat", num_vars_padded));
-  *out = g;
+  *out = g.release();
   SP_CATCH(ctx)
 }
 void sp_nizk_gens_free(sp_nizk_gens* g) { delete g; }
@@ -608,6 +618,8 @@ static int nizk_prove_common(sp_ctx* ctx, const sp_instance* inst, const u256* d
                              const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   SP_TRY(ctx)
   if (ninputs != inst->inst.num_inputs) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs");
+  if (!seed) throw SpError(SP_ERR_INVALID_ARG, "tape seed is NULL: draw it from the OS RNG (random.rs:13-15); a fixed seed makes every blind public");
+  require_reduced(inputs, ninputs, "inputs"); require_reduced(seed, 1, "tape seed");
   Transcript T(std::string((const char*)label, label_len));
   NizkProof P;
   nizk_prove(ctx->c, inst->inst, d_vars, fq_vec(inputs, ninputs), *gens->g, T, fq_in(seed), P);
@@ -633,18 +645,18 @@ int sp_nizk_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_poly* 
 // ---- SNARK
 int sp_snark_gens_create(sp_ctx* ctx, size_t num_cons, size_t num_vars, size_t num_inputs, size_t num_nz_entries, sp_snark_gens** out) {
   SP_TRY(ctx)
-  sp_snark_gens* g = new sp_snark_gens;
+  std::unique_ptr<sp_snark_gens> g(new sp_snark_gens);
   g->g.reset(new SnarkGens(&ctx->c, num_cons, num_vars, num_inputs, num_nz_entries));
-  *out = g;
+  *out = g.release();
   SP_CATCH(ctx)
 }
 void sp_snark_gens_free(sp_snark_gens* g) { delete g; }
 int sp_snark_encode(sp_ctx* ctx, const sp_instance* inst, const sp_snark_gens* gens, sp_snark_encoding** out) {
   SP_TRY(ctx)
-  sp_snark_encoding* e = new sp_snark_encoding;
+  std::unique_ptr<sp_snark_encoding> e(new sp_snark_encoding);
   e->e.reset(new SnarkEncoding());
   snark_encode(ctx->c, inst->inst, *gens->g, *e->e);
-  *out = e;
+  *out = e.release();
   SP_CATCH(ctx)
 }
 void sp_snark_encoding_free(sp_snark_encoding* e) { delete e; }
@@ -679,6 +691,8 @@ static int snark_prove_common(sp_ctx* ctx, const sp_instance* inst, const sp_sna
   SP_TRY(ctx)
   if (ninputs != inst->inst.num_inputs) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs");
   if (!enc->e->comb_ops.p) throw SpError(SP_ERR_INVALID_ARG, "this handle holds a commitment only (sp_snark_commitment_load): proving needs sp_snark_encode");
+  if (!seed) throw SpError(SP_ERR_INVALID_ARG, "tape seed is NULL: draw it from the OS RNG (random.rs:13-15); a fixed seed makes every blind public");
+  require_reduced(inputs, ninputs, "inputs"); require_reduced(seed, 1, "tape seed");
   Transcript T(std::string((const char*)label, label_len));
   Writer w;
   snark_prove(ctx->c, inst->inst, *enc->e, d_vars, fq_vec(inputs, ninputs), *gens->g, T, fq_in(seed), w);
@@ -703,6 +717,7 @@ int sp_snark_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_snark
 int sp_nizk_verify(sp_ctx* ctx, const sp_instance* inst, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens, const uint8_t* label, size_t label_len,
                    const uint8_t* proof, size_t proof_len) {
   SP_TRY(ctx)
+  require_reduced(inputs, ninputs, "inputs");
   Transcript T(std::string((const char*)label, label_len));
   nizk_verify(ctx->c, inst->inst, fq_vec(inputs, ninputs), *gens->g, T, proof, proof_len);
   SP_CATCH(ctx)
@@ -710,6 +725,7 @@ int sp_nizk_verify(sp_ctx* ctx, const sp_instance* inst, const uint64_t* inputs,
 int sp_snark_verify(sp_ctx* ctx, const sp_snark_encoding* comm, const uint64_t* inputs, size_t ninputs, const sp_snark_gens* gens, const uint8_t* label,
                     size_t label_len, const uint8_t* proof, size_t proof_len) {
   SP_TRY(ctx)
+  require_reduced(inputs, ninputs, "inputs");
   Transcript T(std::string((const char*)label, label_len));
   snark_verify(ctx->c, *comm->e, fq_vec(inputs, ninputs), *gens->g, T, proof, proof_len);
   SP_CATCH(ctx)

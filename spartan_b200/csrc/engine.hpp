@@ -46,6 +46,7 @@ struct Ctx {
   std::vector<std::pair<std::string, double>> timings;
   std::map<std::string, double> fine;   // accumulated sub-phase timers (SP_FINE_TIMERS=1), flushed into `timings` by the prove entry points
 
+  void* ev_a = nullptr; void* ev_b = nullptr; bool timer_running = false;   // sp_timer_start / sp_timer_stop_ms
   explicit Ctx(int dev);
   ~Ctx();
   // host-polled kernel results (mapped pinned memory): see dev::HostSig

@@ -41,6 +41,13 @@ inline u256 host_fp_mul(const u256& a, const u256& b);
 #define SP_HOST_FAST 0
 #endif
 
+// Constant multiplier of a sumcheck fold: a0 + r*(a1 - a0) with r fixed for a whole launch (dense_mlpoly.rs:215-223 binds every entry of every
+// table with the same r).  k[8*j + i] = limb i of (r * 2^(32 j) mod q) with r taken OUT of Montgomery form, so that
+//   a0 + sum_j d_j * K_j  =  a0 + r*d  (mod q)   for d = a1 - a0 given as eight 32-bit limbs d_j, all values staying in the Montgomery domain:
+// the reduction of the shifted partial products is precomputed into the table (72 wide multiplications per fold instead of 112, and the
+// addition of a0 rides in the first carry chain).  Built on the host once per round (fq_const_table) and passed as a kernel argument.
+struct FqConst { uint32_t k[64]; };
+
 }  // namespace sp
 #include "mul_ptx.cuh"
 namespace sp {
@@ -267,6 +274,73 @@ SP_HD u256 fq_from_u64(uint64_t x) {                                // From<u64>
 }
 // Scalar::from_bytes_wide (ristretto255.rs:435-466): lo*R2 + hi*R3
 SP_HD u256 fq_from_wide(const u256& lo, const u256& hi) { return fq_add(fq_mul(lo, fq_R2()), fq_mul(hi, fq_R3())); }
+
+// table for fq_fold_const: K_0 = r out of Montgomery form, K_{j+1} = K_j * 2^32 mod q  (one Montgomery product by 2^32*R each)
+SP_HD FqConst fq_const_table(const u256& r_mont) {
+  FqConst c;
+  u256 kj = fq_from_mont(r_mont);
+  const u256 two32 = fq_from_u64((uint64_t)1 << 32);
+  for (int j = 0; j < 8; j++) {
+    for (int i = 0; i < 8; i++) c.k[8 * j + i] = kj.v[i];
+    kj = fq_mul(kj, two32);
+  }
+  return c;
+}
+// a0 + r*(a1 - a0), bit-identical to fq_add(a0, fq_mul(r, fq_sub(a1, a0))) (both are the canonical residue)
+SP_HD u256 fq_fold_const(const u256& a0, const u256& a1, const FqConst& rc) {
+#if defined(__CUDA_ARCH__) && !defined(SP_NO_PTX)
+  // d = a1 - a0 + q in (0, 2q): two unconditional chains, no select
+  u256 d;
+  asm("sub.cc.u32 %0, %8, %16;\n\tsubc.cc.u32 %1, %9, %17;\n\tsubc.cc.u32 %2, %10, %18;\n\tsubc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\tsubc.cc.u32 %5, %13, %21;\n\tsubc.cc.u32 %6, %14, %22;\n\tsubc.u32 %7, %15, %23;\n\t"
+      "add.cc.u32 %0, %0, %24;\n\taddc.cc.u32 %1, %1, %25;\n\taddc.cc.u32 %2, %2, %26;\n\taddc.cc.u32 %3, %3, %27;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\taddc.cc.u32 %5, %5, 0;\n\taddc.cc.u32 %6, %6, 0;\n\taddc.u32 %7, %7, %28;"
+      : "=&r"(d.v[0]), "=&r"(d.v[1]), "=&r"(d.v[2]), "=&r"(d.v[3]), "=&r"(d.v[4]), "=&r"(d.v[5]), "=&r"(d.v[6]), "=&r"(d.v[7])
+      : "r"(a1.v[0]), "r"(a1.v[1]), "r"(a1.v[2]), "r"(a1.v[3]), "r"(a1.v[4]), "r"(a1.v[5]), "r"(a1.v[6]), "r"(a1.v[7]),
+        "r"(a0.v[0]), "r"(a0.v[1]), "r"(a0.v[2]), "r"(a0.v[3]), "r"(a0.v[4]), "r"(a0.v[5]), "r"(a0.v[6]), "r"(a0.v[7]),
+        "r"(SPQ0), "r"(SPQ1), "r"(SPQ2), "r"(SPQ3), "r"(SPQ7));
+  return fq_csub_ptx(fq_fold_const_ptx(a0, d, rc));
+#else
+  // portable specification: the same sum of partial products on 64-bit accumulators, then the fold through 2^252 = -c (mod q)
+  uint32_t d[8];
+  {
+    int64_t borrow = 0;
+    uint32_t t[8];
+    for (int i = 0; i < 8; i++) { int64_t x = (int64_t)a1.v[i] - (int64_t)a0.v[i] + borrow; t[i] = (uint32_t)x; borrow = x >> 32; }
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)t[i] + fq_modulus_limb(i); d[i] = (uint32_t)c; c >>= 32; }
+  }
+  uint32_t T[10];
+  for (int i = 0; i < 8; i++) T[i] = a0.v[i];
+  T[8] = 0; T[9] = 0;
+  for (int j = 0; j < 8; j++) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)d[j] * rc.k[8 * j + i] + T[i]; T[i] = (uint32_t)c; c >>= 32; }
+    c += T[8]; T[8] = (uint32_t)c; c >>= 32;
+    T[9] += (uint32_t)c;
+  }
+  // T < 2^288: hi = T >> 252 (36 bits)
+  const uint64_t hi = ((uint64_t)T[8] << 4) | (T[7] >> 28);
+  const uint32_t hi0 = (uint32_t)hi, hi1 = (uint32_t)(hi >> 32);
+  uint32_t X[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  {
+    uint64_t c = 0;
+    for (int i = 0; i < 4; i++) { c += (uint64_t)hi0 * fq_modulus_limb(i); X[i] = (uint32_t)c; c >>= 32; }
+    X[4] = (uint32_t)c;
+    c = 0;
+    for (int i = 0; i < 4; i++) { c += (uint64_t)hi1 * fq_modulus_limb(i) + X[i + 1]; X[i + 1] = (uint32_t)c; c >>= 32; }
+    X[5] = (uint32_t)c;
+  }
+  u256 u;
+  {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)(i == 7 ? (T[7] & 0x0fffffffu) : T[i]) + fq_modulus_limb(i); u.v[i] = (uint32_t)c; c >>= 32; }
+    int64_t borrow = 0;
+    for (int i = 0; i < 8; i++) { int64_t x = (int64_t)u.v[i] - (int64_t)X[i] + borrow; u.v[i] = (uint32_t)x; borrow = x >> 32; }
+  }
+  return fq_cond_sub_q(u);
+#endif
+}
 
 // a^(q-2) by the reference's addition chain (ristretto255.rs:541-595); a == 0 -> 0
 SP_HD u256 fq_inv(const u256& a) {

@@ -19,6 +19,11 @@ int spt_portable(void) {
 #endif
 }
 void spt_fq_mul(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fq_mul(in256(a), in256(b))); }
+// the constant-multiplier fold of the sumcheck kernels (portable specification of fq_fold_const_ptx): table built from r, then a0 + r*(a1-a0)
+void spt_fq_fold_const(const uint8_t* a0, const uint8_t* a1, const uint8_t* r, uint8_t* out) {
+  FqConst rc = fq_const_table(in256(r));
+  out256(out, fq_fold_const(in256(a0), in256(a1), rc));
+}
 void spt_fq_add(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fq_add(in256(a), in256(b))); }
 void spt_fq_sub(const uint8_t* a, const uint8_t* b, uint8_t* r) { out256(r, fq_sub(in256(a), in256(b))); }
 void spt_fq_inv(const uint8_t* a, uint8_t* r) { out256(r, fq_inv(in256(a))); }

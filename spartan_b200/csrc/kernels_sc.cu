@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t
 
 // Fused: bind the top variable with r (len -> len/2) and evaluate the next round's polynomial on the folded table.
 // Thread i owns elements {i, i+len/4, i+len/2, i+3len/4} of every table: in-place update is race-free.
-template <int KIND>
-__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, size_t len, const u256 r, u256* partials,
+// CF: bind with the constant-multiplier fold (fq_fold_const: table of r*2^(32j) mod q in uniform registers, 72 wide products and no separate
+// modular addition) instead of sub + Montgomery product + add; same canonical values either way.
+template <int KIND, bool CF>
+__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, size_t len, const u256 r, const __grid_constant__ FqConst rc, u256* partials,
                                                        unsigned int* counters, u256* out, HostSig sig) {
   constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
   const ScInst& in = batch.inst[blockIdx.y];
@@ -76,8 +78,11 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, s
     for (int t = 0; t < NT; t++) {
       u256 a0 = ld256(in.t[t] + i), a1 = ld256(in.t[t] + i + half);
       u256 b0 = ld256(in.t[t] + i + quarter), b1 = ld256(in.t[t] + i + quarter + half);
-      lo[t] = fq_add(a0, fq_mul(r, fq_sub(a1, a0)));   // dense_mlpoly.rs:218
-      hi[t] = fq_add(b0, fq_mul(r, fq_sub(b1, b0)));
+      if (CF) { lo[t] = fq_fold_const(a0, a1, rc); hi[t] = fq_fold_const(b0, b1, rc); }
+      else {
+        lo[t] = fq_add(a0, fq_mul(r, fq_sub(a1, a0)));   // dense_mlpoly.rs:218
+        hi[t] = fq_add(b0, fq_mul(r, fq_sub(b1, b0)));
+      }
       if (t == 2) {
         if (in.write_c) { st256(in.c_out + i, lo[t]); st256(in.c_out + i + quarter, hi[t]); }
       } else {
@@ -89,14 +94,82 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, s
   block_reduce_finish<3>(acc, partials, counters, out, 3, sig);
 }
 
+// ---- register-lean formulation of the fused round (3 CTAs of 256 threads per SM instead of 2).
+// The tables of an index are visited one after the other: bind (lo, hi), store, form the three evaluation arguments lo, 2hi-lo, 3hi-2lo and
+// fold them straight into three running products, so that only ONE table's values are live at a time; the three per-thread sums live in
+// shared memory ([point][limb][thread]: conflict-free) because they are touched once per index.  Same values as k_sc_fold_eval, same layout.
+// Order of the factors: A*B, A*B*C as stored; A*(B*C-D) as B, C, D, A.
+#ifndef SC_V2_THREADS
+#define SC_V2_THREADS 128   // 5 CTAs x 4 warps per SM at <= 96 registers (6 CTAs: 80 registers)
+#endif
+#ifndef SC_V2_BLOCKS
+#define SC_V2_BLOCKS 5
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(SC_V2_THREADS, SC_V2_BLOCKS) k_sc_fold_eval_v2(ScBatch batch, size_t len, const __grid_constant__ FqConst rc, u256* partials,
+                                                            unsigned int* counters, u256* out, HostSig sig) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  constexpr int NP = KIND == SC_QUAD ? 2 : 3;
+  __shared__ uint32_t accs[3][8][SC_V2_THREADS];
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1, quarter = len >> 2;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int l = 0; l < 8; l++) accs[k][l][tid] = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < quarter; i += (size_t)gridDim.x * blockDim.x) {
+    u256 P0, P2, P3;
+#pragma unroll
+    for (int step = 0; step < NT; step++) {
+      const int t = KIND == SC_CUBIC4 ? (step + 1) & 3 : step;     // B, C, D, A for A*(B*C-D)
+      u256* T = in.t[t];
+      u256 lo, hi;
+      {
+        u256 a0 = ld256(T + i), a1 = ld256(T + i + half), b0 = ld256(T + i + quarter), b1 = ld256(T + i + quarter + half);
+        lo = fq_fold_const(a0, a1, rc);   // dense_mlpoly.rs:218
+        hi = fq_fold_const(b0, b1, rc);
+      }
+      if (t == 2) { if (in.write_c) { st256(in.c_out + i, lo); st256(in.c_out + i + quarter, hi); } }
+      else { st256(T + i, lo); st256(T + i + quarter, hi); }
+      const u256 dl = fq_sub(hi, lo);
+      const u256 x2 = fq_add(hi, dl);                              // 2*hi - lo      (sumcheck.rs:466-468 / :630-639)
+      if (step == 0) {
+        P0 = lo; P2 = x2;
+        if (NP == 3) P3 = fq_add(x2, dl);                          // 3*hi - 2*lo    (sumcheck.rs:642-651)
+      } else if (KIND == SC_CUBIC4 && step == 2) {                 // ... - D
+        P0 = fq_sub(P0, lo); P2 = fq_sub(P2, x2); P3 = fq_sub(P3, fq_add(x2, dl));
+      } else {
+        P0 = fq_mul(P0, lo); P2 = fq_mul(P2, x2);
+        if (NP == 3) P3 = fq_mul(P3, fq_add(x2, dl));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+      u256 a;
+#pragma unroll
+      for (int l = 0; l < 8; l++) a.v[l] = accs[k][l][tid];
+      a = fq_add(a, k == 0 ? P0 : (k == 1 ? P2 : P3));
+#pragma unroll
+      for (int l = 0; l < 8; l++) accs[k][l][tid] = a.v[l];
+    }
+  }
+  u256 acc[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int l = 0; l < 8; l++) acc[k].v[l] = accs[k][l][tid];
+  block_reduce_finish<3>(acc, partials, counters, out, 3, sig);
+}
+
 // Small tables (len/4 <= SC_SMALL_MAX): the round's latency, not its throughput, is what the prover waits for, so the work of one index is
 // spread over 2*NT threads for the bind step (one multiplication deep) and 3 threads for the evaluations (two deep), exchanging the bound
 // values through shared memory, instead of one thread running all 14 multiplications back to back.  Same arithmetic, same results.
 #define SC_SMALL_Q 64
 #define SC_SMALL_MAX 1024
-template <int KIND>
-__global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch batch, size_t len, const u256 r, u256* partials, unsigned int* counters,
-                                                                     u256* out, HostSig sig) {
+template <int KIND, bool CF>
+__global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch batch, size_t len, const u256 r, const __grid_constant__ FqConst rc, u256* partials,
+                                                                     unsigned int* counters, u256* out, HostSig sig) {
   constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
   constexpr int NP = KIND == SC_QUAD ? 2 : 3;   // evaluation points 0, 2 (, 3)
   __shared__ u256 sh[NT][2][SC_SMALL_Q];
@@ -109,7 +182,7 @@ __global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch b
     const int t = th >> 1, h = th & 1;
     const size_t idx = i + (h ? quarter : 0);
     u256 x0 = ld256(in.t[t] + idx), x1 = ld256(in.t[t] + idx + half);
-    u256 v = fq_add(x0, fq_mul(r, fq_sub(x1, x0)));   // dense_mlpoly.rs:218
+    u256 v = CF ? fq_fold_const(x0, x1, rc) : fq_add(x0, fq_mul(r, fq_sub(x1, x0)));   // dense_mlpoly.rs:218
     if (t == 2) { if (in.write_c) st256(in.c_out + idx, v); }
     else st256(in.t[t] + idx, v);
     sh[t][h][e] = v;
@@ -180,17 +253,17 @@ __global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch b
 struct FoldBatch {
   u256* t[64];
 };
-__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const u256 r) {
+__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const __grid_constant__ FqConst rc) {
   const size_t half = len >> 1;
   u256* T = tabs.t[blockIdx.y];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
     u256 a0 = ld256(T + i), a1 = ld256(T + i + half);
-    st256(T + i, fq_add(a0, fq_mul(r, fq_sub(a1, a0))));
+    st256(T + i, fq_fold_const(a0, a1, rc));   // dense_mlpoly.rs:218
   }
 }
 
 // scratch layout: [counters: 64 x u32][partials]
-static const size_t SC_MAX_BLOCKS = 148 * 4 + 64;
+static const size_t SC_MAX_BLOCKS = 148 * 6 + 64;
 size_t sc_scratch_bytes(int ninst) { return 256 + (size_t)ninst * SC_MAX_BLOCKS * 3 * sizeof(u256); }
 
 static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
@@ -218,32 +291,51 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
   static const bool small_ok = getenv("SP_SC_NO_SMALL") == nullptr;
+  static const bool cf = getenv("SP_SC_NO_CONSTFOLD") == nullptr;   // A/B switch for the constant-multiplier fold (tools/bench_kernels.py)
+  const FqConst rc = cf ? fq_const_table(r) : FqConst();
+#define SP_SC_LAUNCH(KERNEL, K, THREADS) \
+  do { if (cf) KERNEL<K, true><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig); \
+       else KERNEL<K, false><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig); } while (0)
   if (small_ok && len / 4 <= SC_SMALL_MAX && len >= 4) {
     dim3 grid((unsigned)((len / 4 + SC_SMALL_Q - 1) / SC_SMALL_Q), ninst);
     switch (kind) {
-      case SC_QUAD: k_sc_fold_eval_small<SC_QUAD><<<grid, SC_SMALL_Q * 4, 0, s>>>(b, len, r, partials, counters, out, sig); break;
-      case SC_CUBIC3: k_sc_fold_eval_small<SC_CUBIC3><<<grid, SC_SMALL_Q * 6, 0, s>>>(b, len, r, partials, counters, out, sig); break;
-      default: k_sc_fold_eval_small<SC_CUBIC4><<<grid, SC_SMALL_Q * 8, 0, s>>>(b, len, r, partials, counters, out, sig); break;
+      case SC_QUAD: SP_SC_LAUNCH(k_sc_fold_eval_small, SC_QUAD, SC_SMALL_Q * 4); break;
+      case SC_CUBIC3: SP_SC_LAUNCH(k_sc_fold_eval_small, SC_CUBIC3, SC_SMALL_Q * 6); break;
+      default: SP_SC_LAUNCH(k_sc_fold_eval_small, SC_CUBIC4, SC_SMALL_Q * 8); break;
     }
     SP_LAUNCHED(); check("sc_fold_eval_small");
     return;
   }
-  dim3 grid(grid_for(len / 4, 256, 2), ninst);
+  static const bool v2 = getenv("SP_SC_V2") != nullptr && cf;   // register-lean formulation (A/B switch)
+  if (v2) {
+    dim3 grid(grid_for(len / 4, SC_V2_THREADS, SC_V2_BLOCKS), ninst);
+    if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
+    switch (kind) {
+      case SC_QUAD: k_sc_fold_eval_v2<SC_QUAD><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig); break;
+      case SC_CUBIC3: k_sc_fold_eval_v2<SC_CUBIC3><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig); break;
+      default: k_sc_fold_eval_v2<SC_CUBIC4><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig); break;
+    }
+    SP_LAUNCHED(); check("sc_fold_eval_v2");
+    return;
+  }
+  dim3 grid(grid_for(len / 4, 256, SP_SC_LB), ninst);
   if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
   switch (kind) {
-    case SC_QUAD: k_sc_fold_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, r, partials, counters, out, sig); break;
-    case SC_CUBIC3: k_sc_fold_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, r, partials, counters, out, sig); break;
-    default: k_sc_fold_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, r, partials, counters, out, sig); break;
+    case SC_QUAD: SP_SC_LAUNCH(k_sc_fold_eval, SC_QUAD, 256); break;
+    case SC_CUBIC3: SP_SC_LAUNCH(k_sc_fold_eval, SC_CUBIC3, 256); break;
+    default: SP_SC_LAUNCH(k_sc_fold_eval, SC_CUBIC4, 256); break;
   }
+#undef SP_SC_LAUNCH
   SP_LAUNCHED(); check("sc_fold_eval");
 }
 void fold_top(u256* const* tables, int ntables, size_t len, const u256& r, cudaStream_t s) {
   ProfScope ps("fold_top", (double)ntables * len * 48.0, s);
+  const FqConst rc = fq_const_table(r);
   for (int base = 0; base < ntables; base += 64) {
     FoldBatch fb; int n = ntables - base < 64 ? ntables - base : 64;
     for (int i = 0; i < n; i++) fb.t[i] = tables[base + i];
     dim3 grid(grid_for(len / 2, 256, 4), n);
-    k_fold_top<<<grid, 256, 0, s>>>(fb, len, r);
+    k_fold_top<<<grid, 256, 0, s>>>(fb, len, rc);
     SP_LAUNCHED();
   }
   check("fold_top");

@@ -2,6 +2,7 @@
 // Follows the exact Fiat-Shamir schedule of /root/reference/src/r1csproof.rs:144-349 so that the
 // proof bytes equal the reference's for identical instance, assignment, transcript label and RandomTape seed.
 #include "prover.hpp"
+#include "../../include/spartan_b200.h"
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -48,6 +49,7 @@ Ctx::Ctx(int dev_) : device(dev_) {
 Ctx::~Ctx() {
   try { sync(); } catch (...) {}
   scratch.release(); red.release(); small.release();
+  if (ev_a) { dev::event_destroy(ev_a); dev::event_destroy(ev_b); }
   dev::hfree_pinned(pinned);
   dev::stream_destroy(stream);
 }
@@ -687,6 +689,8 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
 
 void nizk_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T, const Fq& tape_seed,
                 NizkProof& out) {
+  if (inst.digest.empty())
+    throw SpError(SP_ERR_INVALID_ARG, "NIZK::prove: the instance has no R1CSShapeDigest (sp_instance_set_digest); the transcript would not bind the R1CS shape (lib.rs:514)");
   ctx.timings.clear();
   PhaseTimer t(ctx, "NIZK::prove");
   RandomTape tape("proof", tape_seed);                                   // lib.rs:511

@@ -23,7 +23,9 @@ struct Reader {
   Reader(const uint8_t* b, size_t len) : p(b), n(len) {}
   void need(size_t k) { if (n - pos < k) throw Reject("truncated proof"); }
   uint64_t u64() { need(8); uint64_t x = 0; for (int i = 0; i < 8; i++) x |= (uint64_t)p[pos + i] << (8 * i); pos += 8; return x; }
-  Fq scalar() { need(32); Fq f; memcpy(&f.m, p + pos, 32); pos += 32; return f; }
+  // a Scalar on the wire is its four Montgomery limbs (serde derive on `Scalar([u64;4])`): the reference accepts any limbs, but every host
+  // routine here assumes a reduced residue, so limbs >= q are rejected instead of being carried into fq_mul / fq_eq (no malleability either)
+  Fq scalar() { need(32); if (!fq_bytes_canonical(p + pos)) throw Reject("scalar limbs are not reduced modulo q"); Fq f; memcpy(&f.m, p + pos, 32); pos += 32; return f; }
   Cp point() { need(32); Cp c; memcpy(c.b, p + pos, 32); pos += 32; return c; }
   size_t len(size_t item) { uint64_t k = u64(); if (k > (n - pos) / item) throw Reject("vector length exceeds the proof"); return (size_t)k; }
   std::vector<Fq> scalars() { size_t k = len(32); std::vector<Fq> v(k); for (auto& s : v) s = scalar(); return v; }
@@ -520,8 +522,18 @@ void instance_evaluate(Ctx& ctx, const Instance& inst, const std::vector<Fq>& rx
   ctx.get_small(40, out, 3);
 }
 
+static bool pow2(size_t x) { return x && !(x & (x - 1)); }
+// shape sanity shared by both verifiers: the padded dimensions the prover enforces (lib.rs:129-198, r1csproof.rs:156); without it a
+// hand-made commitment with num_vars = 0 or num_cons <= 1 would leave the round vectors empty (`.back()`, `ry[0]`)
+static void check_dims(size_t num_cons, size_t num_vars, size_t num_inputs) {
+  if (num_cons < 2 || num_vars < 1 || !pow2(num_cons) || !pow2(num_vars)) throw SpError(SP_ERR_INVALID_ARG, "verifier: num_cons >= 2 and num_vars >= 1 must be powers of two");
+  if (!(num_inputs < num_vars)) throw SpError(SP_ERR_INVALID_ARG, "verifier: |input| + 1 must be at most the number of variables");
+}
+
 // NIZK::verify (lib.rs:549-591)
 void nizk_verify(Ctx& ctx, const Instance& inst, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T, const uint8_t* proof, size_t len) {
+  check_dims(inst.num_cons, inst.num_vars, inst.num_inputs);
+  if (inst.digest.empty()) throw SpError(SP_ERR_INVALID_ARG, "NIZK::verify: the instance has no R1CSShapeDigest (sp_instance_set_digest); the transcript would not bind the R1CS shape (lib.rs:514)");
   Reader r(proof, len);
   NizkProof p;
   rd(r, p.r1cs_sat_proof);
@@ -540,6 +552,11 @@ void nizk_verify(Ctx& ctx, const Instance& inst, const std::vector<Fq>& input, c
 
 // SNARK::verify (lib.rs:423-465); `comm` supplies the ComputationCommitment
 void snark_verify(Ctx& ctx, const SnarkEncoding& comm, const std::vector<Fq>& input, const SnarkGens& gens, Transcript& T, const uint8_t* proof, size_t len) {
+  check_dims(comm.num_cons, comm.num_vars, comm.num_inputs);
+  {  // SparseMatPolyCommitment consistency (sparse_mlpoly.rs:366-420): 3 matrices, power-of-two op count, cells = max(num_cons, 2*num_vars)
+    const size_t cells = std::max(comm.num_cons, 2 * comm.num_vars);
+    if (comm.batch_size != 3 || !pow2(comm.num_ops) || comm.num_mem_cells != cells) throw SpError(SP_ERR_INVALID_ARG, "verifier: inconsistent computation commitment");
+  }
   Reader r(proof, len);
   R1CSProof sat;
   rd(r, sat);

@@ -102,6 +102,27 @@ def test_nizk_user_instance_with_padding(sb):
 
 
 @pytest.mark.parametrize("logn", [16, 20])
+def test_nizk_large_bytes_match_oracle(sb, logn):
+    """NIZK::prove at 2^16 and at the size of the reference's published profile (2^20, README.md:394-413): bincode(NIZK) identical to the
+    oracle's (all host cores); 47,024-byte sat proof at 2^20 (README.md:411)"""
+    import os
+    n = 1 << logn
+    oc.lib.oracle_set_threads(max(1, (os.cpu_count() or 2) // 2))
+    oi, ovars, oinputs, ogens, oproof = oracle_nizk(n, n, 10, 0)
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(n, n, 10, seed=0)
+    inst.set_digest(oi.digest)
+    gens = sb.NIZKGens(n, n, 10)
+    proof = sb.NIZK.prove(inst, vars_, inputs, gens, b"example", sb.tape_seed(0))
+    want = oproof.ser()
+    assert len(proof.bytes) == len(want)
+    first = next((i for i in range(len(want)) if want[i] != proof.bytes[i]), None)
+    assert first is None, "first differing byte at %d of %d" % (first, len(want))
+    if logn == 20:
+        assert len(pr.ser(oproof.r1cs_sat_proof)) == 47024
+    proof.verify(inst, inputs, b"example", gens)
+
+
+@pytest.mark.parametrize("logn", [14])
 def test_nizk_large_accepted_by_oracle_verifier(sb, logn):
     """full-size run (2^20 = the size of the reference's published profile, README.md:394-413): the oracle's NIZK::verify accepts the
     GPU proof; the sat-proof length is the reference's published 47,024 bytes at 2^20 (README.md:411)"""

@@ -70,6 +70,18 @@ def test_fq_against_oracle(lib):
     assert oc.from_mont_bytes(out.raw) == 2**64 - 1
 
 
+def test_fq_fold_const_equals_bound_poly_var_top(lib):
+    """the constant-multiplier fold a0 + r*(a1 - a0) (table of r*2^(32j) mod q, one fold through 2^252 = -c) returns the very limbs of
+    dense_mlpoly.rs:218 computed the long way, including at the edges of the field"""
+    rng = np.random.default_rng(17)
+    vals = EDGE_Q + [int.from_bytes(rng.bytes(32), "little") % Q for _ in range(200)]
+    out = C.create_string_buffer(32)
+    for i in range(len(vals)):
+        a0, a1, r = vals[i], vals[(3 * i + 1) % len(vals)], vals[(7 * i + 5) % len(vals)]
+        lib.spt_fq_fold_const(C.c_char_p(oc.mont_bytes(a0)), C.c_char_p(oc.mont_bytes(a1)), C.c_char_p(oc.mont_bytes(r)), out)
+        assert out.raw == oc.mont_bytes((a0 + r * (a1 - a0)) % Q), (a0, a1, r)
+
+
 def test_fq_mul_bit_exact_with_reference_restatement(lib):
     """same Montgomery limbs as oracle/csrc/fq.c (the restatement of ristretto255.rs:690-714) on raw limb inputs"""
     rng = np.random.default_rng(5)

@@ -75,6 +75,8 @@ def run(prog, regs):
             res = v[0]
         elif op == "and":
             res = v[0] & v[1]
+        elif op == "or":
+            res = v[0] | v[1]
         else:
             raise ValueError(op)
         regs[dst] = res
@@ -219,6 +221,132 @@ def gen_fq_mul():
     return p, a, b, r
 
 
+def gen_fq_fold_const():
+    """a0 + r*(a1 - a0) for a per-launch constant r, as a0 + sum_k d_k * RK[k] with d = a1 - a0 + q (< 2q) and the host-made table
+    RK[k] = r * 2^(32k) mod q (plain integers, r out of Montgomery form): 8 rows of 8 wide products land on the SAME nine limbs (the reduction
+    mod q of the shifted partial products is already inside the table), then one fold of the top 36 bits through 2^252 = -c (mod q).
+    72 wide products instead of the 112 of a Montgomery multiplication, and the addition of a0 rides in the first row's carry chain.
+    Inputs: a (= a0, canonical), b (= d, < 2q), k[0..63] (RK, row-major).  Output < 2q, congruent to a0 + r*(a1-a0)."""
+    p = Prog()
+    a = ["a%d" % i for i in range(8)]
+    d = ["b%d" % i for i in range(8)]
+    K = ["k%d" % i for i in range(64)]
+    E, O = {}, {}
+    for k in range(8):
+        # even columns j = 0,2,4,6 -> limbs (j, j+1); odd columns j = 1,3,5,7 -> limbs (j, j+1) = O index (j-1, j)
+        for n, j in enumerate([0, 2, 4, 6]):
+            for part, idx in (("lo", j), ("hi", j + 1)):
+                dst = p.r("e%d" % idx)
+                addend = a[idx] if k == 0 else E[idx]
+                first = n == 0 and part == "lo"
+                op = "mad.lo.cc" if first else "madc.%s.cc" % part
+                p.emit(op, dst, d[k], K[8 * k + j], addend)
+                E[idx] = dst
+        dst = p.r("e8")
+        p.emit("addc", dst, E.get(8, 0), 0)
+        E[8] = dst
+        for n, j in enumerate([1, 3, 5, 7]):
+            for part, idx in (("lo", j - 1), ("hi", j)):
+                dst = p.r("o%d" % idx)
+                if k == 0:
+                    p.emit("mul.%s" % part, dst, d[k], K[8 * k + j])
+                else:
+                    first = n == 0 and part == "lo"
+                    last = n == 3 and part == "hi"
+                    op = "mad.lo.cc" if first else ("madc.hi" if last else "madc.%s.cc" % part)   # O < 2^256: no carry out of its top limb
+                    p.emit(op, dst, d[k], K[8 * k + j], O[idx])
+                O[idx] = dst
+    T = [E[0]]
+    for i in range(1, 9):
+        dst = p.r("t%d" % i)
+        p.emit("add.cc" if i == 1 else ("addc.cc" if i < 8 else "addc"), dst, E[i], O[i - 1])
+        T.append(dst)
+    # T = T_hi * 2^252 + T_lo,  T_hi < 2^36:  T = T_lo - T_hi * c (mod q), c = q - 2^252 (limbs QL[0..3])
+    p.emit("shr", "h0a", T[7], 28); p.emit("shl", "h0b", T[8], 4); p.emit("or", "hi0", "h0a", "h0b")
+    p.emit("shr", "hi1", T[8], 28)
+    p.emit("and", "t7m", T[7], 0x0FFFFFFF)
+    p.regs.update(["h0a", "h0b", "hi0", "hi1", "t7m"])
+    p.emit("mul.lo", "x0", "hi0", QL[0]); p.emit("mul.hi", "x1", "hi0", QL[0])
+    p.emit("mul.lo", "x2", "hi0", QL[2]); p.emit("mul.hi", "x3", "hi0", QL[2])
+    p.emit("mul.lo", "y1", "hi0", QL[1]); p.emit("mul.hi", "y2", "hi0", QL[1])
+    p.emit("mul.lo", "y3", "hi0", QL[3]); p.emit("mul.hi", "y4", "hi0", QL[3])
+    # hi1 * c * 2^32: c0 -> limbs (1,2), c2 -> (3,4) join Y; c1 -> (2,3), c3 -> (4,5) join X
+    p.emit("mad.lo.cc", "y1", "hi1", QL[0], "y1"); p.emit("madc.hi.cc", "y2", "hi1", QL[0], "y2")
+    p.emit("madc.lo.cc", "y3", "hi1", QL[2], "y3"); p.emit("madc.hi.cc", "y4", "hi1", QL[2], "y4")
+    p.emit("addc", "y5", 0, 0)
+    p.emit("mad.lo.cc", "x2", "hi1", QL[1], "x2"); p.emit("madc.hi.cc", "x3", "hi1", QL[1], "x3")
+    p.emit("madc.lo.cc", "x4", "hi1", QL[3], 0); p.emit("madc.hi", "x5", "hi1", QL[3], 0)
+    p.emit("add.cc", "x1", "x1", "y1"); p.emit("addc.cc", "x2", "x2", "y2"); p.emit("addc.cc", "x3", "x3", "y3")
+    p.emit("addc.cc", "x4", "x4", "y4"); p.emit("addc", "x5", "x5", "y5")
+    # U = T_lo + q - X   in (0, 2q)
+    r = [p.r("r%d" % i) for i in range(8)]
+    lo = T[:7] + ["t7m"]
+    for i in range(8):
+        p.emit("add.cc" if i == 0 else ("addc.cc" if i < 7 else "addc"), r[i], lo[i], QL[i])
+    X = ["x0", "x1", "x2", "x3", "x4", "x5", 0, 0]
+    for i in range(8):
+        p.emit("sub.cc" if i == 0 else ("subc.cc" if i < 7 else "subc"), r[i], r[i], X[i])
+    return p, a, d, K, r
+
+
+def emit_fold_c(name, prog, a, d, K, r, comment):
+    temps = sorted(x for x in prog.regs if x not in a and x not in d and x not in K)
+    lines = ["// " + comment, "__device__ __forceinline__ u256 %s(const u256& a, const u256& b, const FqConst& rc) {" % name, "  u256 r;", "  asm(\"{\\n\\t\""]
+    for i in range(0, len(temps), 24):
+        lines.append("      \".reg .u32 %s;\\n\\t\"" % ", ".join(temps[i:i + 24]))
+
+    def opnd(x):
+        if isinstance(x, int):
+            return str(x)
+        if x in a:
+            return "%%%d" % (8 + a.index(x))
+        if x in d:
+            return "%%%d" % (16 + d.index(x))
+        if x in K:
+            return "%%%d" % (24 + K.index(x))
+        return x
+    ptxop = {"mul.lo": "mul.lo.u32", "mul.hi": "mul.hi.u32", "shl": "shl.b32", "shr": "shr.u32", "mov": "mov.u32", "and": "and.b32", "or": "or.b32"}
+    for ins in prog.ins:
+        op, dst, src = ins[0], ins[1], ins[2:]
+        lines.append("      \"%s %s, %s;\\n\\t\"" % (ptxop.get(op, op + ".u32"), dst, ", ".join(opnd(s_) for s_ in src)))
+    for i in range(8):
+        lines.append("      \"mov.u32 %%%d, %s;\\n\\t\"" % (i, r[i]))
+    lines.append("      \"}\"")
+    lines.append("      : " + ", ".join("\"=r\"(r.v[%d])" % i for i in range(8)))
+    lines.append("      : " + ", ".join("\"r\"(a.v[%d])" % i for i in range(8)) + ", " + ", ".join("\"r\"(b.v[%d])" % i for i in range(8)) + ",")
+    for i in range(0, 64, 16):
+        lines.append("        " + ", ".join("\"r\"(rc.k[%d])" % j for j in range(i, i + 16)) + ("," if i < 48 else ");"))
+    lines.append("  return r;")
+    lines.append("}")
+    return "\n".join(lines)
+
+
+def check_fold(prog, a, d, K, r, nrand=4000):
+    rnd = random.Random(7)
+    Rinv = pow(2**256, -1, Q)
+    edge = [0, 1, 2, Q - 1, Q - 2, 2**252, 2**252 - 1, 2**128, 2**32 - 1]
+    cases = [(x, y, z) for x in edge for y in edge for z in edge[:6]] + [(rnd.getrandbits(256) % Q, rnd.getrandbits(256) % Q, rnd.getrandbits(256) % Q) for _ in range(nrand)]
+    worst = 0
+    for a0, a1, rm in cases:
+        rplain = rm * Rinv % Q                       # r out of Montgomery form
+        rk = [(rplain << (32 * k)) % Q for k in range(8)]
+        dd = a1 - a0 + Q
+        regs = {}
+        for i, v in enumerate(limbs(a0)):
+            regs[a[i]] = v
+        for i, v in enumerate(limbs(dd)):
+            regs[d[i]] = v
+        for k in range(8):
+            for j, v in enumerate(limbs(rk[k])):
+                regs[K[8 * k + j]] = v
+        run(prog, regs)
+        got = sum(regs[r[i]] << (32 * i) for i in range(8))
+        want = (a0 + rm * (a1 - a0) * Rinv) % Q      # Montgomery-domain a0 + r*(a1-a0), exactly what fq_add(a0, fq_mul(r, fq_sub(a1,a0))) returns
+        assert 0 < got < 2 * Q and got % Q == want, (hex(a0), hex(a1), hex(rm), hex(got), hex(want))
+        worst = max(worst, got)
+    return worst
+
+
 def limbs(x):
     return [(x >> (32 * i)) & M32 for i in range(8)]
 
@@ -287,6 +415,12 @@ def main():
     def chk_fp(x, y, got):
         assert got < 2**256 and got % P == x * y % P, (hex(x), hex(y), hex(got))
     check(pfp, a2, b2, r2, {"dom": lambda v: v % 2**256, "check": chk_fp})
+    # lazily reduced operands of the evaluation products: up to 5q (x3 = 3*hi - 2*lo + 2q) still gives < 2^256 and the right residue
+    def chk_fq_loose(x, y, got):
+        assert got < 2**256 and got % Q == x * y * Rinv % Q
+    check(pfq, a, b, r, {"dom": lambda v: v % (5 * Q), "check": chk_fq_loose}, nrand=3000)
+    pfo, fa, fd, fK, fr = gen_fq_fold_const()
+    check_fold(pfo, fa, fd, fK, fr)
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spartan_b200", "csrc", "mul_ptx.cuh")
     with open(out, "w") as f:
         f.write("// GENERATED by tools/gen_ptx_mul.py (emulator-checked against Python integers before emission) — do not edit.\n")
@@ -294,8 +428,10 @@ def main():
         f.write("#pragma once\n#if defined(__CUDA_ARCH__)\nnamespace sp {\n")
         f.write(emit_c("fq_mul_ptx", pfq, a, b, r, "Montgomery product a*b*2^-256 mod q, unreduced in [0, 2q)") + "\n")
         f.write(emit_c("fp_mul_ptx", pfp, a2, b2, r2, "a*b mod 2^255-19, loose in [0, 2^256)") + "\n")
+        f.write("// per-launch constant multiplier of the fold  a0 + r*(a1-a0)  (FqConst, field.cuh):  k[8*j+i] = limb i of (r * 2^(32j) mod q), r out of Montgomery form\n")
+        f.write(emit_fold_c("fq_fold_const_ptx", pfo, fa, fd, fK, fr, "a + sum_j b_j * RK[j] folded once through 2^252 = -c: result in (0, 2q), congruent to a0 + r*(a1-a0); b = a1 - a0 + q; %d PTX instructions" % (len(pfo.ins) + 8)) + "\n")
         f.write("}  // namespace sp\n#endif\n")
-    print("wrote", out, "fq", len(pfq.ins), "fp", len(pfp.ins))
+    print("wrote", out, "fq", len(pfq.ins), "fp", len(pfp.ins), "fold_const", len(pfo.ins))
 
 
 if __name__ == "__main__":
