@@ -49,6 +49,18 @@ int sp_ctx_create(int device, sp_ctx** out);
 void sp_ctx_destroy(sp_ctx* ctx);
 const char* sp_last_error(const sp_ctx* ctx);  /* ctx may be NULL: message of the last failed sp_ctx_create */
 unsigned long long sp_kernel_launches(void);   /* kernels launched by this library since load */
+
+/* ---- one proof over several GPUs (the reference is single-process, the loops being sharded are dense_mlpoly.rs:215-223,
+ * sumcheck.rs:290-357 / :460-469 / :625-652, dense_mlpoly.rs:165-177, product_tree.rs:18-56).  One process per GPU, one context per process.
+ * Every rank calls sp_comm_export, the hosts exchange the sp_comm_handle_bytes()-byte handles by any transport (MPI, a socket, torch.distributed),
+ * every rank calls sp_comm_connect with all handles in rank order (world = 2, 4 or 8 GPUs of one NVLink domain).  From then on sp_nizk_prove* and
+ * sp_snark_prove* must be called by EVERY rank with identical arguments: each call is one sharded proof, every rank returns the same proof bytes —
+ * the bytes the single-GPU prover returns.  Operator-level entry points, encode and the verifiers stay single-GPU. */
+size_t sp_comm_handle_bytes(void);
+int sp_comm_export(sp_ctx* ctx, uint8_t* handle_out);
+int sp_comm_connect(sp_ctx* ctx, int rank, int world, const uint8_t* handles /* world x sp_comm_handle_bytes() */);
+int sp_comm_info(const sp_ctx* ctx, int* rank, int* world);
+int sp_comm_set_enabled(sp_ctx* ctx, int enabled);   /* 0: the next prove calls run on this rank's GPU alone (all ranks must switch together) */
 /* phase timings of the last prove call, the labels of the reference's `profile` feature (src/timer.rs; src/r1csproof.rs:152-298) */
 int sp_timings(sp_ctx* ctx, char* buf, size_t buflen);
 /* bytes moved host->device / device->host by this library since load (bench.py e2e leg) */

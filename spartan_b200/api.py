@@ -80,9 +80,26 @@ class Context:
             raise ProofVerifyError("DecompressionError: " + msg)
         raise SpartanB200Error("spartan_b200 error %d: %s" % (rc, msg))
 
+    def connect_peers(self, rank, world, allgather):
+        """Join `world` single-GPU processes into one sharded prover (sp_comm_export / sp_comm_connect).  `allgather(b: bytes) -> list[bytes]`
+        is the host-side exchange (every rank contributes its handle, all get the list in rank order): spartan_b200.dist.allgather_bytes under
+        torch.distributed.  Afterwards NIZK.prove / SNARK.prove must be called by every rank with the same arguments."""
+        lib.sp_comm_handle_bytes.restype = C.c_size_t
+        hb = int(lib.sp_comm_handle_bytes())
+        mine = C.create_string_buffer(hb)
+        self.check(lib.sp_comm_export(self.h, mine))
+        handles = allgather(mine.raw)
+        assert len(handles) == world and all(len(h) == hb for h in handles)
+        self.check(lib.sp_comm_connect(self.h, C.c_int(rank), C.c_int(world), C.c_char_p(b"".join(handles))))
+        self.rank, self.world = rank, world
+
+    def set_sharding(self, enabled):
+        """switch sharded proving off / on for a connected context (every rank must switch together)"""
+        lib.sp_comm_set_enabled(self.h, C.c_int(1 if enabled else 0))
+
     def timings(self):
-        buf = C.create_string_buffer(4096)
-        lib.sp_timings(self.h, buf, _sz(4096))
+        buf = C.create_string_buffer(8192)
+        lib.sp_timings(self.h, buf, _sz(8192))
         out = {}
         for item in buf.value.decode().split(";"):
             if "=" in item:

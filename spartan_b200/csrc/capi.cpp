@@ -62,6 +62,24 @@ int sp_timings(sp_ctx* ctx, char* buf, size_t buflen) {
   return SP_OK;
 }
 
+// ---- intra-proof sharding: one process per GPU, windows exchanged as CUDA IPC handles by whatever transport the host has
+size_t sp_comm_handle_bytes(void) { return dev::ipc_handle_bytes(); }
+int sp_comm_export(sp_ctx* ctx, uint8_t* handle_out) {
+  SP_TRY(ctx)
+  ctx->c.comm_create();
+  if (ctx->c.comm->connected) throw SpError(SP_ERR_INVALID_ARG, "communicator already connected");
+  ctx->c.comm->export_handle(handle_out);
+  SP_CATCH(ctx)
+}
+int sp_comm_connect(sp_ctx* ctx, int rank, int world, const uint8_t* handles) {
+  SP_TRY(ctx)
+  if (!ctx->c.comm) throw SpError(SP_ERR_INVALID_ARG, "sp_comm_export must be called first (it creates the window whose handle the peers map)");
+  ctx->c.comm->connect(rank, world, handles);
+  SP_CATCH(ctx)
+}
+int sp_comm_set_enabled(sp_ctx* ctx, int enabled) { ctx->c.shard_enabled = enabled != 0; return SP_OK; }
+int sp_comm_info(const sp_ctx* ctx, int* rank, int* world) { *rank = ctx->c.rank(); *world = ctx->c.world(); return SP_OK; }
+
 void sp_io_bytes(unsigned long long* h, unsigned long long* d) { dev::io_bytes(h, d); }
 void sp_prof_enable(int on) { dev::prof_enable(on != 0); }
 int sp_prof_report(char* buf, size_t buflen) {

@@ -60,14 +60,40 @@ struct HostSig {
   unsigned int* done = nullptr;
   unsigned int seq = 0;
 };
+// ---- intra-proof sharding over NVLink peer memory (comm.cu).  One process per GPU; every rank owns a "window" (plain cudaMalloc memory
+// exported with cudaIpcGetMemHandle and mapped by every peer), laid out as [control | data half 0 | data half 1]:
+//   control: per-source flag words and mailboxes for the per-round exchange of partial sums, flag words for the bulk all-gathers, an error word
+//   data   : destination of the bulk all-gathers (alternating halves), read in place by the kernels that follow
+// All ranks execute the same sequence of collectives, so a sequence number identifies an operation on every rank.
+#define SP_MAX_RANKS 8
+#define SP_XR_SLOTS 4
+#define SP_XR_CAP 80                                   // u256 per (slot, source): 24 instances x 3 evaluations fit
+#define SP_WIN_CTRL_BYTES ((size_t)1 << 20)
+#define SP_WIN_HALF_BYTES ((size_t)96 << 20)
+struct WinCtrl {                                        // at offset 0 of every window
+  unsigned int xflag[SP_MAX_RANKS];                     // [source]: sequence number of the last partial-sum message from `source`
+  unsigned int bflag[SP_MAX_RANKS];                     // [source]: sequence number of the last bulk all-gather contribution from `source`
+  unsigned int err;                                     // set by a kernel whose peer wait timed out
+  unsigned int pad[15];
+  u256 mbox[SP_XR_SLOTS][SP_MAX_RANKS][SP_XR_CAP];      // [seq % SP_XR_SLOTS][source][value]
+};
+// Cross-rank completion of a reduction kernel: the finishing warp stores this rank's totals into every peer's mailbox (NVLink stores), publishes
+// the sequence number, waits for the peers' messages and adds them up in rank order (exact field arithmetic: every rank gets identical bytes),
+// then hands the sums to the host.  world <= 1: no exchange.
+struct XRank {
+  int world = 1, rank = 0;
+  unsigned int seq = 0;
+  WinCtrl* win[SP_MAX_RANKS] = {};                      // this process's mapping of every rank's window (win[rank] = own)
+};
+
 // scratch: >= sc_scratch_bytes(); out: ninst*3 scalars [e0,e2,e3] (e3 = 0 for SC_QUAD), device memory
 size_t sc_scratch_bytes(int ninst);
 void dot_pairs(u256* out, const u256* const* a_list, const u256* const* b_list, int count, size_t n, void* scratch, cudaStream_t s, HostSig sig = HostSig());
 void heads(u256* out, const u256* const* tables, int count, cudaStream_t s, HostSig sig = HostSig());
-void sc_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s, HostSig sig = HostSig());
+void sc_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s, HostSig sig = HostSig(), const XRank& xr = XRank());
 // fold every table of every instance by r (len -> len/2, in place) and evaluate the next round on the result; r travels as a kernel argument
 void sc_fold_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s,
-                  HostSig sig = HostSig());
+                  HostSig sig = HostSig(), const XRank& xr = XRank());
 // fold only (bound_poly_var_top, dense_mlpoly.rs:215-223): tables[k][i] += r*(tables[k][i+len/2]-tables[k][i])
 void fold_top(u256* const* d_tables, int ntables, size_t len, const u256& r, cudaStream_t s);
 void fold_top_single(u256* table, size_t len, const u256& r, cudaStream_t s);
@@ -95,6 +121,29 @@ void ipa_fold_ab(u256* a, u256* b, size_t n, const u256& u, const u256& uinv, cu
 void ipa_lr_scalars(u256* outL, u256* outR, const u256* a, const u256* svec, size_t n_cur, size_t n_full, cudaStream_t s);
 void ipa_update_s(u256* svec, size_t n_cur_half, size_t n_full, const u256& u, const u256& uinv, cudaStream_t s);
 void fill_one(u256* out, size_t n, cudaStream_t s);
+
+// windows: IPC-exportable device allocations and their mappings in the peers
+void* win_alloc(size_t bytes);
+void win_free(void* p);
+size_t ipc_handle_bytes();
+void ipc_export(void* devptr, uint8_t* out);
+void* ipc_open(const uint8_t* handle);
+void ipc_close(void* p);
+// ---- sharded table producers: rank `rank` of `world` holds the global indices i = j*world + rank (cyclic partition) at local index j
+void scale(u256* inout, const u256& c, size_t n, cudaStream_t s);                                        // x[i] *= c
+void take_cyclic(u256* out, const u256* full, size_t n_local, int rank, int world, cudaStream_t s);      // out[j] = full[j*world + rank]
+void spmv_cyclic(u256* out, size_t nrows_local, int rank, int world, const uint32_t* ptr, const uint32_t* idx, const u256* val, const u256* x, cudaStream_t s);
+void spark_hash_cyclic(u256* out, size_t n_local, int rank, int world, const u256* addr, const u256* val, const u256* ts, int ts_plus_one, const u256* d_rg, cudaStream_t s);
+// ---- bulk all-gathers into every rank's window (comm.cu); `dst_off`: byte offset inside the window, the same on every rank
+struct CommDev {                                        // device-side view of the communicator
+  int world = 1, rank = 0;
+  uint8_t* win[SP_MAX_RANKS] = {};
+};
+// every rank's `bytes` land at dst_off + source*bytes of every window
+void push_block(const CommDev& c, const void* src, size_t bytes, size_t dst_off, unsigned int seq, unsigned int* ticket, cudaStream_t s);
+// table t of rank `source`, element j  ->  window element (dst_off/32) + t*(n_local*world) + j*world + source
+void push_cyclic(const CommDev& c, const u256* const* tables, int ntables, size_t n_local, size_t dst_off, unsigned int seq, unsigned int* ticket, cudaStream_t s);
+void wait_peers(const CommDev& c, unsigned int seq, cudaStream_t s);   // returns (on the stream) once every peer's contribution `seq` has landed
 
 // ---- sparse matrix-vector products on CSR (row-major) / CSC (column-major) copies of the COO triples
 void spmv(u256* out, size_t nrows, const uint32_t* ptr, const uint32_t* idx, const u256* val, const u256* x, cudaStream_t s);

@@ -33,8 +33,50 @@ struct DevBuf {  // owning device allocation
   void release() { if (p) dev::pool_free(p); p = nullptr; n = 0; }
 };
 
+// Intra-proof sharding: this rank's window, the peers' windows mapped through CUDA IPC, and the sequence counters every rank
+// advances in lock step (all ranks run the same prover code on the same transcript, so they issue the same collectives in the same order).
+struct Comm {
+  int world = 1, rank = 0;
+  uint8_t* win[SP_MAX_RANKS] = {};     // win[rank]: own allocation; others: cudaIpcOpenMemHandle mappings
+  bool connected = false;
+  unsigned int xseq = 0, bseq = 0;     // per-round partial-sum exchanges / bulk all-gathers issued so far
+  DevBuf<unsigned int> ticket;         // block counter of the push kernels (zeroed once, self-resetting)
+  Comm();
+  ~Comm();
+  Comm(const Comm&) = delete;
+  Comm& operator=(const Comm&) = delete;
+  static size_t window_bytes() { return SP_WIN_CTRL_BYTES + 2 * SP_WIN_HALF_BYTES; }
+  void export_handle(uint8_t* out) const { dev::ipc_export(win[rank], out); }   // valid before connect(): rank is 0 then, win[0] is the own window
+  void connect(int rank_, int world_, const uint8_t* handles);                   // handles: world x ipc_handle_bytes(), in rank order
+  dev::XRank next_xr() {
+    dev::XRank x; x.world = world; x.rank = rank; x.seq = ++xseq;
+    for (int p = 0; p < world; p++) x.win[p] = reinterpret_cast<dev::WinCtrl*>(win[p]);
+    return x;
+  }
+  dev::CommDev devview() const { dev::CommDev c; c.world = world; c.rank = rank; for (int p = 0; p < world; p++) c.win[p] = win[p]; return c; }
+  // data half of the next bulk all-gather (alternating: a half is reused only after every rank has passed the collective in between)
+  size_t next_half_off() { ++bseq; return SP_WIN_CTRL_BYTES + (size_t)(bseq & 1) * SP_WIN_HALF_BYTES; }
+};
+
 struct Ctx {
   int device = 0;
+  std::unique_ptr<Comm> comm;          // null: single-GPU context
+  int world() const { return comm && comm->connected ? comm->world : 1; }
+  int rank() const { return comm && comm->connected ? comm->rank : 0; }
+  // all-gather helpers (no-ops' worth of work when world() == 1 is the caller's business: they require a connected communicator)
+  // every rank contributes `bytes` from device memory `src`; returns a device pointer (inside the own window) to world x bytes, rank-major
+  const uint8_t* allgather_block(const void* src, size_t bytes);
+  // every rank contributes `ntables` tables of n_local elements (cyclic shards); returns the window copy: table t = ptr + t*n_local*world, global order
+  u256* allgather_cyclic(const u256* const* tables, int ntables, size_t n_local);
+  void comm_create();                  // allocate the window (idempotent); connect through comm->connect
+  // Sharding is switched on per prove call (ShardScope): operator-level entry points stay single-GPU even on a connected context, because a
+  // collective needs every rank to make the same call.
+  bool sharding = false;
+  bool shard_enabled = true;           // sp_comm_set_enabled: a connected context can also prove on its own GPU only (every rank must agree)
+  int shard_world() const { return sharding ? world() : 1; }
+  // a table of `global_len` elements is worth sharding when every rank keeps at least one streaming-size fused round (see sc_fold_eval)
+  static constexpr size_t SHARD_MIN_LOCAL = 8192;
+  bool shard_table(size_t global_len) const { return shard_world() > 1 && global_len >= 2 * SHARD_MIN_LOCAL * (size_t)shard_world(); }
   cudaStream_t stream = nullptr;
   uint8_t* pinned = nullptr;       // staging for small host<->device exchanges
   size_t pinned_bytes = 0;
@@ -64,6 +106,23 @@ struct Ctx {
   void upload(u256* d, const Fq* h, size_t n);
   std::vector<Fq> download(const u256* d, size_t n);
 };
+
+struct ShardScope {   // RAII: sharded proving for the duration of one prove call on a connected context
+  Ctx& ctx; bool prev;
+  explicit ShardScope(Ctx& c) : ctx(c), prev(c.sharding) { c.sharding = c.world() > 1 && c.shard_enabled; }
+  ~ShardScope() { ctx.sharding = prev; }
+};
+// eq(r, j*W + rank) = c * eq(r[0 .. ell-log2 W), j): the factor contributed by the last log2(W) variables, which the rank fixes
+inline Fq shard_eq_scale(const std::vector<Fq>& r, int W, int rank) {
+  int logW = 0;
+  while ((1 << logW) < W) logW++;
+  Fq c = Fq::one();
+  for (int k = 0; k < logW; k++) {
+    const Fq& rj = r[r.size() - logW + k];
+    c *= ((rank >> (logW - 1 - k)) & 1) ? rj : Fq::one() - rj;
+  }
+  return c;
+}
 
 // One SHAKE256 generator stream (a `label` of MultiCommitGens::new, commitments.rs:15-33) expanded to `nbases` points,
 // with the fixed-base window table on the device and host copies of the tables of a few named bases.

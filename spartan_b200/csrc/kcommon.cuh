@@ -70,13 +70,58 @@ __device__ __forceinline__ u256 warp_sum_fq(u256 x) {
   return x;
 }
 
+// ---- system-scope flag accesses and the cross-rank completion of a reduction (dev.hpp: XRank)
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= seq (sequence numbers only grow); a peer that never arrives traps the kernel after 30 s instead of hanging the GPU
+__device__ __forceinline__ void wait_flag_sys(const unsigned int* flag, unsigned int seq) {
+  const unsigned long long t0 = global_timer_ns();
+  unsigned int spins = 0;
+  while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+    if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 30000000000ull) __trap();
+  }
+}
+// One warp (all 32 lanes): out[0..nvals) holds this rank's totals; on return it holds the sum over all ranks (also stored to host_out).
+__device__ __forceinline__ void xrank_exchange(const XRank& xr, u256* out, int nvals, u256* host_out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int slot = xr.seq % SP_XR_SLOTS;
+  for (int v = lane; v < nvals; v += 32) {
+    const u256 x = ld256_cg(out + v);
+    for (int p = 0; p < xr.world; p++)
+      if (p != xr.rank) st256(&xr.win[p]->mbox[slot][xr.rank][v], x);          // NVLink store into the peer's mailbox
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < xr.world && lane != xr.rank) {
+    st_release_sys(&xr.win[lane]->xflag[xr.rank], xr.seq);                     // tell peer `lane` that message `seq` of this rank has landed
+    wait_flag_sys(&xr.win[xr.rank]->xflag[lane], xr.seq);                      // and wait for its message
+  }
+  __syncwarp();
+  for (int v = lane; v < nvals; v += 32) {
+    u256 s = fq_zero();
+    for (int p = 0; p < xr.world; p++)                                          // rank order; exact arithmetic: identical bytes on every rank
+      s = fq_add(s, p == xr.rank ? ld256_cg(out + v) : ld256_cg(&xr.win[xr.rank]->mbox[slot][p][v]));
+    st256(out + v, s);
+    if (host_out) st256(host_out + v, s);
+  }
+}
+
 // Block-wide sum of NV field values per thread, then cross-block finalisation by the last block to arrive.
 // partials: [gridDim.y][gridDim.x][NV]; counters: [gridDim.y] zero-initialised, self-resetting.
 // `sig` (optional): the finishing block also stores the results into mapped pinned host memory and then publishes `seq` in a host flag
 // word, so the host can pick a round's evaluations up by polling instead of a memcpy + stream synchronise.
 template <int NV>
 __device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* partials, unsigned int* counters, u256* out, int out_stride,
-                                                    HostSig sig = HostSig()) {
+                                                    HostSig sig = HostSig(), const XRank& xr = XRank()) {
   __shared__ u256 sm[32][NV];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -103,6 +148,7 @@ __device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* parti
   if (is_last) {
     __threadfence();
     if (warp == 0) {
+      const bool xr_on = xr.world > 1;       // sharded: the host gets the sum over all ranks, not this rank's totals
 #pragma unroll
       for (int k = 0; k < NV; k++) {
         u256 s = fq_zero();
@@ -110,21 +156,27 @@ __device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* parti
         s = warp_sum_fq(s);
         if (lane == 0) {
           st256(&out[(size_t)blockIdx.y * out_stride + k], s);
-          if (sig.host_out) st256(&sig.host_out[(size_t)blockIdx.y * out_stride + k], s);
+          if (sig.host_out && !xr_on) st256(&sig.host_out[(size_t)blockIdx.y * out_stride + k], s);
         }
       }
+      unsigned int last_inst = 0;
       if (lane == 0) {
         counters[blockIdx.y] = 0;
         if (sig.flag) {
           __threadfence_system();
           unsigned int done = atomicAdd(sig.done, 1u) + 1;       // instances (blockIdx.y) finish independently
-          if (done == gridDim.y) { *sig.done = 0; __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
+          last_inst = done == gridDim.y;
+          if (last_inst) *sig.done = 0;
         }
+      }
+      last_inst = __shfl_sync(0xffffffffu, last_inst, 0);
+      if (last_inst) {
+        if (xr_on) { __threadfence(); xrank_exchange(xr, out, (int)(gridDim.y * out_stride), sig.host_out); }
+        if (lane == 0) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
       }
     }
   }
 }
-
 
 }  // namespace dev
 }  // namespace sp

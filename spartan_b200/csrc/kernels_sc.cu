@@ -43,7 +43,8 @@ __device__ __forceinline__ void sc_accumulate(u256 (&acc)[3], const u256 (&lo)[4
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t len, u256* partials, unsigned int* counters, u256* out, HostSig sig) {
+__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t len, u256* partials, unsigned int* counters, u256* out, HostSig sig,
+                                                                   const __grid_constant__ XRank xr) {
   constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
   const ScInst& in = batch.inst[blockIdx.y];
   const size_t half = len >> 1;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t
     for (int t = 0; t < NT; t++) { lo[t] = ld256(in.t[t] + i); hi[t] = ld256(in.t[t] + i + half); }
     sc_accumulate<KIND>(acc, lo, hi);
   }
-  block_reduce_finish<3>(acc, partials, counters, out, 3, sig);
+  block_reduce_finish<3>(acc, partials, counters, out, 3, sig, xr);
 }
 
 // Fused: bind the top variable with r (len -> len/2) and evaluate the next round's polynomial on the folded table.
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval(ScBatch batch, size_t
 // modular addition) instead of sub + Montgomery product + add; same canonical values either way.
 template <int KIND, bool CF>
 __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, size_t len, const u256 r, const __grid_constant__ FqConst rc, u256* partials,
-                                                       unsigned int* counters, u256* out, HostSig sig) {
+                                                       unsigned int* counters, u256* out, HostSig sig, const __grid_constant__ XRank xr) {
   constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
   const ScInst& in = batch.inst[blockIdx.y];
   const size_t half = len >> 1, quarter = len >> 2;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, s
     }
     sc_accumulate<KIND>(acc, lo, hi);
   }
-  block_reduce_finish<3>(acc, partials, counters, out, 3, sig);
+  block_reduce_finish<3>(acc, partials, counters, out, 3, sig, xr);
 }
 
 // ---- register-lean formulation of the fused round (3 CTAs of 256 threads per SM instead of 2).
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, s
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(SC_V2_THREADS, SC_V2_BLOCKS) k_sc_fold_eval_v2(ScBatch batch, size_t len, const __grid_constant__ FqConst rc, u256* partials,
-                                                            unsigned int* counters, u256* out, HostSig sig) {
+                                                            unsigned int* counters, u256* out, HostSig sig, const __grid_constant__ XRank xr) {
   constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
   constexpr int NP = KIND == SC_QUAD ? 2 : 3;
   __shared__ uint32_t accs[3][8][SC_V2_THREADS];
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(SC_V2_THREADS, SC_V2_BLOCKS) k_sc_fold_eval_v2
   for (int k = 0; k < 3; k++)
 #pragma unroll
     for (int l = 0; l < 8; l++) acc[k].v[l] = accs[k][l][tid];
-  block_reduce_finish<3>(acc, partials, counters, out, 3, sig);
+  block_reduce_finish<3>(acc, partials, counters, out, 3, sig, xr);
 }
 
 // Small tables (len/4 <= SC_SMALL_MAX): the round's latency, not its throughput, is what the prover waits for, so the work of one index is
@@ -271,7 +272,7 @@ static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
   for (int i = 0; i < ninst; i++) b.inst[i] = insts[i];
 }
 
-void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s, HostSig sig) {
+void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s, HostSig sig, const XRank& xr) {
   ProfScope ps("sc_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 32.0, s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
@@ -279,13 +280,14 @@ void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out,
   dim3 grid(grid_for(len / 2, 256, 2), ninst);
   if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
   switch (kind) {
-    case SC_QUAD: k_sc_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig); break;
-    case SC_CUBIC3: k_sc_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig); break;
-    default: k_sc_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig); break;
+    case SC_QUAD: k_sc_eval<SC_QUAD><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig, xr); break;
+    case SC_CUBIC3: k_sc_eval<SC_CUBIC3><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig, xr); break;
+    default: k_sc_eval<SC_CUBIC4><<<grid, 256, 0, s>>>(b, len, partials, counters, out, sig, xr); break;
   }
   SP_LAUNCHED(); check("sc_eval");
 }
-void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s, HostSig sig) {
+void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s, HostSig sig, const XRank& xr) {
+  if (xr.world > 1 && (len / 4 <= SC_SMALL_MAX || !sig.flag)) throw std::runtime_error("spartan_b200: a sharded sumcheck round needs a streaming-size table and a host signal");
   ProfScope ps("sc_fold_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 48.0, s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
@@ -293,9 +295,9 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
   static const bool small_ok = getenv("SP_SC_NO_SMALL") == nullptr;
   static const bool cf = getenv("SP_SC_NO_CONSTFOLD") == nullptr;   // A/B switch for the constant-multiplier fold (tools/bench_kernels.py)
   const FqConst rc = cf ? fq_const_table(r) : FqConst();
-#define SP_SC_LAUNCH(KERNEL, K, THREADS) \
-  do { if (cf) KERNEL<K, true><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig); \
-       else KERNEL<K, false><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig); } while (0)
+#define SP_SC_LAUNCH(KERNEL, K, THREADS, ...) \
+  do { if (cf) KERNEL<K, true><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig, ##__VA_ARGS__); \
+       else KERNEL<K, false><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig, ##__VA_ARGS__); } while (0)
   if (small_ok && len / 4 <= SC_SMALL_MAX && len >= 4) {
     dim3 grid((unsigned)((len / 4 + SC_SMALL_Q - 1) / SC_SMALL_Q), ninst);
     switch (kind) {
@@ -311,9 +313,9 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
     dim3 grid(grid_for(len / 4, SC_V2_THREADS, SC_V2_BLOCKS), ninst);
     if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
     switch (kind) {
-      case SC_QUAD: k_sc_fold_eval_v2<SC_QUAD><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig); break;
-      case SC_CUBIC3: k_sc_fold_eval_v2<SC_CUBIC3><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig); break;
-      default: k_sc_fold_eval_v2<SC_CUBIC4><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig); break;
+      case SC_QUAD: k_sc_fold_eval_v2<SC_QUAD><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig, xr); break;
+      case SC_CUBIC3: k_sc_fold_eval_v2<SC_CUBIC3><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig, xr); break;
+      default: k_sc_fold_eval_v2<SC_CUBIC4><<<grid, SC_V2_THREADS, 0, s>>>(b, len, rc, partials, counters, out, sig, xr); break;
     }
     SP_LAUNCHED(); check("sc_fold_eval_v2");
     return;
@@ -321,9 +323,9 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
   dim3 grid(grid_for(len / 4, 256, SP_SC_LB), ninst);
   if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
   switch (kind) {
-    case SC_QUAD: SP_SC_LAUNCH(k_sc_fold_eval, SC_QUAD, 256); break;
-    case SC_CUBIC3: SP_SC_LAUNCH(k_sc_fold_eval, SC_CUBIC3, 256); break;
-    default: SP_SC_LAUNCH(k_sc_fold_eval, SC_CUBIC4, 256); break;
+    case SC_QUAD: SP_SC_LAUNCH(k_sc_fold_eval, SC_QUAD, 256, xr); break;
+    case SC_CUBIC3: SP_SC_LAUNCH(k_sc_fold_eval, SC_CUBIC3, 256, xr); break;
+    default: SP_SC_LAUNCH(k_sc_fold_eval, SC_CUBIC4, 256, xr); break;
   }
 #undef SP_SC_LAUNCH
   SP_LAUNCHED(); check("sc_fold_eval");

@@ -46,6 +46,13 @@ Ctx::Ctx(int dev_) : device(dev_) {
   dev::dzero(red.p, red.n, stream);
   sync();
 }
+void Ctx::comm_create() {
+  if (comm) return;
+  dev::set_device(device);
+  comm.reset(new Comm());
+  dev::dzero(comm->ticket.p, 16, stream);
+  sync();
+}
 Ctx::~Ctx() {
   try { sync(); } catch (...) {}
   scratch.release(); red.release(); small.release();
@@ -65,6 +72,44 @@ void Ctx::wait_sig(const dev::HostSig& s) {
   }
   std::atomic_thread_fence(std::memory_order_acquire);
 }
+// ---- communicator
+Comm::Comm() {
+  win[0] = (uint8_t*)dev::win_alloc(window_bytes());
+  ticket.alloc(4);
+}
+Comm::~Comm() {
+  for (int p = 0; p < SP_MAX_RANKS; p++) {
+    if (!win[p]) continue;
+    if (p == rank) dev::win_free(win[p]); else dev::ipc_close(win[p]);
+  }
+}
+void Comm::connect(int rank_, int world_, const uint8_t* handles) {
+  if (connected) throw SpError(SP_ERR_INVALID_ARG, "communicator already connected");
+  if (world_ < 1 || world_ > SP_MAX_RANKS || (world_ & (world_ - 1)) || rank_ < 0 || rank_ >= world_) throw SpError(SP_ERR_INVALID_ARG, "sharding needs a power-of-two world of at most 8 ranks");
+  uint8_t* own = win[0];
+  win[0] = nullptr;
+  rank = rank_; world = world_;
+  const size_t hb = dev::ipc_handle_bytes();
+  for (int p = 0; p < world; p++) win[p] = p == rank ? own : (uint8_t*)dev::ipc_open(handles + (size_t)p * hb);
+  connected = true;
+}
+const uint8_t* Ctx::allgather_block(const void* src, size_t bytes) {
+  Comm& c = *comm;
+  if ((size_t)c.world * bytes > SP_WIN_HALF_BYTES) throw std::runtime_error("spartan_b200: all-gather larger than the window");
+  const size_t off = c.next_half_off();
+  dev::push_block(c.devview(), src, bytes, off, c.bseq, c.ticket.p, stream);
+  dev::wait_peers(c.devview(), c.bseq, stream);
+  return c.win[c.rank] + off;
+}
+u256* Ctx::allgather_cyclic(const u256* const* tables, int ntables, size_t n_local) {
+  Comm& c = *comm;
+  if ((size_t)ntables * n_local * c.world * sizeof(u256) > SP_WIN_HALF_BYTES) throw std::runtime_error("spartan_b200: all-gather larger than the window");
+  const size_t off = c.next_half_off();
+  dev::push_cyclic(c.devview(), tables, ntables, n_local, off, c.bseq, c.ticket.p, stream);
+  dev::wait_peers(c.devview(), c.bseq, stream);
+  return reinterpret_cast<u256*>(c.win[c.rank] + off);
+}
+
 void Ctx::put_small(size_t slot, const Fq* v, size_t k) {
   // staged through pageable memory on purpose: cudaMemcpyAsync from pageable memory snapshots the source before returning
   dev::h2d(small.p + slot, v, k * sizeof(u256), stream);
@@ -258,9 +303,16 @@ std::vector<Fq> host_eq_evals(const std::vector<Fq>& r) {  // EqPolynomial::eval
 // ================================================================================================ ZK sumcheck on the device
 // prove_quad (sumcheck.rs:428-586) and prove_cubic_with_additive_term (sumcheck.rs:588-776).
 // tables: NT device arrays of length 2^num_rounds, folded in place (their first element holds the final evaluation).
-static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const Fq& blind_claim, size_t num_rounds, u256* const* tables, int nt,
+// sharded: `tables_in` are this rank's cyclic shards (length 2^num_rounds / world).  The first rounds then run on the shards — the fused
+// kernels exchange their partial sums over NVLink before handing the round's evaluations to the host — until the local tables drop below
+// streaming size; the shards are then all-gathered into replicated tables (in the window) and the latency-bound tail runs on every rank alike.
+static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const Fq& blind_claim, size_t num_rounds, u256* const* tables_in, int nt,
                               const CommitKey& g1, const CommitKey& gn, Transcript& T, RandomTape& tape, ZKSumcheckInstanceProof& proof,
-                              std::vector<Fq>& r, std::vector<Fq>& finals, Fq& blind_post) {
+                              std::vector<Fq>& r, std::vector<Fq>& finals, Fq& blind_post, bool sharded = false) {
+  std::vector<u256*> tabs(tables_in, tables_in + nt);
+  u256* const* tables = tabs.data();
+  bool sh = sharded && ctx.shard_world() > 1;
+  const int W = sh ? ctx.shard_world() : 1;
   const int degree = kind == dev::SC_QUAD ? 2 : 3;
   std::vector<Fq> blinds_poly = tape.random_vector("blinds_poly", num_rounds);
   std::vector<Fq> blinds_evals = tape.random_vector("blinds_evals", num_rounds);
@@ -313,9 +365,9 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
   inst.c_out = inst.t[2];
   inst.write_c = 1;
   u256* d_out = ctx.small.p + 0;     // 3 result scalars
-  size_t len = (size_t)1 << num_rounds;
+  size_t len = ((size_t)1 << num_rounds) / W;   // current length of the tables this rank holds
   dev::HostSig sig = ctx.next_sig();
-  dev::sc_eval(kind, &inst, 1, len, d_out, ctx.red.p, ctx.stream, sig);
+  dev::sc_eval(kind, &inst, 1, len, d_out, ctx.red.p, ctx.stream, sig, sh ? ctx.comm->next_xr() : dev::XRank());
   for (size_t j = 0; j < num_rounds; j++) {
     Fq e[3];
     FineTimer fw(ctx, "zk wait evals");
@@ -332,9 +384,22 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
     Fq r_j = T.challenge_scalar("challenge_nextround");
     // bind the tables to r_j on the device right away (fused with the next round's evaluation); the host continues with the
     // sigma protocol of this round while the kernel runs
-    if (j + 1 < num_rounds) { sig = ctx.next_sig(); dev::sc_fold_eval(kind, &inst, 1, len, r_j.m, d_out, ctx.red.p, ctx.stream, sig); }
-    else dev::fold_top(tables, nt, len, r_j.m, ctx.stream);
-    len >>= 1;
+    if (j + 1 < num_rounds && sh && len < Ctx::SHARD_MIN_LOCAL) {
+      // leave the sharded stage: bind locally, all-gather the shards into replicated tables, evaluate the next round there
+      dev::fold_top(tables, nt, len, r_j.m, ctx.stream);
+      const size_t glen = (len / 2) * W;
+      u256* g = ctx.allgather_cyclic(tables, nt, len / 2);
+      for (int t = 0; t < nt; t++) { tabs[t] = g + (size_t)t * glen; inst.t[t] = tabs[t]; }
+      inst.c_out = inst.t[2];
+      sh = false;
+      len = glen;
+      sig = ctx.next_sig();
+      dev::sc_eval(kind, &inst, 1, len, d_out, ctx.red.p, ctx.stream, sig);
+    } else {
+      if (j + 1 < num_rounds) { sig = ctx.next_sig(); dev::sc_fold_eval(kind, &inst, 1, len, r_j.m, d_out, ctx.red.p, ctx.stream, sig, sh ? ctx.comm->next_xr() : dev::XRank()); }
+      else dev::fold_top(tables, nt, len, r_j.m, ctx.stream);
+      len >>= 1;
+    }
     fh.stop();
     FineTimer fs(ctx, "zk host sigma (overlaps kernel)");
 
@@ -378,11 +443,21 @@ Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalar
   DevBuf<ge> rows(L);
   DevBuf<u256> d_bl;
   if (blinds) { d_bl.alloc(L); dev::h2d(d_bl.p, blinds, L * sizeof(u256), ctx.stream); }
-  dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars, stride, L, R, blinds ? d_bl.p : nullptr, key.h, ctx.scratch.p, ctx.stream);
   DevBuf<uint8_t> comp(32 * L);
-  dev::compress_batch(comp.p, rows.p, L, ctx.stream);
   out.resize(L);
-  dev::d2h(out.data(), comp.p, 32 * L, ctx.stream);
+  const size_t W = (size_t)ctx.shard_world();
+  if (W > 1 && L >= 2 * W && L % W == 0) {
+    // rows are independent MSMs over the same generators: rank r commits rows [r*L/W, (r+1)*L/W) and the 32-byte encodings are all-gathered
+    const size_t Lr = L / W, row0 = (size_t)ctx.rank() * Lr;
+    dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars + row0 * stride, stride, Lr, R, blinds ? d_bl.p + row0 : nullptr, key.h, ctx.scratch.p, ctx.stream);
+    dev::compress_batch(comp.p, rows.p, Lr, ctx.stream);
+    const uint8_t* all = ctx.allgather_block(comp.p, 32 * Lr);
+    dev::d2h(out.data(), all, 32 * L, ctx.stream);
+  } else {
+    dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars, stride, L, R, blinds ? d_bl.p : nullptr, key.h, ctx.scratch.p, ctx.stream);
+    dev::compress_batch(comp.p, rows.p, L, ctx.stream);
+    dev::d2h(out.data(), comp.p, 32 * L, ctx.stream);
+  }
   ctx.sync();
   return out.empty() ? Cp() : out[0];
 }
@@ -612,7 +687,12 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
   size_t num_rounds_x = 0, num_rounds_y = 0;
   while (((size_t)1 << num_rounds_x) < num_cons) num_rounds_x++;
   while (((size_t)1 << num_rounds_y) < zlen) num_rounds_y++;
-  DevBuf<u256> d_tau(num_cons), d_Az(num_cons), d_Bz(num_cons), d_Cz(num_cons), d_chal(64), eq_small(2 * ((size_t)1 << ((std::max(num_rounds_x, num_rounds_y) + 1) / 2)) + 8);
+  const int W = ctx.shard_world(), rk = ctx.rank();
+  int logW = 0;
+  while ((1 << logW) < W) logW++;
+  const bool sh1 = ctx.shard_table(num_cons), sh2 = ctx.shard_table(zlen);   // sumcheck tables as cyclic shards (rank r holds the indices = r mod W)
+  const size_t n1 = sh1 ? num_cons / W : num_cons, n2 = sh2 ? zlen / W : zlen;
+  DevBuf<u256> d_tau(num_cons), d_Az(n1), d_Bz(n1), d_Cz(n1), d_chal(64), eq_small(2 * ((size_t)1 << ((std::max(num_rounds_x, num_rounds_y) + 1) / 2)) + 8);
   Fq blind_claim_postsc1;
   std::vector<Fq> claims1;
   {
@@ -625,13 +705,20 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
     dev::dzero(d_z.p + num_vars + tail.size(), (num_vars - tail.size()) * sizeof(u256), ctx.stream);
     std::vector<Fq> tau = T.challenge_vector("challenge_tau", num_rounds_x);
     dev::h2d(d_chal.p, tau.data(), tau.size() * sizeof(u256), ctx.stream);
-    dev::eq_evals(d_tau.p, d_chal.p, (int)num_rounds_x, eq_small.p, ctx.stream);
     // inst.multiply_vec (r1cs.rs:268-282)
     u256* outs[3] = {d_Az.p, d_Bz.p, d_Cz.p};
-    for (int m = 0; m < 3; m++) dev::spmv(outs[m], num_cons, inst.M[m].csr_ptr.p, inst.M[m].csr_idx.p, inst.M[m].csr_val.p, d_z.p, ctx.stream);
+    if (sh1) {
+      // this rank's slice of eq(tau, .): eq over the leading variables times the factor its low index bits fix; its rows of A z, B z, C z
+      dev::eq_evals(d_tau.p, d_chal.p, (int)num_rounds_x - logW, eq_small.p, ctx.stream);
+      dev::scale(d_tau.p, shard_eq_scale(tau, W, rk).m, n1, ctx.stream);
+      for (int m = 0; m < 3; m++) dev::spmv_cyclic(outs[m], n1, rk, W, inst.M[m].csr_ptr.p, inst.M[m].csr_idx.p, inst.M[m].csr_val.p, d_z.p, ctx.stream);
+    } else {
+      dev::eq_evals(d_tau.p, d_chal.p, (int)num_rounds_x, eq_small.p, ctx.stream);
+      for (int m = 0; m < 3; m++) dev::spmv(outs[m], num_cons, inst.M[m].csr_ptr.p, inst.M[m].csr_idx.p, inst.M[m].csr_val.p, d_z.p, ctx.stream);
+    }
     u256* tabs[4] = {d_tau.p, d_Az.p, d_Bz.p, d_Cz.p};
     zk_sumcheck_prove(ctx, dev::SC_CUBIC4, Fq::zero(), Fq::zero(), num_rounds_x, tabs, 4, gens.gens_1, gens.gens_4, T, tape, proof.sc_proof_phase1, rx, claims1,
-                      blind_claim_postsc1);
+                      blind_claim_postsc1, sh1);
   }
   const Fq tau_claim = claims1[0], Az_claim = claims1[1], Bz_claim = claims1[2], Cz_claim = claims1[3];
   Fq Az_blind = tape.random_scalar("Az_blind"), Bz_blind = tape.random_scalar("Bz_blind"), Cz_blind = tape.random_scalar("Cz_blind"),
@@ -659,14 +746,18 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
     // evals_rx = eq(rx, .), then the three transposed SpMVs of compute_eval_table_sparse (r1cs.rs:284-298), then r_A*A + r_B*B + r_C*C
     dev::h2d(d_chal.p, rx.data(), rx.size() * sizeof(u256), ctx.stream);
     dev::eq_evals(d_tau.p, d_chal.p, (int)num_rounds_x, eq_small.p, ctx.stream);
-    DevBuf<u256> eA(zlen), eB(zlen), eC(zlen), d_ABC(zlen);
+    DevBuf<u256> eA(n2), eB(n2), eC(n2), d_ABC(n2), d_zloc;
     u256* outs[3] = {eA.p, eB.p, eC.p};
-    for (int m = 0; m < 3; m++) dev::spmv(outs[m], zlen, inst.M[m].csc_ptr.p, inst.M[m].csc_idx.p, inst.M[m].csc_val.p, d_tau.p, ctx.stream);
+    for (int m = 0; m < 3; m++) {
+      if (sh2) dev::spmv_cyclic(outs[m], n2, rk, W, inst.M[m].csc_ptr.p, inst.M[m].csc_idx.p, inst.M[m].csc_val.p, d_tau.p, ctx.stream);   // this rank's columns
+      else dev::spmv(outs[m], zlen, inst.M[m].csc_ptr.p, inst.M[m].csc_idx.p, inst.M[m].csc_val.p, d_tau.p, ctx.stream);
+    }
     dev::h2d(d_chal.p + 32, rabc, 3 * sizeof(u256), ctx.stream);
-    dev::lincomb3(d_ABC.p, eA.p, eB.p, eC.p, d_chal.p + 32, zlen, ctx.stream);
-    u256* tabs[2] = {d_z.p, d_ABC.p};
+    dev::lincomb3(d_ABC.p, eA.p, eB.p, eC.p, d_chal.p + 32, n2, ctx.stream);
+    if (sh2) { d_zloc.alloc(n2); dev::take_cyclic(d_zloc.p, d_z.p, n2, rk, W, ctx.stream); }
+    u256* tabs[2] = {sh2 ? d_zloc.p : d_z.p, d_ABC.p};
     zk_sumcheck_prove(ctx, dev::SC_QUAD, claim_phase2, blind_claim_phase2, num_rounds_y, tabs, 2, gens.gens_1, gens.gens_3, T, tape, proof.sc_proof_phase2, ry, claims2,
-                      blind_claim_postsc2);
+                      blind_claim_postsc2, sh2);
   }
   {
     PhaseTimer t(ctx, "polyeval");
@@ -692,6 +783,7 @@ void nizk_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
   if (inst.digest.empty())
     throw SpError(SP_ERR_INVALID_ARG, "NIZK::prove: the instance has no R1CSShapeDigest (sp_instance_set_digest); the transcript would not bind the R1CS shape (lib.rs:514)");
   ctx.timings.clear();
+  ShardScope shard(ctx);
   PhaseTimer t(ctx, "NIZK::prove");
   RandomTape tape("proof", tape_seed);                                   // lib.rs:511
   T.append_protocol_name("Spartan NIZK proof");                          // lib.rs:513

@@ -110,27 +110,60 @@ struct DenseView {
   }
 };
 
-// ProductCircuit (product_tree.rs:11-63): every layer kept, layer k (size n/2^k, left half | right half) at offset 2n - 2n/2^k
+// ProductCircuit (product_tree.rs:11-63): every layer kept; layer k has n/2^k entries (left half | right half).
+// Single GPU: one 2n-scalar buffer, layer k at offset 2n - 2n/2^k.  Sharded over W ranks (cyclic partition: entry i of a layer on rank i mod W):
+// the big layers [0, Ks) hold only this rank's n/(2^k W) entries (`loc`, same offset rule on the local sizes) — the Hadamard product that builds
+// layer k+1 pairs i with i + len/2, which stay on one rank — and the layers from Ks on are replicated in `rep` (a circuit over n/2^Ks inputs).
 struct ProdCircuit {
-  DevBuf<u256> buf;
-  size_t n = 0, num_layers = 0;
-  void alloc(size_t n_) { n = n_; num_layers = log2_ceil(n_); buf.alloc(2 * n_); }
-  u256* layer(size_t k) { return buf.p + (2 * n - 2 * (n >> k)); }
-  size_t layer_len(size_t k) const { return n >> k; }
-  void build(Ctx& ctx) {  // layer 0 already written
-    for (size_t k = 0; k + 1 < num_layers; k++) {
-      size_t h = layer_len(k) / 2;
-      dev::hadamard(layer(k + 1), layer(k), layer(k) + h, h, ctx.stream);  // compute_layer (product_tree.rs:18-34)
-    }
+  DevBuf<u256> loc, rep;
+  size_t n = 0, num_layers = 0, Ks = 0;
+  int W = 1;
+  void alloc(Ctx& ctx, size_t n_) {
+    n = n_; num_layers = log2_ceil(n_); W = ctx.shard_world(); Ks = 0;
+    // layer k's sumcheck runs on tables of n/2^(k+1) entries: shard it while those are worth sharding
+    while (Ks + 1 < num_layers && ctx.shard_table((n >> Ks) / 2)) Ks++;
+    if (Ks) loc.alloc(2 * (n / W));
+    rep.alloc(2 * (n >> Ks));
+  }
+  bool sharded(size_t k) const { return k < Ks; }
+  size_t layer_len(size_t k) const { return n >> k; }                                  // global entries
+  size_t local_len(size_t k) const { return k < Ks ? (n >> k) / W : n >> k; }          // entries this rank holds
+  u256* layer(size_t k) {
+    if (k < Ks) { const size_t nl = n / W; return loc.p + (2 * nl - 2 * (nl >> k)); }
+    const size_t nr = n >> Ks, kk = k - Ks;
+    return rep.p + (2 * nr - 2 * (nr >> kk));
   }
 };
+// every layer of a group of equally sized circuits: one launch per layer (compute_layer, product_tree.rs:18-34); at the boundary between the
+// sharded and the replicated layers the local products are all-gathered into every rank's copy
+static void build_circuits(Ctx& ctx, std::vector<ProdCircuit*> cs) {
+  ProdCircuit& c0 = *cs[0];
+  for (size_t k = 0; k + 1 < c0.num_layers; k++) {
+    const size_t h = c0.local_len(k) / 2;
+    std::vector<u256*> outs; std::vector<const u256*> as, bs;
+    if (k + 1 == c0.Ks) {
+      DevBuf<u256> tmp(cs.size() * h);
+      for (size_t i = 0; i < cs.size(); i++) { outs.push_back(tmp.p + i * h); as.push_back(cs[i]->layer(k)); bs.push_back(cs[i]->layer(k) + h); }
+      dev::hadamard_many(outs.data(), as.data(), bs.data(), (int)cs.size(), h, ctx.stream);
+      std::vector<const u256*> src(outs.begin(), outs.end());
+      u256* g = ctx.allgather_cyclic(src.data(), (int)cs.size(), h);
+      const size_t glen = h * (size_t)c0.W;
+      for (size_t i = 0; i < cs.size(); i++) dev::d2d(cs[i]->layer(k + 1), g + i * glen, glen * sizeof(u256), ctx.stream);
+      ctx.sync();   // tmp is released here
+      continue;
+    }
+    for (auto* c : cs) { outs.push_back(c->layer(k + 1)); as.push_back(c->layer(k)); bs.push_back(c->layer(k) + h); }
+    dev::hadamard_many(outs.data(), as.data(), bs.data(), (int)cs.size(), h, ctx.stream);
+  }
+}
 
 static Fq circuit_evaluate(Ctx& ctx, ProdCircuit& c) {  // ProductCircuit::evaluate (product_tree.rs:58-63)
   std::vector<Fq> v = ctx.download(c.layer(c.num_layers - 1), 2);
   return v[0] * v[1];
 }
 
-struct DotpCircuit { u256 *left, *right, *weight; size_t len; };
+// DotProductCircuit (product_tree.rs:66-108) of `len` entries; the tables the sumcheck binds are this rank's cyclic shards when `sharded`
+struct DotpCircuit { u256 *left, *right, *weight; size_t len; bool sharded; Fq claim; };
 
 // ProductCircuitEvalProofBatched::prove (product_tree.rs:259-383) with SumcheckInstanceProof::prove_cubic_batched (sumcheck.rs:254-424) inlined
 static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vector<DotpCircuit>& dotps, Transcript& T, ProductCircuitEvalProofBatched& out,
@@ -143,7 +176,10 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     ctx.sync();
     for (size_t i = 0; i < np; i++) { Fq v[2]; memcpy(v, ctx.pinned + 64 * i, 64); claims_to_verify[i] = v[0] * v[1]; }
   }
-  const size_t max_half = prods[0]->n / 2;
+  const int W = prods[0]->W, rk = ctx.rank();
+  const size_t Ks = prods[0]->Ks;
+  // the shared eq table and its two ping-pong halves: local sizes while a layer is sharded, full sizes for the replicated layers
+  const size_t max_half = std::max(prods[0]->local_len(0) / 2, Ks < num_layers ? prods[0]->local_len(Ks) / 2 : 1);
   DevBuf<u256> cpar_a(std::max<size_t>(max_half / 2, 1)), cpar_b(std::max<size_t>(max_half / 2, 1)), d_rand(64), eq_small(2 * ((size_t)1 << ((num_layers + 1) / 2)) + 8);
   DevBuf<u256> cpar0(std::max<size_t>(max_half, 1));
   std::vector<Fq> rand;
@@ -151,30 +187,35 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
   DevBuf<u256> d_heads(64);
   for (size_t layer_id = num_layers; layer_id-- > 0;) {
     const size_t len = prods[0]->layer_len(layer_id);  // left + right
-    const size_t half = len / 2;                       // table length of this layer's sumcheck
+    const size_t half = len / 2;                       // table length of this layer's sumcheck (global)
     const size_t num_rounds = log2_ceil(half);
+    bool sh = prods[0]->sharded(layer_id);             // this layer's tables are cyclic shards: the first rounds run sharded
+    const size_t lhalf = sh ? half / W : half;         // ... of this many entries per rank
     // poly_C_par = eq(rand)                                                  (product_tree.rs:279-280)
     if (!rand.empty()) dev::h2d(d_rand.p, rand.data(), rand.size() * sizeof(u256), ctx.stream);
-    dev::eq_evals(cpar0.p, d_rand.p, (int)rand.size(), eq_small.p, ctx.stream);
+    if (sh) {
+      int logW = 0;
+      while ((1 << logW) < W) logW++;
+      dev::eq_evals(cpar0.p, d_rand.p, (int)rand.size() - logW, eq_small.p, ctx.stream);
+      dev::scale(cpar0.p, shard_eq_scale(rand, W, rk).m, lhalf, ctx.stream);
+    } else dev::eq_evals(cpar0.p, d_rand.p, (int)rand.size(), eq_small.p, ctx.stream);
     std::vector<dev::ScInst> insts;
     for (size_t i = 0; i < np; i++) {
       dev::ScInst in;
-      in.t[0] = prods[i]->layer(layer_id); in.t[1] = prods[i]->layer(layer_id) + half; in.t[2] = cpar0.p; in.t[3] = nullptr;
+      in.t[0] = prods[i]->layer(layer_id); in.t[1] = prods[i]->layer(layer_id) + lhalf; in.t[2] = cpar0.p; in.t[3] = nullptr;
       in.c_out = cpar_a.p; in.write_c = i == 0;
       insts.push_back(in);
     }
     const bool with_dotp = layer_id == 0 && nd > 0;
     if (with_dotp) {
       for (size_t i = 0; i < nd; i++) {
-        dev::dot3(ctx.small.p + 128 + i, dotps[i].left, dotps[i].right, dotps[i].weight, dotps[i].len, ctx.red.p, ctx.stream);  // DotProductCircuit::evaluate
+        if (dotps[i].sharded != sh) throw SpError(SP_ERR_INTERNAL, "dot-product circuits and product circuits disagree on sharding");
         dev::ScInst in;
         in.t[0] = dotps[i].left; in.t[1] = dotps[i].right; in.t[2] = dotps[i].weight; in.t[3] = nullptr;
         in.c_out = dotps[i].weight; in.write_c = 1;
         insts.push_back(in);
+        claims_to_verify.push_back(dotps[i].claim);   // DotProductCircuit::evaluate, taken on the unsharded tables by the caller
       }
-      std::vector<Fq> dv(nd);
-      ctx.get_small(128, dv.data(), nd);
-      for (auto& v : dv) claims_to_verify.push_back(v);
     }
     const size_t ninst = insts.size();
     std::vector<Fq> coeff_vec = T.challenge_vector("rand_coeffs_next_layer", claims_to_verify.size());
@@ -184,9 +225,9 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     LayerProofBatched lp;
     std::vector<Fq> rand_prod;
     Fq e = claim;
-    size_t cur = half;
+    size_t cur = lhalf;                                // current length of the tables this rank holds
     dev::HostSig sig;
-    if (num_rounds > 0) { sig = ctx.next_sig(); dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream, sig); }
+    if (num_rounds > 0) { sig = ctx.next_sig(); dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream, sig, sh ? ctx.comm->next_xr() : dev::XRank()); }
     u256* cin = cpar0.p;
     u256* cpp[2] = {cpar_a.p, cpar_b.p};
     int flip = 0;
@@ -205,7 +246,31 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
       rand_prod.push_back(r_j);
       // bind every table (shared C written once, through a ping-pong buffer)
       for (size_t i = 0; i < np; i++) { insts[i].t[2] = cin; insts[i].c_out = cpp[flip]; }
-      if (j + 1 < num_rounds) { sig = ctx.next_sig(); dev::sc_fold_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, r_j.m, d_out, ctx.red.p, ctx.stream, sig); }
+      if (j + 1 < num_rounds && sh && cur < Ctx::SHARD_MIN_LOCAL) {
+        // leave the sharded stage: bind locally, all-gather every table into replicated copies (in the window), evaluate the next round there
+        std::vector<u256*> tabs;
+        for (size_t i = 0; i < ninst; i++) { tabs.push_back(insts[i].t[0]); tabs.push_back(insts[i].t[1]); if (i >= np) tabs.push_back(insts[i].t[2]); }
+        tabs.push_back(cin);
+        dev::fold_top(tabs.data(), (int)tabs.size(), cur, r_j.m, ctx.stream);
+        const size_t glen = (cur / 2) * (size_t)W;
+        std::vector<const u256*> src(tabs.begin(), tabs.end());
+        u256* g = ctx.allgather_cyclic(src.data(), (int)src.size(), cur / 2);
+        size_t k = 0;
+        for (size_t i = 0; i < ninst; i++) {
+          insts[i].t[0] = g + (k++) * glen; insts[i].t[1] = g + (k++) * glen;
+          if (i >= np) { insts[i].t[2] = g + (k++) * glen; insts[i].c_out = insts[i].t[2]; }
+        }
+        cin = g + k * glen;
+        for (size_t i = 0; i < np; i++) insts[i].t[2] = cin;
+        sh = false;
+        cur = glen;
+        sig = ctx.next_sig();
+        dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream, sig);
+        e = poly.evaluate(r_j);
+        lp.proof.compressed_polys.push_back(poly.compress());
+        continue;
+      }
+      if (j + 1 < num_rounds) { sig = ctx.next_sig(); dev::sc_fold_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, r_j.m, d_out, ctx.red.p, ctx.stream, sig, sh ? ctx.comm->next_xr() : dev::XRank()); }
       else {
         std::vector<u256*> tabs;
         for (size_t i = 0; i < ninst; i++) { tabs.push_back(insts[i].t[0]); tabs.push_back(insts[i].t[1]); if (i >= np) tabs.push_back(insts[i].t[2]); }
@@ -272,6 +337,7 @@ static std::vector<Fq> bound_bot_all(std::vector<Fq> v, const std::vector<Fq>& c
 void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const u256* d_vars, const std::vector<Fq>& input, const SnarkGens& gens,
                  Transcript& T, const Fq& tape_seed, Writer& w) {
   ctx.timings.clear();
+  ShardScope shard(ctx);   // on a connected multi-GPU context every rank runs this same function on the same inputs (see DESIGN.md "Multi-GPU")
   auto t_start = std::chrono::steady_clock::now();
   auto mark = [&](const char* name, std::chrono::steady_clock::time_point t0) {
     ctx.timings.push_back({name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()});
@@ -347,34 +413,29 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   auto tb = std::chrono::steady_clock::now();
   dev::h2d(d_chal.p, r_mem_check.data(), 2 * sizeof(u256), ctx.stream);
   struct Side { ProdCircuit init, audit, read[3], write[3]; } S[2];
+  const int W = ctx.shard_world(), rk = ctx.rank();
+  auto hash_into = [&](ProdCircuit& c, size_t n, const u256* addr, const u256* val, const u256* ts, int plus_one) {
+    c.alloc(ctx, n);
+    if (c.sharded(0)) dev::spark_hash_cyclic(c.layer(0), n / W, rk, W, addr, val, ts, plus_one, d_chal.p, ctx.stream);   // this rank's entries of the hash layer
+    else dev::spark_hash(c.layer(0), n, addr, val, ts, plus_one, d_chal.p, ctx.stream);
+  };
   for (int side = 0; side < 2; side++) {
     Side& s = S[side];
     const u256* mem = side == 0 ? mem_rx.p : mem_ry.p;
-    s.init.alloc(cells); s.audit.alloc(cells);
-    dev::spark_hash(s.init.layer(0), cells, nullptr, mem, nullptr, 0, d_chal.p, ctx.stream);
-    dev::spark_hash(s.audit.layer(0), cells, nullptr, mem, side == 0 ? dv.row_audit : dv.col_audit, 0, d_chal.p, ctx.stream);
+    hash_into(s.init, cells, nullptr, mem, nullptr, 0);
+    hash_into(s.audit, cells, nullptr, mem, side == 0 ? dv.row_audit : dv.col_audit, 0);
     for (int m = 0; m < 3; m++) {
-      s.read[m].alloc(N); s.write[m].alloc(N);
       const u256* addr = side == 0 ? dv.row_addr[m] : dv.col_addr[m];
       const u256* ts = side == 0 ? dv.row_ts[m] : dv.col_ts[m];
       const u256* val = side == 0 ? row_val[m] : col_val[m];
-      dev::spark_hash(s.read[m].layer(0), N, addr, val, ts, 0, d_chal.p, ctx.stream);
-      dev::spark_hash(s.write[m].layer(0), N, addr, val, ts, 1, d_chal.p, ctx.stream);
+      hash_into(s.read[m], N, addr, val, ts, 0);
+      hash_into(s.write[m], N, addr, val, ts, 1);
     }
   }
-  {  // every layer of the 4 memory-sized and the 12 ops-sized product trees: one launch per layer (product_tree.rs:36-56)
-    auto build_group = [&](std::vector<ProdCircuit*> cs) {
-      for (size_t k = 0; k + 1 < cs[0]->num_layers; k++) {
-        size_t h = cs[0]->layer_len(k) / 2;
-        std::vector<u256*> outs; std::vector<const u256*> as, bs;
-        for (auto* c : cs) { outs.push_back(c->layer(k + 1)); as.push_back(c->layer(k)); bs.push_back(c->layer(k) + h); }
-        dev::hadamard_many(outs.data(), as.data(), bs.data(), (int)cs.size(), h, ctx.stream);
-      }
-    };
-    build_group({&S[0].init, &S[0].audit, &S[1].init, &S[1].audit});
-    build_group({&S[0].read[0], &S[0].read[1], &S[0].read[2], &S[0].write[0], &S[0].write[1], &S[0].write[2],
-                 &S[1].read[0], &S[1].read[1], &S[1].read[2], &S[1].write[0], &S[1].write[1], &S[1].write[2]});
-  }
+  // every layer of the 4 memory-sized and the 12 ops-sized product trees: one launch per layer (product_tree.rs:36-56)
+  build_circuits(ctx, {&S[0].init, &S[0].audit, &S[1].init, &S[1].audit});
+  build_circuits(ctx, {&S[0].read[0], &S[0].read[1], &S[0].read[2], &S[0].write[0], &S[0].write[1], &S[0].write[2],
+                       &S[1].read[0], &S[1].read[1], &S[1].read[2], &S[1].write[0], &S[1].write[1], &S[1].write[2]});
   ctx.sync();
   mark("build_layered_network", tb);
 
@@ -398,25 +459,30 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
     if (side == 0) { pl.row_init = init; pl.row_read = read; pl.row_write = write; pl.row_audit = audit; }
     else { pl.col_init = init; pl.col_read = read; pl.col_write = write; pl.col_audit = audit; }
   }
-  // dot-product circuits: clones of (row_ops_val, col_ops_val, val), split in halves (sparse_mlpoly.rs:1090-1117)
-  DevBuf<u256> dotp_buf(9 * N);
+  // dot-product circuits: clones of (row_ops_val, col_ops_val, val), split in halves (sparse_mlpoly.rs:1090-1117).  Their claims are taken on the
+  // full tables; the copies the sumcheck binds are this rank's cyclic shards when the ops circuits are sharded.
+  const bool sh_dotp = S[0].read[0].sharded(0);
+  const size_t hN = N / 2, hloc = sh_dotp ? hN / W : hN;
+  DevBuf<u256> dotp_buf(18 * hloc);
   std::vector<DotpCircuit> dotps;
   for (int m = 0; m < 3; m++) {
-    u256* l = dotp_buf.p + (size_t)(3 * m) * N; u256* r = l + N; u256* wgt = r + N;
-    dev::d2d(l, row_val[m], N * sizeof(u256), ctx.stream);
-    dev::d2d(r, col_val[m], N * sizeof(u256), ctx.stream);
-    dev::d2d(wgt, dv.val[m], N * sizeof(u256), ctx.stream);
-    size_t h = N / 2;
-    dev::dot3(ctx.small.p + 48, l, r, wgt, h, ctx.red.p, ctx.stream);
-    dev::dot3(ctx.small.p + 49, l + h, r + h, wgt + h, h, ctx.red.p, ctx.stream);
+    const u256* srcs[3] = {row_val[m], col_val[m], dv.val[m]};
+    dev::dot3(ctx.small.p + 48, srcs[0], srcs[1], srcs[2], hN, ctx.red.p, ctx.stream);
+    dev::dot3(ctx.small.p + 49, srcs[0] + hN, srcs[1] + hN, srcs[2] + hN, hN, ctx.red.p, ctx.stream);
     Fq lr2[2];
     ctx.get_small(48, lr2, 2);
     T.append_scalar("claim_eval_dotp_left", lr2[0]);
     T.append_scalar("claim_eval_dotp_right", lr2[1]);
     if (!(lr2[0] + lr2[1] == inst_evals[m])) throw SpError(SP_ERR_INTERNAL, "dot-product circuit does not evaluate to the claimed matrix evaluation");
     pl.eval_dotp_left.push_back(lr2[0]); pl.eval_dotp_right.push_back(lr2[1]);
-    dotps.push_back(DotpCircuit{l, r, wgt, h});
-    dotps.push_back(DotpCircuit{l + h, r + h, wgt + h, h});
+    for (int part = 0; part < 2; part++) {
+      u256* base = dotp_buf.p + (size_t)(6 * m + 3 * part) * hloc;
+      for (int t = 0; t < 3; t++) {
+        if (sh_dotp) dev::take_cyclic(base + t * hloc, srcs[t] + part * hN, hloc, rk, W, ctx.stream);
+        else dev::d2d(base + t * hloc, srcs[t] + part * hN, hN * sizeof(u256), ctx.stream);
+      }
+      dotps.push_back(DotpCircuit{base, base + hloc, base + 2 * hloc, hloc, sh_dotp, lr2[part]});
+    }
   }
   std::vector<Fq> rand_ops, rand_mem;
   {

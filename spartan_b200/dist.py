@@ -26,6 +26,27 @@ def init(backend=None):
     return rank, world, local
 
 
+def allgather_bytes(b):
+    """every rank contributes the same number of bytes; returns the list in rank order (CUDA tensors under NCCL, CPU tensors under gloo)"""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [bytes(b)]
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor(list(b), dtype=torch.uint8, device=dev)
+    out = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().tolist()) for t in out]
+
+
+def connect(ctx):
+    """make `ctx` (this rank's spartan_b200.Context) one rank of a sharded prover over all ranks of the process group"""
+    rank, world, _ = env()
+    if world > 1:
+        ctx.connect_peers(rank, world, allgather_bytes)
+    return ctx
+
+
 def rank_seed(rank, base_seed=0):
     """instance / tape seed of the proof a rank produces"""
     return base_seed + rank
