@@ -9,6 +9,10 @@ value    : inputs (the assignment) resident in HBM when the clock starts;   e2e:
            inside the timed region, proof bytes copied back to the host
 N > 1    : one process per GPU (torchrun); every rank proves its own instance of the same size (independent proofs: no data-path
            collective), value = N * constraints / max-over-ranks time          -> "scaling": "weak"
+           The same line carries `strong`: ONE proof sharded over the N GPUs (tables / commitment rows / product circuits partitioned,
+           per-round partial sums exchanged over NVLink inside the kernels; spartan_b200/csrc/comm.cu), its latency and that its bytes equal
+           the single-GPU proof's; and BASELINE.json configs[2]/[3] at N GPUs: `msm_var_2p24` (2^24-point MSM, point-add all-reduce) and
+           `dense_sumcheck_2p22` (per-round fold GB/s of a 2^22-entry cubic sumcheck, scalar-add all-reduce).
 --impl reference : the CPU restatement of the reference (oracle/, C loops under OpenMP on all host cores) on a bounded sample of the
            same workload (SNARK::prove at 2^SAMPLE_LOG constraints); rank 0 only.
 """
@@ -159,28 +163,68 @@ def cpu_baseline_leg():
             "sample": "one SNARK::prove at 2^%d = the GPU arm's configuration (oracle = CPU restatement of the reference, OpenMP over its C loops; %.1f s)" % (CPU_SAMPLE_LOG, dt)}
 
 
-def msm_var_leg(sb, api, ctx, logn=24):
+def msm_var_leg(sb, api, sd, ctx, rank, world, logn=24):
     """BASELINE.json configs[2]: standalone variable-base MSM, N = 2^24 ristretto255 points (MultiCommitGens::new(N, b"msm-bench").G, no
-    precomputed tables), uniformly random scalars below q; bucket method of spartan_b200/csrc/kernels_pip.cu through sp_msm_var_resident."""
+    precomputed tables), uniformly random scalars below q; bucket method of spartan_b200/csrc/kernels_pip.cu.  On W > 1 GPUs the vector is
+    split by index range, every rank runs the bucket MSM on its slice and the partial sums meet in a point-add all-reduce (sp_msm_var_sharded)."""
     import numpy as np
+    import torch
     n = 1 << logn
     P = api.Points.derive(n, b"msm-bench", ctx=ctx)
     rng = np.random.default_rng(0)
     t = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64)
     t[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)          # < 2^252 < q: valid Montgomery residues, i.e. uniformly random field elements
-    S = sb.DensePolynomial(t, ctx=ctx)
+    per = n // world
+    S = sb.DensePolynomial(t[rank * per:(rank + 1) * per], ctx=ctx)
     del t
-    out = P.msm(S)
+    run = (lambda: P.msm_sharded(S, offset=rank * per)) if world > 1 else (lambda: P.msm(S))
+    out = run()
     ts = []
     for _ in range(3):
+        sd.barrier(); torch.cuda.synchronize()
         api.timer_start(ctx)
-        out2 = P.msm(S)
+        out2 = run()
         ts.append(api.timer_stop_ms(ctx))
-    assert out == out2
-    ms = min(ts)
-    return {"points": n, "ms": ms, "Mpoint_adds_per_s_reference_equivalent": 33.0 * n / (ms / 1e3) / 1e6, "Mpoints_per_s": n / (ms / 1e3) / 1e6,
-            "what": "sp_msm_var_resident: 2^%d caller-supplied points, 253-bit scalars, scalars and points resident in HBM; 33 adds/point = dalek Pippenger w=8 (SURVEY.md 8d)" % logn,
+        assert out == out2
+    ms = sd.max_over_ranks([min(ts)])[0]
+    return {"points": n, "n_gpus": world, "ms": ms, "Mpoint_adds_per_s_reference_equivalent": 33.0 * n / (ms / 1e3) / 1e6, "Mpoints_per_s": n / (ms / 1e3) / 1e6,
+            "what": "2^%d caller-supplied points, 253-bit scalars, scalars and points resident in HBM, %s; 33 adds/point = dalek Pippenger w=8 (SURVEY.md 8d)"
+                    % (logn, "split by index range over %d GPUs + point-add all-reduce over NVLink (sp_msm_var_sharded)" % world if world > 1 else "sp_msm_var_resident"),
             "result_prefix": out.hex()[:16]}
+
+
+def dense_sumcheck_leg(sb, api, sd, ctx, rank, world, pk, logn=22, rounds=5):
+    """BASELINE.json configs[3]: cubic-with-additive-term sumcheck (A*(B*C-D), sumcheck.rs:625-652 + dense_mlpoly.rs:215-223) on four 2^22-entry
+    tables, rounds timed one by one: round 0 is the plain evaluation (32 B x len per table), rounds 1.. the fused bind + evaluate (48 B x len per
+    table, len = the table length before the bind).  On W > 1 GPUs every rank holds the cyclic shard of each table and the kernels exchange
+    their partial sums over NVLink (sp_sumcheck_*_sharded); GB/s is whole-job algorithmic bytes / max-over-ranks time."""
+    import numpy as np
+    import torch
+    n = 1 << logn
+    rng = np.random.default_rng(1)
+    polys = []
+    for _ in range(4):
+        t = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64)
+        t[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+        polys.append(sb.DensePolynomial(t[rank::world] if world > 1 else t, ctx=ctx))
+        del t
+    r = sb.prg_scalars("r", rounds + 1)
+    ev = (lambda: api.sumcheck_eval_sharded(2, polys)) if world > 1 else (lambda: api.sumcheck_eval(2, polys))
+    fe = (lambda rr: api.sumcheck_fold_eval_sharded(2, polys, rr)) if world > 1 else (lambda rr: api.sumcheck_fold_eval(2, polys, rr))
+    ev()
+    out = []
+    length = n
+    for j in range(rounds + 1):
+        sd.barrier(); torch.cuda.synchronize()
+        api.timer_start(ctx)
+        e = ev() if j == 0 else fe(r[j])
+        ms = sd.max_over_ranks([api.timer_stop_ms(ctx)])[0]
+        by = 4 * (32.0 if j == 0 else 48.0) * length
+        out.append({"round": j, "table_len": length, "us": ms * 1e3, "GBs": by / 1e9 / (ms / 1e3), "frac_of_hbm": by / 1e9 / (ms / 1e3) / (pk["hbm_gbs"] * world)})
+        if j > 0:
+            length //= 2
+    return {"tables": 4, "log_len": logn, "n_gpus": world, "rounds": out, "evals_prefix": bytes(e.tobytes()[:8]).hex(),
+            "note": "time = kernel + the device->host copy of the three evaluations (and, sharded, the NVLink exchange of 96 B per rank inside the kernel); frac_of_hbm against N x the measured copy bandwidth"}
 
 
 def run_b200(args):
@@ -191,6 +235,9 @@ def run_b200(args):
     import spartan_b200 as sb
     from spartan_b200 import api
     ctx = sb.Context(local if world > 1 else 0)
+    if world > 1:
+        sd.connect(ctx)            # IPC windows over NVLink; sharded proving is switched on only for the `strong` leg below
+        ctx.set_sharding(False)
     n = 1 << LOG_N
     # every rank proves its own instance (seed = rank): independent proofs, no data-path collective
     inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, seed=sd.rank_seed(rank), ctx=ctx)
@@ -241,9 +288,9 @@ def run_b200(args):
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
-        api.timer_start(ctx)
+        w0 = time.perf_counter()                    # host wall-clock around the public call: the call is synchronous (it returns the proof bytes)
         proof = step_e2e()
-        per_step_e2e.append(api.timer_stop_ms(ctx))
+        per_step_e2e.append((time.perf_counter() - w0) * 1e3)
     barrier()
     h1, d1 = api.io_bytes()
     t_e2e = sum(per_step_e2e) / 1e3
@@ -274,9 +321,15 @@ def run_b200(args):
             roof["note"] = ("algorithmic bytes = 48 B x len per table per launch (read len*32, write len/2*32); CUDA-event time per launch on the prover stream; "
                             "ncu --set full of the same kernel: profiles/r01_ncu_full_sc_fold_eval.txt")
         if roof:
-            # ncu --set full of the first (largest single-instance) launch of this kernel in the step: profiles/r01_ncu_full_sc_fold_eval.txt
-            roof["traffic"] = 167.7e6
-            roof["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of the captured first ZK-sumcheck launch of the step (4 tables of 2^20: algorithmic 201.3e6 B; part of the tables is still L2-resident from the SpMV that produced them)"
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's first launch of a step, from the committed ncu capture (written by
+            # tools/ncu_summary.py full ... --json); null when no capture of the current build is committed
+            try:
+                with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+                    tr = json.load(f)["sc_fold_eval"]
+                roof["traffic"] = tr["dram_bytes"]
+                roof["traffic_note"] = "%s; algorithmic bytes of that launch %.4g" % (tr["what"], tr["algorithmic_bytes"])
+            except Exception:
+                roof["traffic"] = None
         roof_msm = rl(dom[0], dom[1], "hbm")
         roof_msm["note"] = ("dominant kernel by time; fixed-base ristretto255 comb, INTEGER-ALU bound (20 table lookups x 7 field multiplications per term): its "
                             "algorithmic bytes are only scalars + bases, so the HBM fraction is honestly tiny")
@@ -290,16 +343,55 @@ def run_b200(args):
             msm_rate = {"terms": terms, "ms": m["largest_ms"], "Mpoint_adds_per_s_reference_equivalent": 33.0 * terms / (m["largest_ms"] / 1e3) / 1e6,
                         "Mpoint_adds_per_s_executed": 20.0 * terms / (m["largest_ms"] / 1e3) / 1e6, "Mterms_per_s": terms / (m["largest_ms"] / 1e3) / 1e6,
                         "what": "largest msm_rows launch of the step: commit_nondet_witness, 2048 rows x 4096 generators (sparse_mlpoly.rs:64-67)"}
+    # ---- strong scaling: ONE proof (rank 0's instance: seed 0) sharded over all N GPUs
+    strong = None
+    if world > 1 and not args.no_strong:
+        import hashlib
+        if rank == 0:
+            inst0, inputs0, comm0, dv0 = inst, inputs, comm, d_vars
+        else:
+            inst0, vars0, inputs0 = sb.Instance.produce_synthetic_r1cs(n, n, NUM_INPUTS, seed=0, ctx=ctx)
+            comm0 = sb.SNARK.encode(inst0, gens)
+            dv0 = sb.DensePolynomial(vars0.limbs, ctx=ctx)
+        seed0 = sb.tape_seed(0)
+        single = sb.SNARK.prove(inst0, comm0, dv0, inputs0, gens, b"example", seed0)          # every rank alone: the reference bytes
+        ctx.set_sharding(True)
+        for _ in range(max(args.warmup, 3)):
+            sharded = sb.SNARK.prove(inst0, comm0, dv0, inputs0, gens, b"example", seed0)
+        barrier()
+        ts = []
+        for _ in range(args.steps):
+            flush.zero_()
+            barrier()
+            api.timer_start(ctx)
+            sharded = sb.SNARK.prove(inst0, comm0, dv0, inputs0, gens, b"example", seed0)
+            ts.append(api.timer_stop_ms(ctx))
+        barrier()
+        phases = {k: round(v, 3) for k, v in ctx.timings().items() if not k.startswith("fine:")}
+        ctx.set_sharding(False)
+        t_strong = sd.max_over_ranks([sum(ts) / 1e3])[0]
+        same = sd.max_over_ranks([0.0 if sharded.bytes == single.bytes else 1.0])[0] == 0.0
+        strong = {"what": "ONE SNARK::prove of the same configuration sharded over %d GPUs (intra-proof: cyclic table shards, row-sharded commitments, "
+                          "partial sums exchanged over NVLink inside the reduction kernels); latency, not throughput" % world,
+                  "scaling": "strong", "ms_per_proof": t_strong / args.steps * 1e3, "constraints_per_s": n * args.steps / t_strong,
+                  "speedup_vs_one_gpu_same_run": (t_res / args.steps) / (t_strong / args.steps),
+                  "proof_bytes_identical_to_single_gpu_on_every_rank": same, "proof_sha256": hashlib.sha256(sharded.bytes).hexdigest(), "phases_ms": phases,
+                  "limiter": "the ~490 transcript-serialised rounds (latency-bound, replicated on every rank) and the replicated inner-product arguments; only the "
+                             "streaming rounds, the commitments and the product-circuit layers shard"}
+    # ---- BASELINE.json configs[2] and configs[3] at N GPUs (all ranks take part)
+    msm_var, dense_sc = None, None
+    if not args.no_msm_var:
+        if world > 1:
+            ctx.set_sharding(True)
+        try:
+            dense_sc = dense_sumcheck_leg(sb, api, sd, ctx, rank, world, peaks()[0])
+            msm_var = msm_var_leg(sb, api, sd, ctx, rank, world)
+        except Exception as ex:   # extras, never the headline: report instead of failing the bench line
+            msm_var = {"error": str(ex)}
     if rank != 0:
         sd.finalize()
         return
     cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
-    msm_var = None
-    if world == 1 and not args.no_msm_var:
-        try:
-            msm_var = msm_var_leg(sb, api, ctx)
-        except Exception as ex:   # an extra, never the headline: report instead of failing the bench line
-            msm_var = {"error": str(ex)}
     out = {
         "metric": METRIC, "value": sd.aggregate_throughput(n * args.steps, world, t_res), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -309,10 +401,10 @@ def run_b200(args):
                    "timed_region": "Transcript::new + SNARK::prove (benches/snark.rs:55-68); gens / instance / encode excluded", "timer": "CUDA events on the prover stream, max over ranks"},
         "clocks": clocks,
         "e2e": {"value": sd.aggregate_throughput(n * args.steps, world, t_e2e), "unit": UNIT, "ms_per_step": t_e2e / args.steps * 1e3, "h2d_bytes_per_step": (h1 - h0) // args.steps,
-                "d2h_bytes_per_step": (d1 - d0) // args.steps, "api": "spartan_b200.SNARK.prove -> sp_snark_prove (C ABI), assignment in pinned host memory"},
+                "d2h_bytes_per_step": (d1 - d0) // args.steps, "api": "spartan_b200.SNARK.prove -> sp_snark_prove (C ABI), assignment in pinned host memory", "timer": "host wall-clock (perf_counter) around the synchronous call, max over ranks"},
         "gpu_launches": launches,
         "proof_bytes": len(proof.bytes),
-        "roofline": roof, "roofline_dominant_kernel": roof_msm, "msm": msm_rate, "msm_var_2p24": msm_var, "kernels_ms_per_step": kernels,
+        "roofline": roof, "roofline_dominant_kernel": roof_msm, "msm": msm_rate, "msm_var_2p24": msm_var, "dense_sumcheck_2p22": dense_sc, "strong": strong, "kernels_ms_per_step": kernels,
         "phases_ms": {k: round(v, 3) for k, v in ctx.timings().items()},
         "cpu_baseline": cpu,
         "reference_published": {"value": 2 ** 20 / 39.1297568, "unit": UNIT, "what": "README.md:375 SNARK::prove 2^20 on one core of an i7-1065G7 (other hardware)"},
@@ -329,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-msm-var", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

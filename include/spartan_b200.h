@@ -94,6 +94,10 @@ int sp_fold_top(sp_ctx* ctx, sp_poly* const* polys, int k, const uint64_t r_mont
 int sp_sumcheck_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, uint64_t out[3][4]);
 /* fused: bind the top variable of every table to r, then evaluate the next round on the folded tables */
 int sp_sumcheck_fold_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, const uint64_t r_mont[4], uint64_t out[3][4]);
+/* the same two calls on a connected context, on CYCLIC SHARDS (rank r holds entries r, r+W, ...): partial sums are exchanged over NVLink inside
+ * the kernel ("scalar-add all-reduce"), every rank gets the evaluations of the whole tables; shards of >= 8192 entries for fold_eval */
+int sp_sumcheck_eval_sharded(sp_ctx* ctx, int kind, sp_poly* const* polys, uint64_t out[3][4]);
+int sp_sumcheck_fold_eval_sharded(sp_ctx* ctx, int kind, sp_poly* const* polys, const uint64_t r[4], uint64_t out[3][4]);
 /* SumcheckInstanceProof::prove_cubic_batched evaluation loops (sumcheck.rs:290-357): ninst instances of comb = A*B*C (product_tree.rs:283-286).
  * out = ninst x [e0, e2, e3] Montgomery limbs.  The same sp_poly may be passed as C of several instances (poly_C_par); A and B must be distinct. */
 int sp_sumcheck_batched_eval(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly* const* B, sp_poly* const* C, uint64_t* out /* ninst*3*4 */);
@@ -132,6 +136,21 @@ int sp_points_export(sp_ctx* ctx, const sp_points* p, size_t offset, size_t n, u
 /* GroupElement::vartime_multiscalar_mul(scalars[0..n), points[offset..offset+n)).compress() */
 int sp_msm_var(sp_ctx* ctx, const sp_points* p, size_t offset, const uint64_t* scalars_mont, size_t n, uint8_t out32[32]);
 int sp_msm_var_resident(sp_ctx* ctx, const sp_points* p, size_t offset, const sp_poly* scalars, uint8_t out32[32]);
+/* every rank of a connected context passes its slice of the points and of the scalars; point-add all-reduce of the W partial sums; every rank
+ * returns the encoding of the whole sum (group.rs:98-117 on a vector split by index range) */
+int sp_msm_var_sharded(sp_ctx* ctx, const sp_points* p, size_t offset, const sp_poly* scalars, uint8_t out32[32]);
+
+/* ---- inner-product argument, operator level: BulletReductionProof::prove (src/nizk/bullet.rs:32-132) for a host that keeps the transcript and
+ * the orchestration.  sp_ipa_begin copies a_vec / b_vec; the generator vector G is `gens` (G[0..n)).  Each round: sp_ipa_round_LR returns the
+ * compressed L, R of bullet.rs:83-97 (c_L, c_R are formed inside; Q and H are the caller's points), the host appends them and derives u
+ * (bullet.rs:99-103), sp_ipa_fold applies bullet.rs:105-108.  After lg n rounds sp_ipa_finish returns a[0], b[0] and G[0] (bullet.rs:113-122). */
+typedef struct sp_ipa sp_ipa;
+int sp_ipa_begin(sp_ctx* ctx, const sp_gens* gens, const sp_poly* a_vec, const sp_poly* b_vec, sp_ipa** out);
+void sp_ipa_free(sp_ipa* h);
+int sp_ipa_round_LR(sp_ctx* ctx, sp_ipa* h, const uint8_t Q32[32], const uint8_t H32[32], const uint64_t blind_L_mont[4], const uint64_t blind_R_mont[4],
+                    uint8_t L32[32], uint8_t R32[32]);
+int sp_ipa_fold(sp_ctx* ctx, sp_ipa* h, const uint64_t u_mont[4], const uint64_t u_inv_mont[4]);
+int sp_ipa_finish(sp_ctx* ctx, sp_ipa* h, uint64_t a_hat_mont[4], uint64_t b_hat_mont[4], uint8_t G_hat32[32]);
 
 /* ---- instances                                                                           lib.rs:111-274 */
 /* Instance::new: entries are (row, col, canonical 32-byte value); rows < num_cons, cols < num_vars + 1 + num_inputs */
@@ -193,6 +212,25 @@ int sp_nizk_verify(sp_ctx* ctx, const sp_instance* inst, const uint64_t* inputs_
  * (`comm`: a handle from sp_snark_encode or from sp_snark_commitment_load; only its commitment part is read) */
 int sp_snark_verify(sp_ctx* ctx, const sp_snark_encoding* comm, const uint64_t* inputs_mont, size_t ninputs, const sp_snark_gens* gens, const uint8_t* label,
                     size_t label_len, const uint8_t* proof, size_t proof_len);
+
+/* ---- the caller-owned transcript.  The reference's prove / verify take `transcript: &mut Transcript` (src/lib.rs:339-347, :423-429, :501-508,
+ * :549-555): the caller may have absorbed its own data before the call and may keep using the transcript afterwards.  The *_t entry points take
+ * merlin's whole STROBE-128 state instead of a label — SP_TRANSCRIPT_STATE_BYTES = 200 bytes of Keccak state, then pos, pos_begin, cur_flags
+ * (merlin::strobe::Strobe128) — and leave it exactly as the reference's call leaves the caller's transcript.  sp_*_prove / sp_*_verify with a
+ * label are the shorthand for a transcript the caller has just created with Transcript::new(label) and does not reuse (benches/snark.rs:56). */
+#define SP_TRANSCRIPT_STATE_BYTES 203
+int sp_nizk_prove_t(sp_ctx* ctx, const sp_instance* inst, const uint64_t* vars_mont, size_t nvars, const uint64_t* inputs_mont, size_t ninputs,
+                    const sp_nizk_gens* gens, uint8_t* strobe_state /* in, out */, const uint64_t tape_seed[4], uint8_t** proof, size_t* proof_len);
+int sp_snark_prove_t(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const uint64_t* vars_mont, size_t nvars, const uint64_t* inputs_mont,
+                     size_t ninputs, const sp_snark_gens* gens, uint8_t* strobe_state /* in, out */, const uint64_t tape_seed[4], uint8_t** proof, size_t* proof_len);
+int sp_nizk_verify_t(sp_ctx* ctx, const sp_instance* inst, const uint64_t* inputs_mont, size_t ninputs, const sp_nizk_gens* gens, uint8_t* strobe_state /* in, out */,
+                     const uint8_t* proof, size_t proof_len);
+int sp_snark_verify_t(sp_ctx* ctx, const sp_snark_encoding* comm, const uint64_t* inputs_mont, size_t ninputs, const sp_snark_gens* gens,
+                      uint8_t* strobe_state /* in, out */, const uint8_t* proof, size_t proof_len);
+/* merlin::Transcript::{new, append_message, challenge_bytes} on such a state buffer (transcript.rs:13-30), for hosts without merlin and for the tests */
+int sp_transcript_new(const uint8_t* label, size_t label_len, uint8_t* strobe_state /* out */);
+int sp_transcript_append_message(uint8_t* strobe_state, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t msg_len);
+int sp_transcript_challenge_bytes(uint8_t* strobe_state, const uint8_t* label, size_t label_len, uint8_t* out, size_t n);
 
 void sp_free(void* p);
 

@@ -7,5 +7,5 @@ without a GPU every entry point raises.
 """
 from .api import (  # noqa: F401
     Assignment, Context, DensePolynomial, InputsAssignment, Instance, MultiCommitGens, NIZK, NIZKGens, ProofVerifyError, R1CSError, SNARK, SNARKGens,
-    SpartanB200Error, VarsAssignment, default_context, kernel_launches, lib, scalar_from_bytes, scalar_to_bytes, tape_seed, prg_scalars,
+    SpartanB200Error, Transcript, VarsAssignment, default_context, kernel_launches, lib, random_tape_seed, scalar_from_bytes, scalar_to_bytes, tape_seed, prg_scalars,
 )

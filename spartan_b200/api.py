@@ -249,6 +249,21 @@ def sumcheck_fold_eval(kind, polys, r):
     return out
 
 
+def sumcheck_eval_sharded(kind, polys):
+    """sumcheck_eval on cyclic shards held by the ranks of a connected context: returns the evaluations of the whole tables on every rank"""
+    ctx = polys[0].ctx
+    out = np.zeros((3, 4), dtype=np.uint64)
+    ctx.check(lib.sp_sumcheck_eval_sharded(ctx.h, C.c_int(kind), (_vp * len(polys))(*[p.h for p in polys]), _p(out)))
+    return out
+
+
+def sumcheck_fold_eval_sharded(kind, polys, r):
+    ctx = polys[0].ctx
+    out = np.zeros((3, 4), dtype=np.uint64)
+    ctx.check(lib.sp_sumcheck_fold_eval_sharded(ctx.h, C.c_int(kind), (_vp * len(polys))(*[p.h for p in polys]), _p(np.ascontiguousarray(r, dtype=np.uint64)), _p(out)))
+    return out
+
+
 def _handles(polys):
     return (_vp * len(polys))(*[p.h for p in polys])
 
@@ -317,6 +332,39 @@ class MultiCommitGens:
             pass
 
 
+class BulletReduction:
+    """operator-level BulletReductionProof::prove (nizk/bullet.rs:32-132): the device keeps a, b and the (implicitly folded) generators, the
+    caller keeps the transcript.  round_LR() -> (L, R) compressed; fold(u, u_inv); finish() -> (a_hat, b_hat, G_hat compressed)."""
+
+    def __init__(self, gens, a_vec, b_vec):
+        self.ctx = gens.ctx
+        h = _vp()
+        self.ctx.check(lib.sp_ipa_begin(self.ctx.h, gens.h, a_vec.h, b_vec.h, C.byref(h)))
+        self.h = h
+
+    def round_LR(self, Q, H, blind_L, blind_R):
+        L, R = C.create_string_buffer(32), C.create_string_buffer(32)
+        self.ctx.check(lib.sp_ipa_round_LR(self.ctx.h, self.h, C.c_char_p(Q), C.c_char_p(H), _p(np.ascontiguousarray(blind_L, dtype=np.uint64)),
+                                           _p(np.ascontiguousarray(blind_R, dtype=np.uint64)), L, R))
+        return L.raw, R.raw
+
+    def fold(self, u, u_inv):
+        self.ctx.check(lib.sp_ipa_fold(self.ctx.h, self.h, _p(np.ascontiguousarray(u, dtype=np.uint64)), _p(np.ascontiguousarray(u_inv, dtype=np.uint64))))
+
+    def finish(self):
+        a, b, g = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64), C.create_string_buffer(32)
+        self.ctx.check(lib.sp_ipa_finish(self.ctx.h, self.h, _p(a), _p(b), g))
+        return a, b, g.raw
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib.sp_ipa_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class Points:
     """A caller-supplied `&[GroupElement]` (group.rs:8-9) resident on the device, for the variable-base MSM (bucket method, no tables)."""
 
@@ -356,6 +404,12 @@ class Points:
             self.ctx.check(lib.sp_msm_var(self.ctx.h, self.h, _sz(offset), _p(s), _sz(len(s)), out))
         return out.raw
 
+    def msm_sharded(self, scalars, offset=0):
+        """this rank's slice of a vector split by index range over the ranks of a connected context -> encoding of the whole sum (on every rank)"""
+        out = C.create_string_buffer(32)
+        self.ctx.check(lib.sp_msm_var_sharded(self.ctx.h, self.h, _sz(offset), scalars.h, out))
+        return out.raw
+
     def __del__(self):
         try:
             if getattr(self, "h", None):
@@ -379,6 +433,24 @@ def point_decompress_check(points, ctx=None):
     ok = (C.c_int * n)()
     ctx.check(lib.sp_point_decompress_check(ctx.h, C.c_char_p(b"".join(points)), _sz(n), ok))
     return [bool(x) for x in ok]
+
+
+class Transcript:
+    """merlin::Transcript as the caller-owned object the reference's prove / verify mutate (`transcript: &mut Transcript`, lib.rs:339-347):
+    the 203-byte STROBE-128 state, advanced in place by NIZK.prove / SNARK.prove / verify when passed instead of a label."""
+
+    def __init__(self, label):
+        self.state = C.create_string_buffer(203)
+        lib.sp_transcript_new(C.c_char_p(label), _sz(len(label)), self.state)
+
+    def append_message(self, label, msg):
+        msg = bytes(msg)
+        lib.sp_transcript_append_message(self.state, C.c_char_p(label), _sz(len(label)), C.c_char_p(msg), _sz(len(msg)))
+
+    def challenge_bytes(self, label, n):
+        out = C.create_string_buffer(n)
+        lib.sp_transcript_challenge_bytes(self.state, C.c_char_p(label), _sz(len(label)), out, _sz(n))
+        return out.raw
 
 
 # ----------------------------------------------------------------------------- public API of lib.rs
@@ -517,7 +589,11 @@ class NIZK:
         ctx = inst.ctx
         seed = random_tape_seed() if seed is None else np.ascontiguousarray(seed, dtype=np.uint64)
         out, n = C.POINTER(C.c_ubyte)(), _sz()
-        if isinstance(vars, DensePolynomial):
+        if isinstance(transcript_label, Transcript):   # the caller's `&mut Transcript`: advanced in place
+            v = vars.to_numpy() if isinstance(vars, DensePolynomial) else vars.limbs
+            ctx.check(lib.sp_nizk_prove_t(ctx.h, inst.h, _p(v), _sz(len(v)), _p(inputs.limbs), _sz(len(inputs)), gens.h, transcript_label.state, _p(seed),
+                                          C.byref(out), C.byref(n)))
+        elif isinstance(vars, DensePolynomial):
             ctx.check(lib.sp_nizk_prove_resident(ctx.h, inst.h, vars.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, C.c_char_p(transcript_label),
                                                  _sz(len(transcript_label)), _p(seed), C.byref(out), C.byref(n)))
         else:
@@ -528,6 +604,9 @@ class NIZK:
     def verify(self, inst, inputs, transcript_label, gens):
         """NIZK::verify(&self, &inst, &inputs, &mut Transcript::new(transcript_label), &gens): returns None, raises ProofVerifyError"""
         ctx = inst.ctx
+        if isinstance(transcript_label, Transcript):
+            ctx.check(lib.sp_nizk_verify_t(ctx.h, inst.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, transcript_label.state, C.c_char_p(bytes(self.bytes)), _sz(len(self.bytes))))
+            return
         ctx.check(lib.sp_nizk_verify(ctx.h, inst.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, C.c_char_p(transcript_label), _sz(len(transcript_label)),
                                      C.c_char_p(bytes(self.bytes)), _sz(len(self.bytes))))
 
@@ -602,7 +681,11 @@ class SNARK:
         ctx = inst.ctx
         seed = random_tape_seed() if seed is None else np.ascontiguousarray(seed, dtype=np.uint64)
         out, n = C.POINTER(C.c_ubyte)(), _sz()
-        if isinstance(vars, DensePolynomial):
+        if isinstance(transcript_label, Transcript):   # the caller's `&mut Transcript`: advanced in place
+            v = vars.to_numpy() if isinstance(vars, DensePolynomial) else vars.limbs
+            ctx.check(lib.sp_snark_prove_t(ctx.h, inst.h, comm.h, _p(v), _sz(len(v)), _p(inputs.limbs), _sz(len(inputs)), gens.h, transcript_label.state, _p(seed),
+                                           C.byref(out), C.byref(n)))
+        elif isinstance(vars, DensePolynomial):
             ctx.check(lib.sp_snark_prove_resident(ctx.h, inst.h, comm.h, vars.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, C.c_char_p(transcript_label),
                                                   _sz(len(transcript_label)), _p(seed), C.byref(out), C.byref(n)))
         else:
@@ -613,6 +696,9 @@ class SNARK:
     def verify(self, comm, inputs, transcript_label, gens):
         """SNARK::verify(&self, &comm, &inputs, &mut Transcript::new(transcript_label), &gens): returns None, raises ProofVerifyError"""
         ctx = comm.ctx
+        if isinstance(transcript_label, Transcript):
+            ctx.check(lib.sp_snark_verify_t(ctx.h, comm.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, transcript_label.state, C.c_char_p(bytes(self.bytes)), _sz(len(self.bytes))))
+            return
         ctx.check(lib.sp_snark_verify(ctx.h, comm.h, _p(inputs.limbs), _sz(len(inputs)), gens.h, C.c_char_p(transcript_label), _sz(len(transcript_label)),
                                       C.c_char_p(bytes(self.bytes)), _sz(len(self.bytes))))
 

@@ -192,6 +192,39 @@ int sp_sumcheck_fold_eval(sp_ctx* ctx, int kind, sp_poly* const* polys, const ui
   for (int i = 0; i < nt; i++) polys[i]->len /= 2;
   SP_CATCH(ctx)
 }
+// The same two calls on a connected context (sp_comm_connect), every rank passing its CYCLIC SHARDS of the tables (rank r holds the entries
+// r, r+W, r+2W, ...): the kernels exchange their partial sums over NVLink and every rank receives the evaluations of the whole tables.
+// Binding the top variable stays local as long as the local length is >= 2; shards must be of streaming size (>= 8192 entries) for fold_eval.
+static dev::HostSig xr_sig(Ctx& c) { dev::HostSig s; s.done = c.sig_done.p; return s; }
+int sp_sumcheck_eval_sharded(sp_ctx* ctx, int kind, sp_poly* const* polys, uint64_t out[3][4]) {
+  SP_TRY(ctx)
+  if (ctx->c.world() < 2) throw SpError(SP_ERR_INVALID_ARG, "not a connected multi-GPU context");
+  if (kind < 0 || kind > 2) throw SpError(SP_ERR_INVALID_ARG, "bad sumcheck kind");
+  int nt = kind_tables(kind);
+  check_same_len(polys, nt);
+  dev::ScInst in = make_inst(polys, nt);
+  dev::sc_eval((dev::ScKind)kind, &in, 1, polys[0]->len, ctx->c.small.p, ctx->c.red.p, ctx->c.stream, xr_sig(ctx->c), ctx->c.comm->next_xr());
+  Fq e[3];
+  ctx->c.get_small(0, e, 3);
+  memcpy(out, e, 96);
+  SP_CATCH(ctx)
+}
+int sp_sumcheck_fold_eval_sharded(sp_ctx* ctx, int kind, sp_poly* const* polys, const uint64_t r[4], uint64_t out[3][4]) {
+  SP_TRY(ctx)
+  if (ctx->c.world() < 2) throw SpError(SP_ERR_INVALID_ARG, "not a connected multi-GPU context");
+  if (kind < 0 || kind > 2) throw SpError(SP_ERR_INVALID_ARG, "bad sumcheck kind");
+  int nt = kind_tables(kind);
+  check_same_len(polys, nt);
+  if (polys[0]->len < Ctx::SHARD_MIN_LOCAL) throw SpError(SP_ERR_INVALID_ARG, "sharded fold_eval needs shards of at least 8192 entries (gather the shards and finish on one GPU)");
+  Fq rr = fq_in(r);
+  dev::ScInst in = make_inst(polys, nt);
+  dev::sc_fold_eval((dev::ScKind)kind, &in, 1, polys[0]->len, rr.m, ctx->c.small.p, ctx->c.red.p, ctx->c.stream, xr_sig(ctx->c), ctx->c.comm->next_xr());
+  Fq e[3];
+  ctx->c.get_small(0, e, 3);
+  memcpy(out, e, 96);
+  for (int i = 0; i < nt; i++) polys[i]->len /= 2;
+  SP_CATCH(ctx)
+}
 // prove_cubic_batched's evaluation loops (sumcheck.rs:290-357): ninst instances of A*B*C; an sp_poly may serve as C of several instances
 // (the shared eq table poly_C_par) — it is then bound once, through a temporary, and copied back
 static void batched_insts(sp_ctx* ctx, int ninst, sp_poly* const* A, sp_poly* const* B, sp_poly* const* Cc, std::vector<dev::ScInst>& insts,
@@ -380,6 +413,88 @@ int sp_point_roundtrip(sp_ctx* ctx, const uint8_t* in32, size_t n, uint8_t* out3
   SP_CATCH(ctx)
 }
 
+// ---- inner-product argument, operator level: BulletReductionProof::prove (nizk/bullet.rs:32-132) with the host keeping the transcript.
+// One handle per reduction: a_vec / b_vec (consumed), the generator set G (with its fixed-base tables) and the running scalars s of the
+// unfolded-G formulation (DESIGN.md "IPA without folding G").  Per round: sp_ipa_round_LR (bullet.rs:78-97) -> transcript -> sp_ipa_fold (:105-111).
+struct sp_ipa {
+  Ctx* ctx; const GenSet* gs; size_t n, cur;
+  DevBuf<u256> a, b, svec;
+  DevBuf<ge> pts;
+};
+static hge point_in(const uint8_t p32[32], const char* what) {
+  ge g;
+  if (!ristretto_decode(g, bytes_to_u256(p32))) throw SpError(SP_ERR_INVALID_POINT, std::string(what) + " is not a ristretto255 point");
+  return to_hge(g);
+}
+int sp_ipa_begin(sp_ctx* ctx, const sp_gens* gens, const sp_poly* a_vec, const sp_poly* b_vec, sp_ipa** out) {
+  SP_TRY(ctx)
+  const size_t n = a_vec->len;
+  if (n < 1 || (n & (n - 1)) || b_vec->len != n || n > gens->n) throw SpError(SP_ERR_INVALID_ARG, "ipa: |a| = |b| = a power of two, at most the generator count");
+  std::unique_ptr<sp_ipa> h(new sp_ipa);
+  h->ctx = &ctx->c; h->gs = gens->set.get(); h->n = n; h->cur = n;
+  h->a.alloc(n); h->b.alloc(n); h->svec.alloc(n); h->pts.alloc(2);
+  dev::d2d(h->a.p, a_vec->d.p, n * sizeof(u256), ctx->c.stream);
+  dev::d2d(h->b.p, b_vec->d.p, n * sizeof(u256), ctx->c.stream);
+  dev::fill_one(h->svec.p, n, ctx->c.stream);
+  ctx->c.ensure_scratch(dev::msm_scratch_bytes(4, n) + 64);
+  ctx->c.sync();
+  *out = h.release();
+  SP_CATCH(ctx)
+}
+void sp_ipa_free(sp_ipa* h) { delete h; }
+// L = <a_L, G_R> + c_L*Q + blind_L*H,  R = <a_R, G_L> + c_R*Q + blind_R*H  with c_L = <a_L, b_R>, c_R = <a_R, b_L>   (bullet.rs:74-97)
+int sp_ipa_round_LR(sp_ctx* ctx, sp_ipa* h, const uint8_t Q32[32], const uint8_t H32[32], const uint64_t blind_L[4], const uint64_t blind_R[4], uint8_t L32[32],
+                    uint8_t R32[32]) {
+  SP_TRY(ctx)
+  Ctx& c = ctx->c;
+  if (h->cur < 2) throw SpError(SP_ERR_INVALID_ARG, "ipa: the reduction is complete");
+  const size_t half = h->cur / 2;
+  const u256* da[2] = {h->a.p, h->a.p + half};
+  const u256* db[2] = {h->b.p + half, h->b.p};
+  dev::dot_pairs(c.small.p + 16, da, db, 2, half, c.red.p, c.stream);
+  dev::ipa_msm(h->pts.p, h->gs->table.p, h->gs->wbits, h->a.p, h->svec.p, h->cur, h->n, c.scratch.p, c.sig_done.p + 1, c.stream);
+  Fq cc[2];
+  c.get_small(16, cc, 2);
+  ge lr[2];
+  dev::d2h(lr, h->pts.p, 2 * sizeof(ge), c.stream);
+  c.sync();
+  const hge Q = point_in(Q32, "Q"), H = point_in(H32, "H");
+  const Fq bl[2] = {fq_in(blind_L), fq_in(blind_R)};
+  Cp outp[2];
+  hge full[2];
+  for (int k = 0; k < 2; k++) full[k] = hge_add(to_hge(lr[k]), hge_add(hge_scalarmul(cc[k].canonical(), Q), hge_scalarmul(bl[k].canonical(), H)));
+  compress2(full[0], full[1], outp[0], outp[1]);
+  memcpy(L32, outp[0].b, 32); memcpy(R32, outp[1].b, 32);
+  SP_CATCH(ctx)
+}
+// a_L <- a_L*u + u^-1*a_R,  b_L <- b_L*u^-1 + u*b_R,  G_L <- u^-1*G_L + u*G_R (kept implicit in s)      (bullet.rs:105-108)
+int sp_ipa_fold(sp_ctx* ctx, sp_ipa* h, const uint64_t u[4], const uint64_t u_inv[4]) {
+  SP_TRY(ctx)
+  if (h->cur < 2) throw SpError(SP_ERR_INVALID_ARG, "ipa: the reduction is complete");
+  const Fq uu = fq_in(u), ui = fq_in(u_inv);
+  if (!(uu * ui == Fq::one())) throw SpError(SP_ERR_INVALID_SCALAR, "ipa: u_inv is not the inverse of u");
+  const size_t half = h->cur / 2;
+  dev::ipa_fold_ab(h->a.p, h->b.p, half, uu.m, ui.m, ctx->c.stream);
+  dev::ipa_update_s(h->svec.p, half, h->n, uu.m, ui.m, ctx->c.stream);
+  h->cur = half;
+  ctx->c.sync();
+  SP_CATCH(ctx)
+}
+// a[0], b[0] and G[0] of the fully folded vectors (bullet.rs:113-122: the caller forms Gamma_hat from them)
+int sp_ipa_finish(sp_ctx* ctx, sp_ipa* h, uint64_t a_hat[4], uint64_t b_hat[4], uint8_t G_hat32[32]) {
+  SP_TRY(ctx)
+  Ctx& c = ctx->c;
+  if (h->cur != 1) throw SpError(SP_ERR_INVALID_ARG, "ipa: rounds remain");
+  dev::msm_rows(h->pts.p, h->gs->table.p, h->gs->wbits, h->svec.p, h->n, 1, h->n, nullptr, 0, c.scratch.p, c.stream);
+  DevBuf<uint8_t> comp(32);
+  dev::compress_batch(comp.p, h->pts.p, 1, c.stream);
+  dev::d2h(a_hat, h->a.p, 32, c.stream);
+  dev::d2h(b_hat, h->b.p, 32, c.stream);
+  dev::d2h(G_hat32, comp.p, 32, c.stream);
+  c.sync();
+  SP_CATCH(ctx)
+}
+
 // ---- variable-base MSM (kernels_pip.cu)
 static void points_from_ge(sp_ctx* ctx, sp_points* P, const ge* d_ge, size_t n) {
   P->ctx = &ctx->c; P->n = n;
@@ -461,6 +576,32 @@ static void msm_var_run(sp_ctx* ctx, const sp_points* p, size_t offset, const u2
   dev::compress_batch(comp.p, out.p, 1, ctx->c.stream);
   dev::d2h(out32, comp.p, 32, ctx->c.stream);
   ctx->c.sync();
+}
+// MSM split over the ranks of a connected context: every rank passes ITS slice of the points (offset, scalars->len) and of the scalars; the
+// partial sums meet in a point-add all-reduce (all-gather of the W extended points into every window, W-term sum) and every rank returns the
+// same encoding of sum over all ranks.
+int sp_msm_var_sharded(sp_ctx* ctx, const sp_points* p, size_t offset, const sp_poly* scalars, uint8_t out32[32]) {
+  SP_TRY(ctx)
+  Ctx& c = ctx->c;
+  if (c.world() < 2) throw SpError(SP_ERR_INVALID_ARG, "not a connected multi-GPU context");
+  const size_t n = scalars->len;
+  if (offset + n > p->n) throw SpError(SP_ERR_INVALID_ARG, "msm_var: range outside the point set");
+  DevBuf<ge> part(1), total(1);
+  DevBuf<uint8_t> comp(32);
+  if (n == 0) { ge id = ge_identity(); dev::h2d(part.p, &id, sizeof(ge), c.stream); }
+  else {
+    const char* cenv = getenv("SP_PIP_WINDOW");
+    dev::PipPlan plan = dev::pip_plan(n, cenv ? atoi(cenv) : 0);
+    const size_t need = dev::pip_scratch_bytes(plan);
+    if (need > p->scratch_bytes) { p->scratch.alloc(need); p->scratch_bytes = need; }
+    dev::msm_var(part.p, p->pts.p + offset, scalars->d.p, plan, p->scratch.p, c.stream);
+  }
+  const ge* all = reinterpret_cast<const ge*>(c.allgather_block(part.p, sizeof(ge)));
+  dev::sum_points(total.p, all, c.world(), c.stream);
+  dev::compress_batch(comp.p, total.p, 1, c.stream);
+  dev::d2h(out32, comp.p, 32, c.stream);
+  c.sync();
+  SP_CATCH(ctx)
 }
 int sp_msm_var(sp_ctx* ctx, const sp_points* p, size_t offset, const uint64_t* scalars, size_t n, uint8_t out32[32]) {
   SP_TRY(ctx)
@@ -632,15 +773,22 @@ int sp_nizk_gens_create(sp_ctx* ctx, size_t num_cons, size_t num_vars, size_t nu
 }
 void sp_nizk_gens_free(sp_nizk_gens* g) { delete g; }
 
+// the caller's transcript: either a fresh Transcript::new(label) (state == NULL) or the caller-owned STROBE state, updated in place
+struct TranscriptArg {
+  const uint8_t* label; size_t label_len; uint8_t* state;
+  Transcript open() const { return state ? Transcript(Transcript::FromState(), state) : Transcript(std::string((const char*)label, label_len)); }
+  void close(const Transcript& T) const { if (state) T.export_state(state); }
+};
 static int nizk_prove_common(sp_ctx* ctx, const sp_instance* inst, const u256* d_vars, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens,
-                             const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+                             const TranscriptArg& ta, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   SP_TRY(ctx)
   if (ninputs != inst->inst.num_inputs) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs");
   if (!seed) throw SpError(SP_ERR_INVALID_ARG, "tape seed is NULL: draw it from the OS RNG (random.rs:13-15); a fixed seed makes every blind public");
   require_reduced(inputs, ninputs, "inputs"); require_reduced(seed, 1, "tape seed");
-  Transcript T(std::string((const char*)label, label_len));
+  Transcript T = ta.open();
   NizkProof P;
   nizk_prove(ctx->c, inst->inst, d_vars, fq_vec(inputs, ninputs), *gens->g, T, fq_in(seed), P);
+  ta.close(T);
   Writer w;
   P.ser(w);
   *proof = dup_bytes(w.out); *proof_len = w.out.size();
@@ -652,12 +800,22 @@ int sp_nizk_prove(sp_ctx* ctx, const sp_instance* inst, const uint64_t* vars, si
   try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
   catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
   catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
-  return nizk_prove_common(ctx, inst, d_vars.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
+  return nizk_prove_common(ctx, inst, d_vars.p, inputs, ninputs, gens, TranscriptArg{label, label_len, nullptr}, seed, proof, proof_len);
+}
+// NIZK::prove(&inst, vars, &inputs, &gens, transcript: &mut Transcript) with the caller's transcript state in / out (lib.rs:501-508)
+int sp_nizk_prove_t(sp_ctx* ctx, const sp_instance* inst, const uint64_t* vars, size_t nvars, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens,
+                    uint8_t* strobe_state, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+  if (!strobe_state) { ctx->c.last_error = "transcript state is NULL"; return SP_ERR_INVALID_ARG; }
+  DevBuf<u256> d_vars;
+  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
+  catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
+  return nizk_prove_common(ctx, inst, d_vars.p, inputs, ninputs, gens, TranscriptArg{nullptr, 0, strobe_state}, seed, proof, proof_len);
 }
 int sp_nizk_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_poly* vars, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens,
                            const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   if (vars->len != inst->inst.num_vars) { ctx->c.last_error = "resident vars must already be padded to num_vars"; return SP_ERR_INVALID_INPUTS; }
-  return nizk_prove_common(ctx, inst, vars->d.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
+  return nizk_prove_common(ctx, inst, vars->d.p, inputs, ninputs, gens, TranscriptArg{label, label_len, nullptr}, seed, proof, proof_len);
 }
 
 // ---- SNARK
@@ -705,15 +863,16 @@ int sp_snark_commitment_load(sp_ctx* ctx, const uint8_t* bytes, size_t len, sp_s
   SP_CATCH(ctx)
 }
 static int snark_prove_common(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const u256* d_vars, const uint64_t* inputs, size_t ninputs,
-                              const sp_snark_gens* gens, const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+                              const sp_snark_gens* gens, const TranscriptArg& ta, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   SP_TRY(ctx)
   if (ninputs != inst->inst.num_inputs) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs");
   if (!enc->e->comb_ops.p) throw SpError(SP_ERR_INVALID_ARG, "this handle holds a commitment only (sp_snark_commitment_load): proving needs sp_snark_encode");
   if (!seed) throw SpError(SP_ERR_INVALID_ARG, "tape seed is NULL: draw it from the OS RNG (random.rs:13-15); a fixed seed makes every blind public");
   require_reduced(inputs, ninputs, "inputs"); require_reduced(seed, 1, "tape seed");
-  Transcript T(std::string((const char*)label, label_len));
+  Transcript T = ta.open();
   Writer w;
   snark_prove(ctx->c, inst->inst, *enc->e, d_vars, fq_vec(inputs, ninputs), *gens->g, T, fq_in(seed), w);
+  ta.close(T);
   *proof = dup_bytes(w.out); *proof_len = w.out.size();
   SP_CATCH(ctx)
 }
@@ -723,12 +882,22 @@ int sp_snark_prove(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding
   try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
   catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
   catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
-  return snark_prove_common(ctx, inst, enc, d_vars.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
+  return snark_prove_common(ctx, inst, enc, d_vars.p, inputs, ninputs, gens, TranscriptArg{label, label_len, nullptr}, seed, proof, proof_len);
+}
+// SNARK::prove(..., transcript: &mut Transcript) with the caller's transcript state in / out (lib.rs:339-347)
+int sp_snark_prove_t(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const uint64_t* vars, size_t nvars, const uint64_t* inputs, size_t ninputs,
+                     const sp_snark_gens* gens, uint8_t* strobe_state, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
+  if (!strobe_state) { ctx->c.last_error = "transcript state is NULL"; return SP_ERR_INVALID_ARG; }
+  DevBuf<u256> d_vars;
+  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
+  catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
+  return snark_prove_common(ctx, inst, enc, d_vars.p, inputs, ninputs, gens, TranscriptArg{nullptr, 0, strobe_state}, seed, proof, proof_len);
 }
 int sp_snark_prove_resident(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const sp_poly* vars, const uint64_t* inputs, size_t ninputs,
                             const sp_snark_gens* gens, const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   if (vars->len != inst->inst.num_vars) { ctx->c.last_error = "resident vars must already be padded to num_vars"; return SP_ERR_INVALID_INPUTS; }
-  return snark_prove_common(ctx, inst, enc, vars->d.p, inputs, ninputs, gens, label, label_len, seed, proof, proof_len);
+  return snark_prove_common(ctx, inst, enc, vars->d.p, inputs, ninputs, gens, TranscriptArg{label, label_len, nullptr}, seed, proof, proof_len);
 }
 
 // ---- verifiers
@@ -747,6 +916,50 @@ int sp_snark_verify(sp_ctx* ctx, const sp_snark_encoding* comm, const uint64_t* 
   Transcript T(std::string((const char*)label, label_len));
   snark_verify(ctx->c, *comm->e, fq_vec(inputs, ninputs), *gens->g, T, proof, proof_len);
   SP_CATCH(ctx)
+}
+
+// verify(..., transcript: &mut Transcript) on the caller's transcript state (lib.rs:423-429, :549-555); the state is updated in place either way
+int sp_nizk_verify_t(sp_ctx* ctx, const sp_instance* inst, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens, uint8_t* strobe_state,
+                     const uint8_t* proof, size_t proof_len) {
+  SP_TRY(ctx)
+  if (!strobe_state) throw SpError(SP_ERR_INVALID_ARG, "transcript state is NULL");
+  require_reduced(inputs, ninputs, "inputs");
+  Transcript T(Transcript::FromState(), strobe_state);
+  struct Out { Transcript& T; uint8_t* s; ~Out() { T.export_state(s); } } out{T, strobe_state};
+  nizk_verify(ctx->c, inst->inst, fq_vec(inputs, ninputs), *gens->g, T, proof, proof_len);
+  SP_CATCH(ctx)
+}
+int sp_snark_verify_t(sp_ctx* ctx, const sp_snark_encoding* comm, const uint64_t* inputs, size_t ninputs, const sp_snark_gens* gens, uint8_t* strobe_state,
+                      const uint8_t* proof, size_t proof_len) {
+  SP_TRY(ctx)
+  if (!strobe_state) throw SpError(SP_ERR_INVALID_ARG, "transcript state is NULL");
+  require_reduced(inputs, ninputs, "inputs");
+  Transcript T(Transcript::FromState(), strobe_state);
+  struct Out { Transcript& T; uint8_t* s; ~Out() { T.export_state(s); } } out{T, strobe_state};
+  snark_verify(ctx->c, *comm->e, fq_vec(inputs, ninputs), *gens->g, T, proof, proof_len);
+  SP_CATCH(ctx)
+}
+// merlin::Transcript for hosts without merlin (tests, C callers): the state buffer is the whole object
+int sp_transcript_new(const uint8_t* label, size_t label_len, uint8_t* strobe_state) {
+  Transcript T(std::string((const char*)label, label_len));
+  T.export_state(strobe_state);
+  return SP_OK;
+}
+int sp_transcript_append_message(uint8_t* strobe_state, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t msg_len) {
+  try {
+    Transcript T(Transcript::FromState(), strobe_state);
+    T.append_message(std::string((const char*)label, label_len).c_str(), msg, msg_len);
+    T.export_state(strobe_state);
+    return SP_OK;
+  } catch (...) { return SP_ERR_INVALID_ARG; }
+}
+int sp_transcript_challenge_bytes(uint8_t* strobe_state, const uint8_t* label, size_t label_len, uint8_t* out, size_t n) {
+  try {
+    Transcript T(Transcript::FromState(), strobe_state);
+    T.challenge_bytes(std::string((const char*)label, label_len).c_str(), out, n);
+    T.export_state(strobe_state);
+    return SP_OK;
+  } catch (...) { return SP_ERR_INVALID_ARG; }
 }
 
 void sp_free(void* p) { free(p); }

@@ -163,6 +163,7 @@ size_t msm_scratch_bytes(size_t L, size_t R);
 void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
               void* scratch, cudaStream_t s);
 
+void sum_points(ge* out, const ge* in, int n, cudaStream_t s);   // out[0] = in[0] + ... + in[n-1], n <= 32
 // both MSMs of an inner-product round (L, R -> out[0], out[1]) over unfolded generators: scalar of generator j is a[.]*svec[j].
 // scratch >= 2 * ceil(n_full/32) points; ticket: one zero-initialised word (self-resetting)
 void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,

@@ -121,10 +121,20 @@ class Transcript {  // merlin::Transcript + ProofTranscript (transcript.rs:5-37)
     memcpy(b, hdr, 6);
     memcpy(b + 6, "STROBEv1.0.2", 12);
     Keccak::f1600(st_);
-    pos_ = 0; pos_begin_ = 0;
+    pos_ = 0; pos_begin_ = 0; cur_flags_ = 0;
     meta_ad((const uint8_t*)"Merlin v1.0", 11, false);
     append_message("dom-sep", (const uint8_t*)label.data(), label.size());
   }
+  // The caller-owned `&mut Transcript` of the reference (lib.rs:339-347, :501-508) crosses the C ABI as merlin's whole STROBE-128 state:
+  // the 200-byte Keccak state followed by pos, pos_begin and cur_flags (merlin/src/strobe.rs `Strobe128 { state, pos, pos_begin, cur_flags }`).
+  static const size_t STATE_BYTES = 203;
+  struct FromState {};
+  Transcript(FromState, const uint8_t* in) {
+    memcpy(st_, in, 200);
+    pos_ = in[200]; pos_begin_ = in[201]; cur_flags_ = in[202];
+    if (pos_ >= R || pos_begin_ > R) throw std::runtime_error("spartan_b200: not a STROBE-128 transcript state (position out of range)");
+  }
+  void export_state(uint8_t* out) const { memcpy(out, st_, 200); out[200] = pos_; out[201] = pos_begin_; out[202] = cur_flags_; }
   void append_message(const char* label, const uint8_t* msg, size_t len) {
     uint8_t l4[4] = {(uint8_t)len, (uint8_t)(len >> 8), (uint8_t)(len >> 16), (uint8_t)(len >> 24)};
     meta_ad((const uint8_t*)label, strlen(label), false);
@@ -171,7 +181,7 @@ class Transcript {  // merlin::Transcript + ProofTranscript (transcript.rs:5-37)
  private:
   static const uint8_t R = 166, FLAG_I = 1, FLAG_A = 2, FLAG_C = 4, FLAG_M = 16, FLAG_K = 32;
   uint64_t st_[25];
-  uint8_t pos_, pos_begin_;
+  uint8_t pos_, pos_begin_, cur_flags_;
   uint8_t* bytes() { return reinterpret_cast<uint8_t*>(st_); }
   void run_f() {
     uint8_t* b = bytes();
@@ -193,6 +203,7 @@ class Transcript {  // merlin::Transcript + ProofTranscript (transcript.rs:5-37)
   }
   void begin_op(uint8_t flags, bool more) {
     if (more) return;
+    cur_flags_ = flags;
     uint8_t old_begin = pos_begin_;
     pos_begin_ = pos_ + 1;
     uint8_t hdr[2] = {old_begin, flags};

@@ -162,7 +162,7 @@ __device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* parti
       unsigned int last_inst = 0;
       if (lane == 0) {
         counters[blockIdx.y] = 0;
-        if (sig.flag) {
+        if (sig.done) {                                          // set whenever somebody waits for ALL instances: the host (flag) or the peers (xr)
           __threadfence_system();
           unsigned int done = atomicAdd(sig.done, 1u) + 1;       // instances (blockIdx.y) finish independently
           last_inst = done == gridDim.y;
@@ -172,7 +172,7 @@ __device__ __forceinline__ void block_reduce_finish(u256 (&acc)[NV], u256* parti
       last_inst = __shfl_sync(0xffffffffu, last_inst, 0);
       if (last_inst) {
         if (xr_on) { __threadfence(); xrank_exchange(xr, out, (int)(gridDim.y * out_stride), sig.host_out); }
-        if (lane == 0) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
+        if (lane == 0 && sig.flag) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
       }
     }
   }

@@ -627,6 +627,12 @@ __global__ void __launch_bounds__(32) k_msm_reduce_small(ge* out, const ge* __re
   for (int d = 16; d > 0; d >>= 1) if (d < 2 * chunks) acc = ge_add(acc, shfl_down_ge(acc, d));
   if (threadIdx.x == 0) st_ge(out + row, acc);
 }
+// out[0] = sum of n <= 32 points (the "point-add allreduce" of a sharded MSM, after the all-gather of the partial results)
+void sum_points(ge* out, const ge* in, int n, cudaStream_t s) {
+  if (n < 1 || n > 32) throw std::runtime_error("spartan_b200: sum_points supports 1..32 points");
+  k_msm_reduce_small<<<1, 32, 0, s>>>(out, in, n);
+  SP_LAUNCHED(); check("sum_points");
+}
 // ---- the two MSMs of one inner-product round in a single launch (bullet.rs:83-97 with unfolded generators, see k_ipa_lr):
 // every generator j carries exactly one non-zero scalar, a[.]*s[j], for L (j in the right half of its n_cur-block) or for R (left half).
 // grid = (chunks, 2 sides); the last block to finish sums the partial points of both sides and publishes L, R to the host.

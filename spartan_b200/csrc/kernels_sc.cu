@@ -287,7 +287,7 @@ void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out,
   SP_LAUNCHED(); check("sc_eval");
 }
 void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s, HostSig sig, const XRank& xr) {
-  if (xr.world > 1 && (len / 4 <= SC_SMALL_MAX || !sig.flag)) throw std::runtime_error("spartan_b200: a sharded sumcheck round needs a streaming-size table and a host signal");
+  if (xr.world > 1 && (len / 4 <= SC_SMALL_MAX || !sig.done)) throw std::runtime_error("spartan_b200: a sharded sumcheck round needs a streaming-size table and a completion counter");
   ProfScope ps("sc_fold_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 48.0, s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;

@@ -100,3 +100,21 @@ def test_two_rank_plumbing_under_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def test_transcript_state_helpers_match_merlin():
+    """sp_transcript_* (the 203-byte STROBE state that crosses the ABI in place of `&mut Transcript`) against the oracle's Merlin, including the
+    Merlin conformance vector and long messages that cross the 166-byte rate several times"""
+    import spartan_b200 as sb
+    from oracle.spartan_ref import core as oc
+    t = sb.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    rng = np.random.default_rng(5)
+    a, b = sb.Transcript(b"example"), oc.Transcript(b"example")
+    for n in [0, 1, 31, 32, 165, 166, 167, 400, 5000]:
+        msg = rng.bytes(n)
+        a.append_message(b"lbl", msg); b.append_message(b"lbl", msg)
+        assert a.challenge_bytes(b"c", 64) == b.challenge_bytes(b"c", 64)
+        assert a.challenge_bytes(b"long", 700) == b.challenge_bytes(b"long", 700)
+    assert len(a.state.raw) == 203 and a.state.raw[200] < 166

@@ -197,3 +197,34 @@ def test_sumcheck_batched(sb, logn):
         assert np.array_equal(p.to_numpy(), t)
     with pytest.raises(api.SpartanB200Error):
         api.sumcheck_batched_eval([dA[0], dA[0]], dB[:2], dC[:2])
+
+
+@pytest.mark.parametrize("n", [2, 32, 1024, 4096])
+def test_bullet_reduction_operator_level(sb, n):
+    """BulletReductionProof::prove (nizk/bullet.rs:32-132) driven from the host through sp_ipa_begin / sp_ipa_round_LR / sp_ipa_fold /
+    sp_ipa_finish with the oracle's transcript: every L, R, the final a, b and G[0] equal the oracle's.  n >= 512 runs the 13-bit-window
+    instance of k_ipa_msm (the generator set of the 2^20 proofs), n = 32 the 8-bit one."""
+    from spartan_b200 import api
+    from oracle.spartan_ref import protocol as pr
+    lg = n.bit_length() - 1
+    g = sb.MultiCommitGens(n, b"ipa-test")
+    ref = oc.MultiCommitGens.new(n, b"ipa-test")
+    a = oc.prg_scalars("ipa-a", n, n)
+    b = oc.prg_scalars("ipa-b", n, n + 1)
+    if n >= 32:
+        a[0] = 0; a[1] = oc.to_arr([1])[0]; b[3] = 0
+    blinds = [(int(x), int(y)) for x, y in zip(oc.to_ints(oc.prg_scalars("bl1", lg, n)), oc.to_ints(oc.prg_scalars("bl2", lg, n)))]
+    Qp = ref.g(0) * 12345
+    H = ref.h
+    To = oc.Transcript(b"ipa")
+    want, _, a_hat, b_hat, G_hat, _ = pr.BulletReductionProof.prove(To, Qp, ref.G, H, oc.to_ints(a), oc.to_ints(b), 7, blinds)
+    T = oc.Transcript(b"ipa")
+    red = api.BulletReduction(g, sb.DensePolynomial(a), sb.DensePolynomial(b))
+    for k in range(lg):
+        L, R = red.round_LR(Qp.compress(), H.compress(), oc.to_arr([blinds[k][0]])[0], oc.to_arr([blinds[k][1]])[0])
+        assert (L, R) == (want.L_vec[k], want.R_vec[k]), "round %d" % k
+        T.append_point(b"L", L); T.append_point(b"R", R)
+        u = T.challenge_scalar(b"u")
+        red.fold(oc.to_arr([u])[0], oc.to_arr([oc.inv(u)])[0])
+    ga, gb, gG = red.finish()
+    assert oc.to_ints(ga[None, :]) == [a_hat] and oc.to_ints(gb[None, :]) == [b_hat] and gG == G_hat.compress()

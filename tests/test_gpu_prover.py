@@ -180,3 +180,47 @@ def parse_nizk(b, rounds_x, rounds_y):
     rx, ry = vec(sc), vec(sc)
     assert pos[0] == len(b) and len(rx) == rounds_x and len(ry) == rounds_y
     return r1cs.NIZK(pr.R1CSProof(comm_vars, sc1, claims, (pok, prod), eq1, sc2, comm_at_ry, pe, eq2), (rx, ry))
+
+
+def test_nizk_caller_owned_transcript(sb):
+    """NIZK::prove / verify on a transcript the caller already absorbed data into (lib.rs:501-508, :549-555): bytes and final transcript state
+    equal to the oracle's"""
+    n, seed = 1024, 2
+    oi, ovars, oinputs = r1cs.Instance.produce_synthetic_r1cs(n, n, 10, seed)
+    ogens = r1cs.NIZKGens(n, n, 10)
+    ot = oc.Transcript(b"application")
+    ot.append_message(b"ctx", b"pre-absorbed")
+    want = r1cs.NIZK.prove(oi, ovars, oinputs, ogens, ot, r1cs.tape_seed(seed)).ser()
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(n, n, 10, seed=seed)
+    inst.set_digest(oi.digest)
+    gens = sb.NIZKGens(n, n, 10)
+    t = sb.Transcript(b"application")
+    t.append_message(b"ctx", b"pre-absorbed")
+    proof = sb.NIZK.prove(inst, vars_, inputs, gens, t, sb.tape_seed(seed))
+    assert proof.bytes == want
+    assert t.challenge_bytes(b"next", 48) == ot.challenge_bytes(b"next", 48)
+    tv = sb.Transcript(b"application")
+    tv.append_message(b"ctx", b"pre-absorbed")
+    proof.verify(inst, inputs, tv, gens)
+    with pytest.raises(sb.ProofVerifyError):
+        proof.verify(inst, inputs, sb.Transcript(b"application"), gens)
+
+
+def test_nizk_requires_a_digest_and_a_seed(sb):
+    """an instance without R1CSShapeDigest must not be proven (the transcript would not bind the shape), and the C entry point rejects a NULL seed"""
+    import ctypes as C
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(16, 16, 3, seed=0)
+    gens = sb.NIZKGens(16, 16, 3)
+    inst.set_digest(b"")
+    with pytest.raises(sb.SpartanB200Error):
+        sb.NIZK.prove(inst, vars_, inputs, gens, b"example", sb.tape_seed(0))
+    inst.set_digest(b"some digest")
+    out, n = C.POINTER(C.c_ubyte)(), C.c_size_t()
+    rc = sb.lib.sp_nizk_prove(inst.ctx.h, inst.h, vars_.limbs.ctypes.data_as(C.c_void_p), C.c_size_t(16), inputs.limbs.ctypes.data_as(C.c_void_p), C.c_size_t(3), gens.h,
+                              C.c_char_p(b"example"), C.c_size_t(7), None, C.byref(out), C.byref(n))
+    assert rc == 3   # SP_ERR_INVALID_ARG
+    # the default seed is fresh OS randomness: two proofs of the same statement differ, both verify
+    p1 = sb.NIZK.prove(inst, vars_, inputs, gens, b"example")
+    p2 = sb.NIZK.prove(inst, vars_, inputs, gens, b"example")
+    assert p1.bytes != p2.bytes
+    p1.verify(inst, inputs, b"example", gens); p2.verify(inst, inputs, b"example", gens)

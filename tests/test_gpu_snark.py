@@ -137,3 +137,39 @@ def test_snark_large_accepted_by_oracle_verifier(sb, logn):
             tampered.verify(ocomm, oc.to_ints(inputs.limbs), oc.Transcript(b"snark_example"), ogens)
     except (AssertionError, ValueError):
         pass
+
+
+def test_snark_caller_owned_transcript(sb):
+    """`transcript: &mut Transcript` semantics (lib.rs:339-347, :423-429): the caller absorbs its own data first, passes the transcript, and keeps
+    using it afterwards.  Proof bytes equal the oracle's, and the transcript is left in the state the oracle's is left in (same next challenge)."""
+    n, seed = 256, 3
+    oi, ovars, oinputs = r1cs.Instance.produce_synthetic_r1cs(n, n, 10, seed)
+    ogens = spark.SNARKGens(n, n, 10, n)
+    ocomm, odecomm = spark.SNARK.encode(oi, ogens)
+    ot = oc.Transcript(b"application")
+    ot.append_message(b"context", b"data the caller absorbed before proving")
+    want = spark.SNARK.prove(oi, ocomm, odecomm, ovars, oinputs, ogens, ot, r1cs.tape_seed(seed)).ser()
+    after = ot.challenge_bytes(b"after-prove", 32)
+    inst, vars_, inputs = sb.Instance.produce_synthetic_r1cs(n, n, 10, seed=seed)
+    gens = sb.SNARKGens(n, n, 10, n)
+    comm = sb.SNARK.encode(inst, gens)
+    t = sb.Transcript(b"application")
+    t.append_message(b"context", b"data the caller absorbed before proving")
+    proof = sb.SNARK.prove(inst, comm, vars_, inputs, gens, t, sb.tape_seed(seed))
+    assert proof.bytes == want
+    assert t.challenge_bytes(b"after-prove", 32) == after
+    tv = sb.Transcript(b"application")
+    tv.append_message(b"context", b"data the caller absorbed before proving")
+    proof.verify(comm, inputs, tv, gens)
+    ov = oc.Transcript(b"application")
+    ov.append_message(b"context", b"data the caller absorbed before proving")
+    parsed, _ = pr.deser(spark.SNARK, proof.bytes)
+    parsed.verify(ocomm, oinputs, ov, ogens)
+    assert tv.challenge_bytes(b"after-verify", 32) == ov.challenge_bytes(b"after-verify", 32)
+    bad = sb.Transcript(b"application")
+    bad.append_message(b"context", b"different caller data")
+    with pytest.raises(sb.ProofVerifyError):
+        proof.verify(comm, inputs, bad, gens)
+    # a label is shorthand for a fresh transcript
+    assert sb.SNARK.prove(inst, comm, vars_, inputs, gens, sb.Transcript(b"snark_example"), sb.tape_seed(seed)).bytes == \
+        sb.SNARK.prove(inst, comm, vars_, inputs, gens, b"snark_example", sb.tape_seed(seed)).bytes

@@ -15,3 +15,24 @@ def test_oracle_reproduces_golden():
     got = json.loads(json.dumps(mg.build()))
     assert got == want
     assert want["nizk"][-1]["proof"]["len"] == 9408          # bincode(NIZK) at 2^10
+
+
+def test_snark_golden_fixtures_are_the_oracles():
+    """tests/golden/snark_proof_sha256.json (made by tests/golden/make_snark_golden.py): the stored proofs hash to the stored digests, have the
+    reference's published length structure at 2^20 (133,720-byte evaluation proof inside, README.md:374), and the 2^16 digest is reproduced by
+    running the oracle now"""
+    import hashlib, json, os
+    from oracle.spartan_ref import core as oc, r1cs, spark, protocol as pr
+    root = os.path.dirname(os.path.abspath(__file__))
+    fx = json.load(open(os.path.join(root, "golden", "snark_proof_sha256.json")))
+    for logn in (20, 22):
+        b = open(os.path.join(root, "golden", "snark_2p%d_proof.bin" % logn), "rb").read()
+        assert hashlib.sha256(b).hexdigest() == fx[str(logn)] and len(b) == fx["%d_len" % logn]
+    p20, pos = pr.deser(spark.SNARK, open(os.path.join(root, "golden", "snark_2p20_proof.bin"), "rb").read())
+    assert len(pr.ser(p20.r1cs_sat_proof)) == 47024 and len(pr.ser(p20.r1cs_eval_proof)) == 133720
+    n = 1 << 16
+    inst, v, i = r1cs.Instance.produce_synthetic_r1cs(n, n, 10, 0)
+    gens = spark.SNARKGens(n, n, 10, n)
+    comm, decomm = spark.SNARK.encode(inst, gens)
+    proof = spark.SNARK.prove(inst, comm, decomm, v.copy(), i, gens, oc.Transcript(b"example"), r1cs.tape_seed(0)).ser()
+    assert hashlib.sha256(proof).hexdigest() == fx["16"] and hashlib.sha256(comm.ser()).hexdigest() == fx["16_commitment"]
