@@ -163,9 +163,11 @@ int sp_instance_synthetic(sp_ctx* ctx, size_t num_cons, size_t num_vars, size_t 
                           uint64_t* inputs_out);
 void sp_instance_free(sp_instance* inst);
 int sp_instance_dims(const sp_instance* inst, size_t* num_cons, size_t* num_vars, size_t* num_inputs);
-/* the digest absorbed by NIZK::prove (lib.rs:514) is zlib(bincode(shape)) from flate2/miniz_oxide — not reproducible byte for byte with
- * another deflate implementation, so it is an opaque caller-supplied input */
+/* R1CSShape::get_digest (r1cs.rs:154-158): NIZK::prove / verify absorb zlib(bincode(shape)) (lib.rs:514).  The reference compresses with flate2's
+ * miniz_oxide backend at level 6; this library computes the same stream with its own restatement of miniz's compressor (csrc/deflate.cpp, bit-identical
+ * to C miniz level 6) on first use.  A caller that wants its own compressor's bytes absorbed instead passes them with sp_instance_set_digest. */
 int sp_instance_set_digest(sp_instance* inst, const uint8_t* digest, size_t len);
+int sp_instance_digest(const sp_instance* inst, uint8_t** out, size_t* len);   /* free with sp_free */
 /* bincode(R1CSShape) — the bytes the reference deflates to obtain the digest (r1cs.rs:154-158) */
 int sp_instance_bincode(const sp_instance* inst, uint8_t** out, size_t* len);
 /* COO export in the reference's entry order: matrix 0/1/2 = A/B/C; vals are Montgomery limbs */

@@ -485,8 +485,7 @@ class Instance:
         nc, nv, ni = _sz(), _sz(), _sz()
         lib.sp_instance_dims(h, C.byref(nc), C.byref(nv), C.byref(ni))
         self.num_cons, self.num_vars, self.num_inputs = nc.value, nv.value, ni.value
-        self.digest = None
-        self.set_digest(zlib.compress(self.bincode(), 6))  # r1cs.rs:154-158 (opaque: see DESIGN.md)
+        self._digest = None
 
     @staticmethod
     def new(num_cons, num_vars, num_inputs, A, B, Cm, ctx=None):
@@ -521,9 +520,19 @@ class Instance:
         lib.sp_free(out)
         return b
 
+    @property
+    def digest(self):
+        """R1CSShape::get_digest (r1cs.rs:154-158): the caller-supplied bytes, else the library's miniz-level-6 zlib stream of bincode(shape)"""
+        if self._digest is None:
+            out, n = C.POINTER(C.c_ubyte)(), _sz()
+            lib.sp_instance_digest(self.h, C.byref(out), C.byref(n))
+            self._digest = _take_bytes(out, n)
+        return self._digest
+
     def set_digest(self, digest):
-        self.digest = bytes(digest)
-        lib.sp_instance_set_digest(self.h, C.c_char_p(self.digest), _sz(len(self.digest)))
+        """absorb these bytes instead (e.g. the digest another compressor produced); b"" returns to the library's own"""
+        self._digest = bytes(digest) if digest else None
+        lib.sp_instance_set_digest(self.h, C.c_char_p(bytes(digest)), _sz(len(digest)))
 
     def export(self, matrix):
         n = _sz()

@@ -16,8 +16,8 @@ NVCC = os.environ.get("SP_NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU = ["kernels.cu", "kernels_sc.cu", "kernels_pip.cu", "comm.cu"]
-CPP = ["prover.cpp", "snark.cpp", "verifier.cpp", "capi.cpp"]
-HDR = ["field.cuh", "mul_ptx.cuh", "curve.cuh", "kcommon.cuh", "dev.hpp", "host.hpp", "engine.hpp", "prover.hpp", "snark.hpp", os.path.join("..", "..", "include", "spartan_b200.h")]
+CPP = ["prover.cpp", "snark.cpp", "verifier.cpp", "capi.cpp", "deflate.cpp"]
+HDR = ["field.cuh", "mul_ptx.cuh", "curve.cuh", "kcommon.cuh", "dev.hpp", "host.hpp", "host_fe51.hpp", "engine.hpp", "prover.hpp", "snark.hpp", os.path.join("..", "..", "include", "spartan_b200.h")]
 
 
 def _stale(target, deps):

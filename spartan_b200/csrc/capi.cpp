@@ -707,19 +707,18 @@ int sp_instance_dims(const sp_instance* inst, size_t* nc, size_t* nv, size_t* ni
 }
 int sp_instance_set_digest(sp_instance* inst, const uint8_t* digest, size_t len) { inst->inst.digest.assign(digest, digest + len); return SP_OK; }
 int sp_instance_bincode(const sp_instance* inst, uint8_t** out, size_t* len) {
-  // bincode(R1CSShape{num_cons,num_vars,num_inputs,A,B,C}), SparseMatPolynomial{num_vars_x,num_vars_y,M:Vec<{row,col,val}>} (r1cs.rs:19-26, sparse_mlpoly.rs:19-37)
-  Writer w;
-  const Instance& I = inst->inst;
-  w.u64(I.num_cons); w.u64(I.num_vars); w.u64(I.num_inputs);
-  size_t nx = 0, ny = 0;
-  while (((size_t)1 << nx) < I.num_cons) nx++;
-  while (((size_t)1 << ny) < 2 * I.num_vars) ny++;
-  for (int m = 0; m < 3; m++) {
-    w.u64(nx); w.u64(ny); w.u64(I.M[m].row.size());
-    for (size_t k = 0; k < I.M[m].row.size(); k++) { w.u64(I.M[m].row[k]); w.u64(I.M[m].col[k]); w.scalar(I.M[m].val[k]); }
-  }
-  *out = dup_bytes(w.out); *len = w.out.size();
+  std::vector<uint8_t> raw = inst->inst.shape_bincode();
+  *out = dup_bytes(raw); *len = raw.size();
   return SP_OK;
+}
+// R1CSShape::get_digest (r1cs.rs:154-158): the bytes NIZK::prove / verify absorb (lib.rs:514) — the caller's (sp_instance_set_digest) or, by
+// default, this library's miniz-level-6 zlib stream of bincode(shape), computed on first use
+int sp_instance_digest(const sp_instance* inst, uint8_t** out, size_t* len) {
+  try {
+    const std::vector<uint8_t>& d = inst->inst.shape_digest();
+    *out = dup_bytes(d); *len = d.size();
+    return SP_OK;
+  } catch (...) { return SP_ERR_INTERNAL; }
 }
 int sp_instance_nnz(const sp_instance* inst, int m, size_t* nnz) { if (m < 0 || m > 2) return SP_ERR_INVALID_ARG; *nnz = inst->inst.M[m].row.size(); return SP_OK; }
 int sp_instance_export(const sp_instance* inst, int m, uint64_t* row, uint64_t* col, uint64_t* val) {

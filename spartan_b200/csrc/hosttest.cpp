@@ -10,7 +10,15 @@ namespace sp { void shake256(uint8_t* out, size_t outlen, const uint8_t* in, siz
 static u256 in256(const uint8_t* b) { u256 r; memcpy(&r, b, 32); return r; }
 static void out256(uint8_t* b, const u256& x) { memcpy(b, &x, 32); }
 
+#include "deflate.cpp"   // host-only translation unit, pulled in here so the CPU tests can call it without the CUDA library
+
 extern "C" {
+// R1CSShape digest compressor: zlib stream of miniz level 6 (deflate.cpp); returns the length (out must hold len + len/8 + 128 bytes)
+size_t spt_zlib6(const uint8_t* in, size_t len, uint8_t* out) {
+  std::vector<uint8_t> z = sp::miniz_zlib_level6(in, len);
+  memcpy(out, z.data(), z.size());
+  return z.size();
+}
 int spt_portable(void) {
 #if SP_HOST_FAST
   return 0;

@@ -640,6 +640,25 @@ template <class T>
 static void up(Ctx* ctx, DevBuf<T>& d, const std::vector<T>& h) { d.alloc(h.size()); dev::h2d(d.p, h.data(), h.size() * sizeof(T), ctx->stream); }
 static void up(Ctx* ctx, DevBuf<u256>& d, const std::vector<Fq>& h) { d.alloc(h.size()); dev::h2d(d.p, h.data(), h.size() * sizeof(u256), ctx->stream); }
 
+std::vector<uint8_t> Instance::shape_bincode() const {
+  // bincode(R1CSShape{num_cons,num_vars,num_inputs,A,B,C}), SparseMatPolynomial{num_vars_x,num_vars_y,M:Vec<{row,col,val}>} (r1cs.rs:19-26, sparse_mlpoly.rs:19-37)
+  Writer w;
+  w.u64(num_cons); w.u64(num_vars); w.u64(num_inputs);
+  size_t nx = 0, ny = 0;
+  while (((size_t)1 << nx) < num_cons) nx++;
+  while (((size_t)1 << ny) < 2 * num_vars) ny++;
+  for (int m = 0; m < 3; m++) {
+    w.out.reserve(w.out.size() + 24 + 48 * M[m].row.size());
+    w.u64(nx); w.u64(ny); w.u64(M[m].row.size());
+    for (size_t k = 0; k < M[m].row.size(); k++) { w.u64(M[m].row[k]); w.u64(M[m].col[k]); w.scalar(M[m].val[k]); }
+  }
+  return std::move(w.out);
+}
+const std::vector<uint8_t>& Instance::shape_digest() const {
+  if (digest.empty()) { std::vector<uint8_t> raw = shape_bincode(); digest = miniz_zlib_level6(raw.data(), raw.size()); }
+  return digest;
+}
+
 void Instance::finalize(Ctx* ctx) {
   size_t ncols = 2 * num_vars;
   for (int m = 0; m < 3; m++) {
@@ -780,14 +799,13 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
 
 void nizk_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T, const Fq& tape_seed,
                 NizkProof& out) {
-  if (inst.digest.empty())
-    throw SpError(SP_ERR_INVALID_ARG, "NIZK::prove: the instance has no R1CSShapeDigest (sp_instance_set_digest); the transcript would not bind the R1CS shape (lib.rs:514)");
   ctx.timings.clear();
   ShardScope shard(ctx);
   PhaseTimer t(ctx, "NIZK::prove");
   RandomTape tape("proof", tape_seed);                                   // lib.rs:511
   T.append_protocol_name("Spartan NIZK proof");                          // lib.rs:513
-  T.append_message("R1CSShapeDigest", inst.digest.data(), inst.digest.size());  // lib.rs:514
+  const std::vector<uint8_t>& digest = inst.shape_digest();                // r1cs.rs:154-158; never empty: the transcript always binds the shape
+  T.append_message("R1CSShapeDigest", digest.data(), digest.size());       // lib.rs:514
   r1cs_prove(ctx, inst, d_vars, input, gens, T, tape, out.r1cs_sat_proof, out.rx, out.ry);
 }
 

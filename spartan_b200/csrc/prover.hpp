@@ -102,9 +102,15 @@ struct SparseMatDev {  // one of A, B, C: COO on host (reference order), CSR + C
 struct Instance {  // lib.rs:111-114 (R1CSShape + digest)
   size_t num_cons = 0, num_vars = 0, num_inputs = 0;
   SparseMatDev M[3];
-  std::vector<uint8_t> digest;
+  // R1CSShape::get_digest (r1cs.rs:154-158): zlib(level 6, miniz) of bincode(shape), computed on first use (deflate.cpp) unless the caller
+  // supplied the bytes of its own compressor through sp_instance_set_digest
+  mutable std::vector<uint8_t> digest;
+  std::vector<uint8_t> shape_bincode() const;
+  const std::vector<uint8_t>& shape_digest() const;
   void finalize(Ctx* ctx);  // build the device copies
 };
+
+std::vector<uint8_t> miniz_zlib_level6(const uint8_t* data, size_t len);   // deflate.cpp
 
 struct NizkProof { R1CSProof r1cs_sat_proof; std::vector<Fq> rx, ry;
   void ser(Writer& w) const { r1cs_sat_proof.ser(w); w.scalars(rx); w.scalars(ry); } };

@@ -533,7 +533,6 @@ static void check_dims(size_t num_cons, size_t num_vars, size_t num_inputs) {
 // NIZK::verify (lib.rs:549-591)
 void nizk_verify(Ctx& ctx, const Instance& inst, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T, const uint8_t* proof, size_t len) {
   check_dims(inst.num_cons, inst.num_vars, inst.num_inputs);
-  if (inst.digest.empty()) throw SpError(SP_ERR_INVALID_ARG, "NIZK::verify: the instance has no R1CSShapeDigest (sp_instance_set_digest); the transcript would not bind the R1CS shape (lib.rs:514)");
   Reader r(proof, len);
   NizkProof p;
   rd(r, p.r1cs_sat_proof);
@@ -542,7 +541,8 @@ void nizk_verify(Ctx& ctx, const Instance& inst, const std::vector<Fq>& input, c
   if (input.size() != inst.num_inputs) throw Reject("number of inputs");
   if (p.rx.size() != log2c(inst.num_cons) || p.ry.size() != log2c(2 * inst.num_vars)) throw Reject("claimed evaluation point");
   T.append_protocol_name("Spartan NIZK proof");
-  T.append_message("R1CSShapeDigest", inst.digest.data(), inst.digest.size());
+  const std::vector<uint8_t>& digest = inst.shape_digest();   // computed here if the caller did not supply its own (r1cs.rs:154-158)
+  T.append_message("R1CSShapeDigest", digest.data(), digest.size());
   Fq evals[3];
   instance_evaluate(ctx, inst, p.rx, p.ry, evals);
   std::vector<Fq> rx, ry;
