@@ -1,5 +1,6 @@
 // spartan_b200 — sumcheck-round kernels (K1/K2 of SURVEY.md §2b), their own translation unit so the two .cu files build in parallel.
 #include <cstdlib>
+#include <algorithm>
 #include "kcommon.cuh"
 
 #ifndef SP_SC_LB
@@ -163,6 +164,111 @@ __global__ void __launch_bounds__(SC_V2_THREADS, SC_V2_BLOCKS) k_sc_fold_eval_v2
   block_reduce_finish<3>(acc, partials, counters, out, 3, sig, xr);
 }
 
+// ---- TMA-staged formulation of the fused round (north_star: "TMA-staged into shared memory"; measured against the register-resident ones in
+// profiles/r02_tuning.md).  A CTA walks tiles of SC_TMA_TI indices; one elected thread issues the 4*NT bulk copies of the NEXT tile
+// (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) while all 256 threads work on the current one in two phases:
+//   A (bind)     : 2*NT*TI independent tasks (table, half, index): read the pair from shared memory, constant-multiplier fold, write the bound value
+//                  back to shared memory and out to HBM — no thread ever holds more than one pair, loads occupy no registers and no issue slots;
+//   B (evaluate) : NP*TI tasks (point, index): form the point's argument per table from (lo, hi) in shared memory, running product, one
+//                  accumulator per thread (a thread always serves the same evaluation point).
+// Two stages of shared memory (32 KiB each for four tables), <= 80 registers: 3 CTAs per SM.
+#ifndef SC_TMA_TI
+#define SC_TMA_TI 64
+#endif
+#ifndef SC_TMA_BLOCKS
+#define SC_TMA_BLOCKS 3
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tSP_MBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra SP_MBAR_DONE;\n\tbra SP_MBAR_WAIT;\n\tSP_MBAR_DONE:\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+template <int KIND>
+__global__ void __launch_bounds__(256, SC_TMA_BLOCKS) k_sc_fold_eval_tma(ScBatch batch, size_t len, const __grid_constant__ FqConst rc, u256* partials, unsigned int* counters,
+                                                             u256* out, HostSig sig, const __grid_constant__ XRank xr) {
+  constexpr int NT = KIND == SC_QUAD ? 2 : (KIND == SC_CUBIC3 ? 3 : 4);
+  constexpr int NP = KIND == SC_QUAD ? 2 : 3;
+  constexpr int TI = SC_TMA_TI;
+  constexpr uint32_t SEG_BYTES = TI * 32, STAGE_BYTES = NT * 4 * SEG_BYTES;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  u256* buf = reinterpret_cast<u256*>(smem_raw);                                    // [stage][table][segment][TI]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + 2 * STAGE_BYTES);         // [2]
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1, quarter = len >> 2;
+  const size_t ntiles = quarter / TI;
+  const int tid = threadIdx.x;
+  auto slot = [&](int stage, int t, int seg) { return buf + ((size_t)(stage * NT + t) * 4 + seg) * TI; };
+  auto issue = [&](int stage, size_t tile) {   // one thread: arm the barrier with the byte count, then the 4*NT bulk copies
+    mbar_expect_tx(&mbar[stage], STAGE_BYTES);
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const u256* T = in.t[t] + tile * TI;
+      bulk_g2s(slot(stage, t, 0), T, SEG_BYTES, &mbar[stage]);
+      bulk_g2s(slot(stage, t, 1), T + half, SEG_BYTES, &mbar[stage]);
+      bulk_g2s(slot(stage, t, 2), T + quarter, SEG_BYTES, &mbar[stage]);
+      bulk_g2s(slot(stage, t, 3), T + quarter + half, SEG_BYTES, &mbar[stage]);
+    }
+  };
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < ntiles) issue(0, blockIdx.x);
+  u256 acc = fq_zero();
+  int k = 0;
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+    const int s = k & 1;
+    if (tid == 0 && tile + gridDim.x < ntiles) issue(s ^ 1, tile + gridDim.x);   // stage s^1 was released by the barrier that ended iteration k-1
+    mbar_wait(&mbar[s], (k >> 1) & 1);
+    // ---- phase A: bind
+#pragma unroll 1
+    for (int task = tid; task < NT * 2 * TI; task += 256) {
+      const int t = task / (2 * TI), h = (task / TI) & 1, e = task % TI;
+      u256* pa = slot(s, t, 2 * h) + e;
+      const u256 v = fq_fold_const(ld256(pa), ld256(slot(s, t, 2 * h + 1) + e), rc);   // dense_mlpoly.rs:218
+      st256(pa, v);
+      const size_t g = tile * TI + e + (h ? quarter : 0);
+      if (t == 2) { if (in.write_c) st256(in.c_out + g, v); }
+      else st256(in.t[t] + g, v);
+    }
+    __syncthreads();
+    // ---- phase B: evaluate at t = 0, 2 (, 3)
+    if (tid < NP * TI) {
+      const int p = tid / TI, e = tid % TI;
+      u256 P = fq_zero();
+#pragma unroll
+      for (int step = 0; step < NT; step++) {
+        const int t = KIND == SC_CUBIC4 ? (step + 1) & 3 : step;     // B, C, D, A for A*(B*C-D)
+        const u256 lo = ld256(slot(s, t, 0) + e), hi = ld256(slot(s, t, 2) + e);
+        u256 x = lo;
+        if (p > 0) { const u256 dl = fq_sub(hi, lo); x = fq_add(hi, dl); if (p == 2) x = fq_add(x, dl); }
+        if (step == 0) P = x;
+        else if (KIND == SC_CUBIC4 && step == 2) P = fq_sub(P, x);
+        else P = fq_mul(P, x);
+      }
+      acc = fq_add(acc, P);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this iteration's generic-proxy accesses to stage s before the bulk copy that refills it
+    __syncthreads();
+  }
+  u256 acc3[3];
+  const int p = tid / TI;
+#pragma unroll
+  for (int q = 0; q < 3; q++) acc3[q] = (tid < NP * TI && p == q) ? acc : fq_zero();
+  block_reduce_finish<3>(acc3, partials, counters, out, 3, sig, xr);
+}
+
 // Small tables (len/4 <= SC_SMALL_MAX): the round's latency, not its throughput, is what the prover waits for, so the work of one index is
 // spread over 2*NT threads for the bind step (one multiplication deep) and 3 threads for the evaluations (two deep), exchanging the bound
 // values through shared memory, instead of one thread running all 14 multiplications back to back.  Same arithmetic, same results.
@@ -306,6 +412,28 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
       default: SP_SC_LAUNCH(k_sc_fold_eval_small, SC_CUBIC4, SC_SMALL_Q * 8); break;
     }
     SP_LAUNCHED(); check("sc_fold_eval_small");
+    return;
+  }
+  static const bool tma = getenv("SP_SC_TMA") != nullptr && cf;   // TMA-staged two-phase formulation (A/B switch)
+  if (tma && len / 4 >= 64 * SC_TMA_TI) {
+    const int nt = kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4;
+    const size_t smem = (size_t)2 * nt * 4 * SC_TMA_TI * 32 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_sc_fold_eval_tma<SC_QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * 4 * SC_TMA_TI * 32 + 64);
+      cudaFuncSetAttribute(k_sc_fold_eval_tma<SC_CUBIC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 3 * 4 * SC_TMA_TI * 32 + 64);
+      cudaFuncSetAttribute(k_sc_fold_eval_tma<SC_CUBIC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 4 * SC_TMA_TI * 32 + 64);
+      attr_set = true;
+    }
+    size_t ntiles = len / 4 / SC_TMA_TI;
+    dim3 grid((unsigned)std::min<size_t>(ntiles, (size_t)sm_count() * SC_TMA_BLOCKS), ninst);
+    if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
+    switch (kind) {
+      case SC_QUAD: k_sc_fold_eval_tma<SC_QUAD><<<grid, 256, smem, s>>>(b, len, rc, partials, counters, out, sig, xr); break;
+      case SC_CUBIC3: k_sc_fold_eval_tma<SC_CUBIC3><<<grid, 256, smem, s>>>(b, len, rc, partials, counters, out, sig, xr); break;
+      default: k_sc_fold_eval_tma<SC_CUBIC4><<<grid, 256, smem, s>>>(b, len, rc, partials, counters, out, sig, xr); break;
+    }
+    SP_LAUNCHED(); check("sc_fold_eval_tma");
     return;
   }
   static const bool v2 = getenv("SP_SC_V2") != nullptr && cf;   // register-lean formulation (A/B switch)

@@ -172,7 +172,7 @@ def test_gens_upload(sb):
         sb.MultiCommitGens.from_points(bad)
 
 
-@pytest.mark.parametrize("logn", [2, 5, 11, 14])
+@pytest.mark.parametrize("logn", [2, 5, 11, 14, 16])
 def test_sumcheck_batched(sb, logn):
     """prove_cubic_batched's loops (sumcheck.rs:290-357): 5 instances, three of them sharing one C table (poly_C_par), whole chain of rounds"""
     from spartan_b200 import api
