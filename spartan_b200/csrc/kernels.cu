@@ -636,8 +636,13 @@ void sum_points(ge* out, const ge* in, int n, cudaStream_t s) {
 // ---- the two MSMs of one inner-product round in a single launch (bullet.rs:83-97 with unfolded generators, see k_ipa_lr):
 // every generator j carries exactly one non-zero scalar, a[.]*s[j], for L (j in the right half of its n_cur-block) or for R (left half).
 // grid = (chunks, 2 sides); the last block to finish sums the partial points of both sides and publishes L, R to the host.
+// (latency-bound: 256 CTAs of which each thread makes <= 3 mixed additions and then two point-addition trees; no register cap, so that ptxas can
+//  keep the four independent field products of a point addition in flight together)
+#ifndef SP_IPA_LB
+#define SP_IPA_LB 1
+#endif
 template <int WBITS, int GROUPS>
-__global__ void __launch_bounds__(128, SP_MSM_LB) k_ipa_msm(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ a, const u256* __restrict__ sv,
+__global__ void __launch_bounds__(128, SP_IPA_LB) k_ipa_msm(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ a, const u256* __restrict__ sv,
                                                            size_t n_cur, size_t n_full, unsigned int* ticket, ge* out, HostSig sig) {
   constexpr int NWIN = (253 + WBITS - 1) / WBITS;
   constexpr int WPT = (NWIN + GROUPS - 1) / GROUPS;
@@ -712,7 +717,7 @@ __global__ void __launch_bounds__(128, SP_MSM_LB) k_ipa_msm(ge* partial, const g
 }
 void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
              cudaStream_t s, HostSig sig) {
-  ProfScope ps("msm_rows", 64.0 * (double)n_full, s);
+  ProfScope ps("ipa_msm", 64.0 * (double)n_full, s);
   constexpr int GROUPS = 8;
   const size_t cols = 128 / GROUPS, total = n_full / 2;
   dim3 grid((unsigned)((total + cols - 1) / cols), 2);
