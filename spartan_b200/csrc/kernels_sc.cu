@@ -360,12 +360,13 @@ __global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch b
 struct FoldBatch {
   u256* t[64];
 };
-__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const __grid_constant__ FqConst rc) {
+template <bool CF>
+__global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, const u256 r, const __grid_constant__ FqConst rc) {
   const size_t half = len >> 1;
   u256* T = tabs.t[blockIdx.y];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
     u256 a0 = ld256(T + i), a1 = ld256(T + i + half);
-    st256(T + i, fq_fold_const(a0, a1, rc));   // dense_mlpoly.rs:218
+    st256(T + i, CF ? fq_fold_const(a0, a1, rc) : fq_add(a0, fq_mul(r, fq_sub(a1, a0))));   // dense_mlpoly.rs:218
   }
 }
 
@@ -373,6 +374,14 @@ __global__ void __launch_bounds__(256) k_fold_top(FoldBatch tabs, size_t len, co
 static const size_t SC_MAX_BLOCKS = 148 * 6 + 64;
 size_t sc_scratch_bytes(int ninst) { return 256 + (size_t)ninst * SC_MAX_BLOCKS * 3 * sizeof(u256); }
 
+// A/B switch for the constant-multiplier fold (tools/bench_kernels.py): SP_SC_CONSTFOLD=0/1 overrides the default
+#ifndef SP_SC_CONSTFOLD_DEFAULT
+#define SP_SC_CONSTFOLD_DEFAULT 0
+#endif
+static bool sc_constfold() {
+  static const bool on = [] { const char* e = getenv("SP_SC_CONSTFOLD"); return e ? atoi(e) != 0 : SP_SC_CONSTFOLD_DEFAULT != 0; }();
+  return on;
+}
 static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
   if (ninst > SC_MAX_INST) throw std::runtime_error("spartan_b200: too many sumcheck instances in one batch");
   for (int i = 0; i < ninst; i++) b.inst[i] = insts[i];
@@ -399,7 +408,7 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
   static const bool small_ok = getenv("SP_SC_NO_SMALL") == nullptr;
-  static const bool cf = getenv("SP_SC_NO_CONSTFOLD") == nullptr;   // A/B switch for the constant-multiplier fold (tools/bench_kernels.py)
+  static const bool cf = sc_constfold();
   const FqConst rc = cf ? fq_const_table(r) : FqConst();
 #define SP_SC_LAUNCH(KERNEL, K, THREADS, ...) \
   do { if (cf) KERNEL<K, true><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig, ##__VA_ARGS__); \
@@ -460,12 +469,14 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
 }
 void fold_top(u256* const* tables, int ntables, size_t len, const u256& r, cudaStream_t s) {
   ProfScope ps("fold_top", (double)ntables * len * 48.0, s);
-  const FqConst rc = fq_const_table(r);
+  const bool cf = sc_constfold();
+  const FqConst rc = cf ? fq_const_table(r) : FqConst();
   for (int base = 0; base < ntables; base += 64) {
     FoldBatch fb; int n = ntables - base < 64 ? ntables - base : 64;
     for (int i = 0; i < n; i++) fb.t[i] = tables[base + i];
     dim3 grid(grid_for(len / 2, 256, 4), n);
-    k_fold_top<<<grid, 256, 0, s>>>(fb, len, rc);
+    if (cf) k_fold_top<true><<<grid, 256, 0, s>>>(fb, len, r, rc);
+    else k_fold_top<false><<<grid, 256, 0, s>>>(fb, len, r, rc);
     SP_LAUNCHED();
   }
   check("fold_top");

@@ -5,26 +5,29 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/c1
 ( timeout 300 tools/probe/probe > gpurun_out/c1_probe.txt 2>&1 )
 for v in nocf cf v2 v2b6 tma tma32; do
   case $v in
-    nocf) export SP_SC_NO_CONSTFOLD=1; unset SP_SC_V2 SP_LIB_TAG;;
-    cf) unset SP_SC_NO_CONSTFOLD SP_SC_V2 SP_LIB_TAG;;
-    v2) unset SP_SC_NO_CONSTFOLD SP_LIB_TAG; export SP_SC_V2=1;;
-    v2b6) unset SP_SC_NO_CONSTFOLD; export SP_SC_V2=1 SP_LIB_TAG=_v2b6;;
-    tma) unset SP_SC_NO_CONSTFOLD SP_SC_V2 SP_LIB_TAG; export SP_SC_TMA=1;;
-    tma32) unset SP_SC_NO_CONSTFOLD SP_SC_V2; export SP_SC_TMA=1 SP_LIB_TAG=_v2b6;;
+    nocf) export SP_SC_CONSTFOLD=0; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG;;
+    cf) export SP_SC_CONSTFOLD=1; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG;;
+    v2) export SP_SC_CONSTFOLD=1 SP_SC_V2=1; unset SP_SC_TMA SP_LIB_TAG;;
+    v2b6) export SP_SC_CONSTFOLD=1 SP_SC_V2=1 SP_LIB_TAG=_v2b6; unset SP_SC_TMA;;
+    tma) export SP_SC_CONSTFOLD=1 SP_SC_TMA=1; unset SP_SC_V2 SP_LIB_TAG;;
+    tma32) export SP_SC_CONSTFOLD=1 SP_SC_TMA=1 SP_LIB_TAG=_v2b6; unset SP_SC_V2;;
   esac
-  ( timeout 300 python tools/bench_kernels.py 20 > gpurun_out/c1_kern20_$v.json 2> gpurun_out/c1_kern20_$v.err )
   ( timeout 300 python tools/bench_kernels.py 22 --snark > gpurun_out/c1_kern22_$v.json 2> gpurun_out/c1_kern22_$v.err )
 done
-unset SP_SC_NO_CONSTFOLD SP_LIB_TAG SP_SC_TMA
-export SP_SC_TMA=1
+unset SP_LIB_TAG SP_SC_V2
+export SP_SC_CONSTFOLD=1 SP_SC_TMA=1
 ( timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_golden.py -m gpu -x -q > gpurun_out/c1_pytest_tma.txt 2>&1 )
 ( timeout 600 python -m pytest tests/test_gpu_snark.py -m gpu -x -q -k "bytes_match_oracle and not bench" >> gpurun_out/c1_pytest_tma.txt 2>&1 )
 tail -3 gpurun_out/c1_pytest_tma.txt
 unset SP_SC_TMA
-export SP_SC_V2=1
+export SP_SC_CONSTFOLD=1 SP_SC_V2=1
 ( timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_golden.py -m gpu -x -q > gpurun_out/c1_pytest_v2.txt 2>&1 )
 ( timeout 600 python -m pytest tests/test_gpu_snark.py -m gpu -x -q -k "bytes_match_oracle and not bench" >> gpurun_out/c1_pytest_v2.txt 2>&1 )
 unset SP_SC_V2
+( timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_golden.py tests/test_gpu_prover.py -m gpu -x -q -k "not large" > gpurun_out/c1_pytest_cf.txt 2>&1 )
+tail -3 gpurun_out/c1_pytest_cf.txt
+( SP_FINE_TIMERS=1 timeout 300 python tools/profile_snark.py 20 > gpurun_out/c1_profile20_cf.txt 2>&1 )
+unset SP_SC_CONSTFOLD
 ( SP_FINE_TIMERS=1 timeout 300 python tools/profile_snark.py 20 > gpurun_out/c1_profile20.txt 2>&1 )
 ( timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/c1_pytest.txt 2>&1 )
 tail -3 gpurun_out/c1_pytest.txt
