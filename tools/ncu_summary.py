@@ -77,5 +77,33 @@ def full(path, title):
         print()
 
 
+
+
+
+def traffic_json(path, out_json):
+    """`full` captures -> {"<family>": {dram_bytes, us, kernel, what}} of the FIRST captured launch of each kernel family: what bench.py reports as
+    roofline.traffic (profiles/r02_ncu_traffic.json)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr, units = rd[0], rd[1]
+    res = {}
+
+    def num(d, key):
+        v = float(d[key].replace(",", ""))
+        u = units[hdr.index(key)]
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "ns": 1e-3, "nsecond": 1e-3, "second": 1e6}.get(u, 1.0)
+    for row in rd[2:]:
+        d = dict(zip(hdr, row))
+        name = short(d.get("Kernel Name", "?"))
+        fam = "sc_fold_eval" if "sc_fold_eval" in name else ("msm_rows" if "msm_rows" in name else ("ipa_msm" if "ipa_msm" in name else name))
+        if fam in res:
+            continue
+        res[fam] = {"kernel": name, "dram_bytes": num(d, "dram__bytes_read.sum") + num(d, "dram__bytes_write.sum"), "us": num(d, "gpu__time_duration.sum"),
+                    "grid": d.get("launch__grid_size"), "regs": d.get("launch__registers_per_thread")}
+    json.dump(res, open(out_json, "w"), indent=1, sort_keys=True)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    {"launches": launches, "full": full, "traffic": traffic_json}[sys.argv[1]](sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
