@@ -57,11 +57,25 @@ void poly_eq_evals(fq_t *evals, const fq_t *r, size_t ell) {
   evals[0] = FQ_R;
   for (size_t j = 0; j < ell; j++) {
     size *= 2;
-    for (size_t i = size - 1;; i -= 2) {
-      fq_t scalar = evals[i / 2];
-      fq_mul(&evals[i], &scalar, &r[j]);
-      fq_sub(&evals[i - 1], &scalar, &evals[i]);
-      if (i == 1) break;
+    if (size <= 8192) {   /* the reference's in-place descending loop */
+      for (size_t i = size - 1;; i -= 2) {
+        fq_t scalar = evals[i / 2];
+        fq_mul(&evals[i], &scalar, &r[j]);
+        fq_sub(&evals[i - 1], &scalar, &evals[i]);
+        if (i == 1) break;
+      }
+    } else {
+      /* same values, all host threads: pair p reads evals[p] and writes evals[2p], evals[2p+1]; only the upper half (2p >= size/2) can be
+         written in place without clobbering an unread parent, so the parents are snapshotted first */
+      size_t half = size / 2;
+      fq_t *parent = (fq_t *)malloc(sizeof(fq_t) * half);
+      memcpy(parent, evals, sizeof(fq_t) * half);
+#pragma omp parallel for schedule(static)
+      for (size_t p = 0; p < half; p++) {
+        fq_mul(&evals[2 * p + 1], &parent[p], &r[j]);
+        fq_sub(&evals[2 * p], &parent[p], &evals[2 * p + 1]);
+      }
+      free(parent);
     }
   }
 }
@@ -149,22 +163,39 @@ void sc_eval_cubic(fq_t out[3], const fq_t *A, const fq_t *B, const fq_t *C, con
 /* ---- sparse matrix ops on COO triples, sparse_mlpoly.rs:454-481 ---- */
 void sparse_multiply_vec(fq_t *Mz, size_t num_rows, const uint64_t *row, const uint64_t *col, const fq_t *val, size_t nnz, const fq_t *z) {
   memset(Mz, 0, sizeof(fq_t) * num_rows);
-  for (size_t k = 0; k < nnz; k++) { fq_t m; fq_mul(&m, &val[k], &z[col[k]]); fq_add(&Mz[row[k]], &Mz[row[k]], &m); }
+  /* products on all host threads, the scatter-add (order-independent: exact field arithmetic) on one */
+  fq_t *prod = (fq_t *)malloc(sizeof(fq_t) * (nnz ? nnz : 1));
+#pragma omp parallel for schedule(static) if (nnz > 4096)
+  for (size_t k = 0; k < nnz; k++) fq_mul(&prod[k], &val[k], &z[col[k]]);
+  for (size_t k = 0; k < nnz; k++) fq_add(&Mz[row[k]], &Mz[row[k]], &prod[k]);
+  free(prod);
 }
 void sparse_eval_table(fq_t *out, size_t num_cols, const uint64_t *row, const uint64_t *col, const fq_t *val, size_t nnz, const fq_t *rx) {
   memset(out, 0, sizeof(fq_t) * num_cols);
-  for (size_t k = 0; k < nnz; k++) { fq_t m; fq_mul(&m, &rx[row[k]], &val[k]); fq_add(&out[col[k]], &out[col[k]], &m); }
+  fq_t *prod = (fq_t *)malloc(sizeof(fq_t) * (nnz ? nnz : 1));
+#pragma omp parallel for schedule(static) if (nnz > 4096)
+  for (size_t k = 0; k < nnz; k++) fq_mul(&prod[k], &rx[row[k]], &val[k]);
+  for (size_t k = 0; k < nnz; k++) fq_add(&out[col[k]], &out[col[k]], &prod[k]);
+  free(prod);
 }
 /* evaluate_with_tables, sparse_mlpoly.rs:426-438 */
 void sparse_evaluate(fq_t *out, const uint64_t *row, const uint64_t *col, const fq_t *val, size_t nnz, const fq_t *trx, const fq_t *try_) {
-  fq_t acc = {{0}}, m;
-  for (size_t k = 0; k < nnz; k++) { fq_mul(&m, &trx[row[k]], &try_[col[k]]); fq_mul(&m, &m, &val[k]); fq_add(&acc, &acc, &m); }
+  fq_t acc = {{0}};
+#pragma omp parallel if (nnz > 4096)
+  {
+    fq_t local = {{0}}, m;
+#pragma omp for schedule(static) nowait
+    for (size_t k = 0; k < nnz; k++) { fq_mul(&m, &trx[row[k]], &try_[col[k]]); fq_mul(&m, &m, &val[k]); fq_add(&local, &local, &m); }
+#pragma omp critical
+    fq_add(&acc, &acc, &local);
+  }
   *out = acc;
 }
 
 /* ---- SPARK helpers ---- */
 /* AddrTimestamps::deref_mem, sparse_mlpoly.rs:256-265 */
 void spark_deref(fq_t *out, const uint64_t *addr, size_t n, const fq_t *mem) {
+#pragma omp parallel for schedule(static) if (n > 4096)
   for (size_t i = 0; i < n; i++) out[i] = mem[addr[i]];
 }
 /* DensePolynomial::from_usize, dense_mlpoly.rs:274-280 */
