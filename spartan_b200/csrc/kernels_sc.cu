@@ -382,13 +382,28 @@ static bool sc_constfold() {
   static const bool on = [] { const char* e = getenv("SP_SC_CONSTFOLD"); return e ? atoi(e) != 0 : SP_SC_CONSTFOLD_DEFAULT != 0; }();
   return on;
 }
+// algorithmic bytes of one launch: every DISTINCT table is streamed once (a C table shared by several instances of a batched sumcheck counts
+// once, not once per instance): `per_elem` bytes per entry (32 for an evaluation pass, 48 for the fused bind + evaluate: read 32, write 16 per input entry)
+static double sc_bytes(const ScInst* insts, int ninst, ScKind kind, size_t len, double per_elem) {
+  const int nt = kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4;
+  const u256* seen[SC_MAX_INST * 4];
+  int ns = 0;
+  if (ninst > SC_MAX_INST) return 0.0;   // fill_batch rejects the launch
+  for (int i = 0; i < ninst; i++)
+    for (int t = 0; t < nt; t++) {
+      bool dup = false;
+      for (int k = 0; k < ns; k++) dup = dup || seen[k] == insts[i].t[t];
+      if (!dup) seen[ns++] = insts[i].t[t];
+    }
+  return (double)ns * (double)len * per_elem;
+}
 static void fill_batch(ScBatch& b, const ScInst* insts, int ninst) {
   if (ninst > SC_MAX_INST) throw std::runtime_error("spartan_b200: too many sumcheck instances in one batch");
   for (int i = 0; i < ninst; i++) b.inst[i] = insts[i];
 }
 
 void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out, void* scratch, cudaStream_t s, HostSig sig, const XRank& xr) {
-  ProfScope ps("sc_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 32.0, s);
+  ProfScope ps("sc_eval", sc_bytes(insts, ninst, kind, len, 32.0), s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
@@ -403,7 +418,7 @@ void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out,
 }
 void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s, HostSig sig, const XRank& xr) {
   if (xr.world > 1 && (len / 4 <= SC_SMALL_MAX || !sig.done)) throw std::runtime_error("spartan_b200: a sharded sumcheck round needs a streaming-size table and a completion counter");
-  ProfScope ps("sc_fold_eval", (double)ninst * (kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4) * len * 48.0, s);
+  ProfScope ps("sc_fold_eval", sc_bytes(insts, ninst, kind, len, 48.0), s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
