@@ -187,7 +187,13 @@ def msm_var_leg(sb, api, sd, ctx, rank, world, logn=24):
         ts.append(api.timer_stop_ms(ctx))
         assert out == out2
     ms = sd.max_over_ranks([min(ts)])[0]
-    return {"points": n, "n_gpus": world, "ms": ms, "Mpoint_adds_per_s_reference_equivalent": 33.0 * n / (ms / 1e3) / 1e6, "Mpoints_per_s": n / (ms / 1e3) / 1e6,
+    golden = None
+    try:   # the oracle's result for exactly these inputs (tests/golden/msm_2p24.json, made on the CPU by tests/golden/make_msm_golden.py)
+        with open(os.path.join(ROOT, "tests", "golden", "msm_2p%d.json" % logn)) as f:
+            golden = json.load(f)["encoding"] == out.hex()
+    except Exception:
+        pass
+    return {"points": n, "n_gpus": world, "ms": ms, "result_equals_oracle_golden": golden, "Mpoint_adds_per_s_reference_equivalent": 33.0 * n / (ms / 1e3) / 1e6, "Mpoints_per_s": n / (ms / 1e3) / 1e6,
             "what": "2^%d caller-supplied points, 253-bit scalars, scalars and points resident in HBM, %s; 33 adds/point = dalek Pippenger w=8 (SURVEY.md 8d)"
                     % (logn, "split by index range over %d GPUs + point-add all-reduce over NVLink (sp_msm_var_sharded)" % world if world > 1 else "sp_msm_var_resident"),
             "result_prefix": out.hex()[:16]}
@@ -331,6 +337,15 @@ def run_b200(args):
             except Exception:
                 roof["traffic"] = None
         roof_msm = rl(dom[0], dom[1], "hbm")
+        try:   # integer-issue roofline of the dominant kernel from the committed ncu capture: executed warp instructions / (duration x issue peak)
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+                cap = json.load(f)[dom[0]]
+            peak_wi = 148 * 4 * pk.get("sm_max_mhz", 1965.0) * 1e6      # one warp instruction per cycle per SM sub-partition
+            roof_msm["roofline_int"] = {"bound": "issue (INT32 pipe: IMAD.WIDE carry chains)", "warp_instructions": cap["warp_instructions"], "us": cap["us"],
+                                        "achieved": cap["warp_instructions"] / (cap["us"] * 1e-6) / 1e9, "peak": peak_wi / 1e9, "unit": "G warp-instr/s",
+                                        "frac": cap["warp_instructions"] / (cap["us"] * 1e-6) / peak_wi, "traffic": cap["dram_bytes"], "source": cap["what"]}
+        except Exception:
+            pass
         roof_msm["note"] = ("dominant kernel by time; fixed-base ristretto255 comb, INTEGER-ALU bound (20 table lookups x 7 field multiplications per term): its "
                             "algorithmic bytes are only scalars + bases, so the HBM fraction is honestly tiny")
         kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}

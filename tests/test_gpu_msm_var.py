@@ -133,3 +133,27 @@ def test_msm_var_large_properties(sb):
     ref = oc.MultiCommitGens.new(m, b"msm-large")
     assert P.msm(t[:m]) == oc.msm(t[:m], ref.G).compress()
     del T
+
+
+def test_msm_var_2p24_matches_oracle_golden(sb):
+    """BASELINE.json configs[2] exactly as bench.py runs it — 2^24 points of the b"msm-bench" generator stream, the scalars of
+    numpy.random.default_rng(0) — against the oracle's result for the same inputs (tests/golden/msm_2p24.json, made by
+    tests/golden/make_msm_golden.py on the CPU), both for the whole vector and for the eight index-range slices the 8-GPU run computes;
+    the slices also have to add up to the whole (point-add all-reduce)."""
+    import json
+    from spartan_b200 import api
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "msm_2p24.json")))
+    n = fx["points"]
+    P = api.Points.derive(n, b"msm-bench")
+    assert hashlib.sha256(b"".join(P.export(i, 1)[0] for i in (0, 1, n // 2, n - 1))).hexdigest() == fx["generator_digest"]
+    rng = np.random.default_rng(0)
+    t = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64)
+    t[:, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+    assert P.msm(sb.DensePolynomial(t)).hex() == fx["encoding"]
+    per = n // 8
+    acc = oc.Point.identity()
+    for k in range(8):
+        enc = P.msm(sb.DensePolynomial(t[k * per:(k + 1) * per]), offset=k * per)
+        assert enc.hex() == fx["slices8"][k], k
+        acc = acc + oc.Point.decompress(enc)
+    assert acc.compress().hex() == fx["encoding"]

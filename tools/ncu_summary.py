@@ -100,7 +100,10 @@ def traffic_json(path, out_json):
         if fam in res:
             continue
         res[fam] = {"kernel": name, "dram_bytes": num(d, "dram__bytes_read.sum") + num(d, "dram__bytes_write.sum"), "us": num(d, "gpu__time_duration.sum"),
-                    "grid": d.get("launch__grid_size"), "regs": d.get("launch__registers_per_thread")}
+                    "grid": d.get("launch__grid_size"), "regs": d.get("launch__registers_per_thread"),
+                    "warp_instructions": float(d.get("smsp__inst_executed.sum", "0").replace(",", "") or 0),
+                    "issue_active_pct": float(d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "0").replace(",", "") or 0),
+                    "what": "first captured launch of this kernel in a SNARK::prove at 2^20 (ncu --set full --clock-control none)"}
     json.dump(res, open(out_json, "w"), indent=1, sort_keys=True)
     print(json.dumps(res, indent=1))
 
