@@ -157,11 +157,6 @@ static void build_circuits(Ctx& ctx, std::vector<ProdCircuit*> cs) {
   }
 }
 
-static Fq circuit_evaluate(Ctx& ctx, ProdCircuit& c) {  // ProductCircuit::evaluate (product_tree.rs:58-63)
-  std::vector<Fq> v = ctx.download(c.layer(c.num_layers - 1), 2);
-  return v[0] * v[1];
-}
-
 // DotProductCircuit (product_tree.rs:66-108) of `len` entries; the tables the sumcheck binds are this rank's cyclic shards when `sharded`
 struct DotpCircuit { u256 *left, *right, *weight; size_t len; bool sharded; Fq claim; };
 
@@ -444,11 +439,27 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   T.append_protocol_name("Sparse polynomial evaluation proof");
   ProductLayerProof& pl = ep.proof_prod_layer;
   T.append_protocol_name("Sparse polynomial product layer proof");  // ProductLayerProof::prove (sparse_mlpoly.rs:1035-1226)
+  // ProductCircuit::evaluate of all 16 circuits (product_tree.rs:58-63): the two entries of every last layer through one gather kernel that
+  // publishes them to the host, instead of 16 copies each followed by a stream synchronise
+  Fq roots[2][8];
+  {
+    std::vector<const u256*> hp;
+    for (int side = 0; side < 2; side++) {
+      Side& s = S[side];
+      ProdCircuit* cs[8] = {&s.init, &s.audit, &s.read[0], &s.read[1], &s.read[2], &s.write[0], &s.write[1], &s.write[2]};
+      for (auto* c : cs) { hp.push_back(c->layer(c->num_layers - 1)); hp.push_back(c->layer(c->num_layers - 1) + 1); }
+    }
+    DevBuf<u256> d_roots(hp.size());
+    dev::HostSig hs = ctx.next_sig();
+    dev::heads(d_roots.p, hp.data(), (int)hp.size(), ctx.stream, hs);
+    ctx.wait_sig(hs);
+    Fq v[32];
+    memcpy(v, ctx.host_res, sizeof v);
+    for (int side = 0; side < 2; side++) for (int c = 0; c < 8; c++) roots[side][c] = v[16 * side + 2 * c] * v[16 * side + 2 * c + 1];
+  }
   for (int side = 0; side < 2; side++) {
-    Side& s = S[side];
-    Fq init = circuit_evaluate(ctx, s.init), audit = circuit_evaluate(ctx, s.audit);
-    std::vector<Fq> read(3), write(3);
-    for (int m = 0; m < 3; m++) { read[m] = circuit_evaluate(ctx, s.read[m]); write[m] = circuit_evaluate(ctx, s.write[m]); }
+    Fq init = roots[side][0], audit = roots[side][1];
+    std::vector<Fq> read = {roots[side][2], roots[side][3], roots[side][4]}, write = {roots[side][5], roots[side][6], roots[side][7]};
     Fq ws = write[0] * write[1] * write[2], rs = read[0] * read[1] * read[2];
     if (!(init * ws == rs * audit)) throw SpError(SP_ERR_INTERNAL, "memory-check subset test failed (sparse_mlpoly.rs:1060)");
     const char* li = side == 0 ? "claim_row_eval_init" : "claim_col_eval_init";
