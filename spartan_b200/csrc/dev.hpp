@@ -94,6 +94,15 @@ void sc_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, u256* ou
 // fold every table of every instance by r (len -> len/2, in place) and evaluate the next round on the result; r travels as a kernel argument
 void sc_fold_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s,
                   HostSig sig = HostSig(), const XRank& xr = XRank());
+// ---- persistent tail of a batched cubic sumcheck (prove_cubic_batched, sumcheck.rs:254-424, once the tables are small): ONE launch runs all the
+// remaining rounds.  CTA i owns instance i (tables A, B and a private copy of C); after every bind it publishes the instance's evaluations to
+// the host (HostSig, sequence numbers sig.seq, sig.seq+1, ...), then spins on a mailbox in mapped pinned host memory until the host has derived
+// the next challenge from the transcript.  After the last bind it publishes the bound heads A[0], B[0], C[0] instead.  No launch, no cold
+// caches and no kernel drain between rounds: a round costs the PCIe round trip plus a few microseconds of arithmetic.
+struct PersistMail { u256 r; unsigned int seq; unsigned int pad[7]; };
+#define SC_PERSIST_MAX_LEN 4096
+void sc_persist(const ScInst* insts, int ninst, int n_shared_c /* instances [0, n_shared_c) read the shared C table */, u256* c_scratch /* n_shared_c * len */,
+                size_t len, const u256& r0, const PersistMail* mail, unsigned int mail_seq0, u256* out, cudaStream_t s, HostSig sig);
 // fold only (bound_poly_var_top, dense_mlpoly.rs:215-223): tables[k][i] += r*(tables[k][i+len/2]-tables[k][i])
 void fold_top(u256* const* d_tables, int ntables, size_t len, const u256& r, cudaStream_t s);
 void fold_top_single(u256* table, size_t len, const u256& r, cudaStream_t s);

@@ -1,5 +1,6 @@
 // spartan_b200 — device context, buffers and generator sets shared by the host prover.
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <map>
@@ -98,6 +99,14 @@ struct Ctx {
   unsigned int sig_seq = 0;
   dev::HostSig next_sig() { dev::HostSig s; s.host_out = host_res; s.flag = host_flag; s.done = sig_done.p; s.seq = ++sig_seq; return s; }
   void wait_sig(const dev::HostSig& s);   // spins on the flag; falls back to a stream synchronise to surface CUDA errors
+  // host -> persistent-kernel mailbox (dev::sc_persist): the next challenge and its sequence number, in mapped pinned memory
+  dev::PersistMail* mail = nullptr;
+  unsigned int mail_seq = 0;
+  void post_challenge(const Fq& r) {
+    memcpy((void*)&mail->r, &r.m, sizeof(u256));
+    std::atomic_thread_fence(std::memory_order_release);
+    *((volatile unsigned int*)&mail->seq) = ++mail_seq;
+  }
   void sync() { dev::stream_sync(stream); }
   void ensure_scratch(size_t bytes) { if (scratch.n < bytes) { sync(); scratch.alloc(bytes); } }
   // upload k scalars to small[slot..]

@@ -357,6 +357,89 @@ __global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch b
   }
 }
 
+// ---- persistent tail (dev.hpp: sc_persist)
+__device__ __forceinline__ u256 ld256_sys(const u256* p) {   // mapped host memory: volatile, never cached in L1
+  const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(p);
+  u256 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = q[i];
+  return r;
+}
+__global__ void __launch_bounds__(512) k_sc_persist(ScBatch batch, int n_shared_c, u256* c_scratch, size_t len, const u256 r0, const PersistMail* mail,
+                                                    unsigned int mail_seq0, u256* out, HostSig sig) {
+  __shared__ u256 ws[16][3];
+  __shared__ u256 s_r;
+  const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u256* T[3] = {batch.inst[inst].t[0], batch.inst[inst].t[1], batch.inst[inst].t[2]};
+  if (inst < n_shared_c) {   // private copy of the shared eq table: the instances then never touch common data
+    u256* mine = c_scratch + (size_t)inst * len;
+    for (size_t i = tid; i < len; i += blockDim.x) st256(mine + i, ld256(T[2] + i));
+    T[2] = mine;
+    __syncthreads();
+  }
+  int nfold = 0;
+  while (((size_t)1 << nfold) < len) nfold++;
+  u256 r = r0;
+  size_t L = len;
+  for (int f = 0; f < nfold; f++) {
+    const size_t half = L >> 1, quarter = L >> 2;
+    if (f + 1 < nfold) {
+      // bind: entries idx in [0, half) of every table, idx + half being the partner             (dense_mlpoly.rs:218)
+      for (size_t task = tid; task < 3 * half; task += blockDim.x) {
+        const int t = (int)(task / half);
+        const size_t idx = task - (size_t)t * half;
+        const u256 x0 = ld256(T[t] + idx), x1 = ld256(T[t] + idx + half);
+        st256(T[t] + idx, fq_add(x0, fq_mul(r, fq_sub(x1, x0))));
+      }
+      __syncthreads();
+      // evaluate the next round polynomial on the bound tables (length half): points 0, 2, 3 of A*B*C      (sumcheck.rs:296-355)
+      u256 acc0 = fq_zero(), acc2 = fq_zero(), acc3 = fq_zero();
+      for (size_t task = tid; task < 3 * quarter; task += blockDim.x) {
+        const int p = (int)(task / quarter);
+        const size_t e = task - (size_t)p * quarter;
+        u256 x[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const u256 lo = ld256(T[t] + e), hi = ld256(T[t] + e + quarter);
+          if (p == 0) x[t] = lo;
+          else { const u256 dl = fq_sub(hi, lo); x[t] = fq_add(hi, dl); if (p == 2) x[t] = fq_add(x[t], dl); }
+        }
+        const u256 v = fq_mul(fq_mul(x[0], x[1]), x[2]);
+        if (p == 0) acc0 = fq_add(acc0, v); else if (p == 1) acc2 = fq_add(acc2, v); else acc3 = fq_add(acc3, v);
+      }
+      acc0 = warp_sum_fq(acc0); acc2 = warp_sum_fq(acc2); acc3 = warp_sum_fq(acc3);
+      if (lane == 0) { ws[warp][0] = acc0; ws[warp][1] = acc2; ws[warp][2] = acc3; }
+      __syncthreads();
+      if (warp < 3) {   // warp k finishes value k
+        u256 v = lane < (int)(blockDim.x >> 5) ? ws[lane][warp] : fq_zero();
+        v = warp_sum_fq(v);
+        if (lane == 0) { st256(&out[(size_t)inst * 3 + warp], v); st256(&sig.host_out[(size_t)inst * 3 + warp], v); __threadfence_system(); }
+      }
+    } else {
+      // last bind (L = 2): the heads are the layer's claims (product_tree.rs:330-347)
+      if (tid < 3) {
+        const u256 x0 = ld256(T[tid]), x1 = ld256(T[tid] + 1);
+        const u256 v = fq_add(x0, fq_mul(r, fq_sub(x1, x0)));
+        st256(T[tid], v);
+        st256(&out[(size_t)inst * 3 + tid], v); st256(&sig.host_out[(size_t)inst * 3 + tid], v);
+        __threadfence_system();
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      const unsigned int done = atomicAdd(sig.done, 1u) + 1;
+      if (done == gridDim.x) { *sig.done = 0; __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq + (unsigned int)f; }
+      if (f + 1 < nfold) {   // wait for the host's next challenge
+        wait_flag_sys(&mail->seq, mail_seq0 + (unsigned int)f + 1);
+        s_r = ld256_sys(&mail->r);
+      }
+    }
+    __syncthreads();
+    if (f + 1 < nfold) r = s_r;
+    L = half;
+  }
+}
 struct FoldBatch {
   u256* t[64];
 };
@@ -497,6 +580,16 @@ void fold_top(u256* const* tables, int ntables, size_t len, const u256& r, cudaS
   check("fold_top");
 }
 void fold_top_single(u256* table, size_t len, const u256& r, cudaStream_t s) { u256* t[1] = {table}; fold_top(t, 1, len, r, s); }
+
+
+void sc_persist(const ScInst* insts, int ninst, int n_shared_c, u256* c_scratch, size_t len, const u256& r0, const PersistMail* mail, unsigned int mail_seq0,
+                u256* out, cudaStream_t s, HostSig sig) {
+  ProfScope ps("sc_persist", sc_bytes(insts, ninst, SC_CUBIC3, len, 96.0), s);
+  if (len < 4 || len > SC_PERSIST_MAX_LEN || (len & (len - 1)) || !sig.flag || !sig.done || !sig.host_out) throw std::runtime_error("spartan_b200: sc_persist: bad arguments");
+  ScBatch b; fill_batch(b, insts, ninst);
+  k_sc_persist<<<ninst, 512, 0, s>>>(b, n_shared_c, c_scratch, len, r0, mail, mail_seq0, out, sig);
+  SP_LAUNCHED(); check("sc_persist");
+}
 
 
 }  // namespace dev

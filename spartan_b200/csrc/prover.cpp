@@ -38,6 +38,8 @@ Ctx::Ctx(int dev_) : device(dev_) {
   host_res = reinterpret_cast<u256*>(pinned + (512 << 10));
   host_flag = reinterpret_cast<unsigned int*>(pinned + (768 << 10));
   *host_flag = 0;
+  mail = reinterpret_cast<dev::PersistMail*>(pinned + (900 << 10));
+  memset(mail, 0, sizeof(dev::PersistMail));
   sig_done.alloc(4);
   dev::dzero(sig_done.p, 16, stream);
   small.alloc(4096);

@@ -178,6 +178,10 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
   DevBuf<u256> cpar_a(std::max<size_t>(max_half / 2, 1)), cpar_b(std::max<size_t>(max_half / 2, 1)), d_rand(64), eq_small(2 * ((size_t)1 << ((num_layers + 1) / 2)) + 8);
   DevBuf<u256> cpar0(std::max<size_t>(max_half, 1));
   std::vector<Fq> rand;
+  // persistent tail (dev::sc_persist): once a layer's tables are small, one launch runs all its remaining rounds; A/B switch
+  static const bool persist_on = [] { const char* e = getenv("SP_SC_PERSIST"); return e && atoi(e) != 0; }();
+  DevBuf<u256> persist_c;
+  if (persist_on) persist_c.alloc(np * (size_t)SC_PERSIST_MAX_LEN);
   u256* d_out = ctx.small.p + 64;   // ninst * 3 scalars
   DevBuf<u256> d_heads(64);
   for (size_t layer_id = num_layers; layer_id-- > 0;) {
@@ -226,6 +230,9 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     u256* cin = cpar0.p;
     u256* cpp[2] = {cpar_a.p, cpar_b.p};
     int flip = 0;
+    bool persist = false;
+    unsigned int persist_seq0 = 0;
+    size_t persist_j0 = 0;
     for (size_t j = 0; j < num_rounds; j++) {
       std::vector<Fq> ev(3 * ninst);
       FineTimer fw(ctx, "batched wait evals");
@@ -239,8 +246,28 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
       poly.append_to_transcript("poly", T);
       Fq r_j = T.challenge_scalar("challenge_nextround");
       rand_prod.push_back(r_j);
+      if (persist) {   // the persistent kernel binds (and evaluates the next round) as soon as it sees the challenge
+        ctx.post_challenge(r_j);
+        sig.seq = persist_seq0 + (unsigned int)(j - persist_j0);
+        cur >>= 1;
+        e = poly.evaluate(r_j);
+        lp.proof.compressed_polys.push_back(poly.compress());
+        continue;
+      }
       // bind every table (shared C written once, through a ping-pong buffer)
       for (size_t i = 0; i < np; i++) { insts[i].t[2] = cin; insts[i].c_out = cpp[flip]; }
+      if (persist_on && !sh && j + 1 < num_rounds && cur >= 4 && cur <= SC_PERSIST_MAX_LEN) {
+        // small tables from here on: one launch for all the remaining rounds of this layer, its first bind with r_j
+        const unsigned int nfold = (unsigned int)log2_ceil(cur);
+        sig = ctx.next_sig();
+        ctx.sig_seq += nfold - 1;        // one sequence number per publication: nfold-1 round evaluations, then the bound heads
+        dev::sc_persist(insts.data(), (int)ninst, (int)np, persist_c.p, cur, r_j.m, ctx.mail, ctx.mail_seq, d_out, ctx.stream, sig);
+        persist = true; persist_seq0 = sig.seq; persist_j0 = j;
+        cur >>= 1;
+        e = poly.evaluate(r_j);
+        lp.proof.compressed_polys.push_back(poly.compress());
+        continue;
+      }
       if (j + 1 < num_rounds && sh && cur < Ctx::SHARD_MIN_LOCAL) {
         // leave the sharded stage: bind locally, all-gather every table into replicated copies (in the window), evaluate the next round there
         std::vector<u256*> tabs;
@@ -280,7 +307,8 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     }
     // final claims: first element of every A / B (and C for the dot-product circuits)
     FineTimer fl(ctx, "batched layer tail (claims d2h + transcript)");
-    {  // one gather kernel that also publishes the values to the host (instead of 2-3 tiny copies per instance and a stream synchronise)
+    if (persist) ctx.wait_sig(sig);   // the heads arrive with the persistent kernel's last publication, in the layout of the gather below
+    else {  // one gather kernel that also publishes the values to the host (instead of 2-3 tiny copies per instance and a stream synchronise)
       std::vector<const u256*> hp(3 * ninst);
       for (size_t i = 0; i < ninst; i++) { hp[3 * i] = insts[i].t[0]; hp[3 * i + 1] = insts[i].t[1]; hp[3 * i + 2] = i >= np ? insts[i].t[2] : insts[i].t[0]; }
       dev::HostSig hs = ctx.next_sig();

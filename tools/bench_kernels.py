@@ -23,7 +23,7 @@ def rand_table(n):
     return t
 
 
-res = {"tag": tag, "logn": logn, "constfold": os.environ.get("SP_SC_CONSTFOLD"), "v2": bool(os.environ.get("SP_SC_V2")), "tma": bool(os.environ.get("SP_SC_TMA"))}
+res = {"tag": tag, "logn": logn, "constfold": os.environ.get("SP_SC_CONSTFOLD"), "v2": bool(os.environ.get("SP_SC_V2")), "tma": bool(os.environ.get("SP_SC_TMA")), "persist": bool(os.environ.get("SP_SC_PERSIST"))}
 for kind, nt, name in [(2, 4, "cubic4"), (0, 2, "quad"), (1, 3, "cubic3")]:
     polys = [sb.DensePolynomial(rand_table(n)) for _ in range(nt)]
     r = sb.prg_scalars("r", 1)[0]

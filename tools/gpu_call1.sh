@@ -3,10 +3,11 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/c1_smi.txt 2>&1
 ( timeout 300 tools/probe/probe > gpurun_out/c1_probe.txt 2>&1 )
-for v in nocf cf v2 v2b6 tma tma32; do
+for v in nocf persist cf v2 v2b6 tma tma32; do
   case $v in
-    nocf) export SP_SC_CONSTFOLD=0; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG;;
-    cf) export SP_SC_CONSTFOLD=1; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG;;
+    nocf) export SP_SC_CONSTFOLD=0; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG SP_SC_PERSIST;;
+    persist) export SP_SC_CONSTFOLD=0 SP_SC_PERSIST=1; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG;;
+    cf) export SP_SC_CONSTFOLD=1; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG SP_SC_PERSIST;;
     v2) export SP_SC_CONSTFOLD=1 SP_SC_V2=1; unset SP_SC_TMA SP_LIB_TAG;;
     v2b6) export SP_SC_CONSTFOLD=1 SP_SC_V2=1 SP_LIB_TAG=_v2b6; unset SP_SC_TMA;;
     tma) export SP_SC_CONSTFOLD=1 SP_SC_TMA=1; unset SP_SC_V2 SP_LIB_TAG;;
@@ -14,7 +15,12 @@ for v in nocf cf v2 v2b6 tma tma32; do
   esac
   ( timeout 300 python tools/bench_kernels.py 22 --snark > gpurun_out/c1_kern22_$v.json 2> gpurun_out/c1_kern22_$v.err )
 done
-unset SP_LIB_TAG SP_SC_V2
+unset SP_LIB_TAG SP_SC_V2 SP_SC_CONSTFOLD SP_SC_TMA
+export SP_SC_PERSIST=1
+( timeout 900 python -m pytest tests/test_gpu_snark.py tests/test_gpu_golden.py -m gpu -x -q -k "not 20" > gpurun_out/c1_pytest_persist.txt 2>&1 )
+tail -3 gpurun_out/c1_pytest_persist.txt
+( SP_FINE_TIMERS=1 timeout 300 python tools/profile_snark.py 20 > gpurun_out/c1_profile20_persist.txt 2>&1 )
+unset SP_SC_PERSIST
 export SP_SC_CONSTFOLD=1 SP_SC_TMA=1
 ( timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_golden.py -m gpu -x -q > gpurun_out/c1_pytest_tma.txt 2>&1 )
 ( timeout 600 python -m pytest tests/test_gpu_snark.py -m gpu -x -q -k "bytes_match_oracle and not bench" >> gpurun_out/c1_pytest_tma.txt 2>&1 )
