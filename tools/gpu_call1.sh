@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/c1_smi.txt 2>&1
 ( timeout 300 tools/probe/probe > gpurun_out/c1_probe.txt 2>&1 )
-for v in nocf persist cf v2 v2b6 tma tma32; do
+for v in nocf persist cf v2 tma tma32; do
   case $v in
     nocf) export SP_SC_CONSTFOLD=0; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG SP_SC_PERSIST;;
     persist) export SP_SC_CONSTFOLD=0 SP_SC_PERSIST=1; unset SP_SC_V2 SP_SC_TMA SP_LIB_TAG;;
@@ -23,12 +23,12 @@ tail -3 gpurun_out/c1_pytest_persist.txt
 unset SP_SC_PERSIST
 export SP_SC_CONSTFOLD=1 SP_SC_TMA=1
 ( timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_golden.py -m gpu -x -q > gpurun_out/c1_pytest_tma.txt 2>&1 )
-( timeout 600 python -m pytest tests/test_gpu_snark.py -m gpu -x -q -k "bytes_match_oracle and not bench" >> gpurun_out/c1_pytest_tma.txt 2>&1 )
+( timeout 300 python -m pytest tests/test_gpu_snark.py -m gpu -x -q -k "bytes_match_oracle and not bench and 1024" >> gpurun_out/c1_pytest_tma.txt 2>&1 )
 tail -3 gpurun_out/c1_pytest_tma.txt
 unset SP_SC_TMA
 export SP_SC_CONSTFOLD=1 SP_SC_V2=1
 ( timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_golden.py -m gpu -x -q > gpurun_out/c1_pytest_v2.txt 2>&1 )
-( timeout 600 python -m pytest tests/test_gpu_snark.py -m gpu -x -q -k "bytes_match_oracle and not bench" >> gpurun_out/c1_pytest_v2.txt 2>&1 )
+( timeout 300 python -m pytest tests/test_gpu_snark.py -m gpu -x -q -k "bytes_match_oracle and not bench and 1024" >> gpurun_out/c1_pytest_v2.txt 2>&1 )
 unset SP_SC_V2
 ( timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_golden.py tests/test_gpu_prover.py -m gpu -x -q -k "not large" > gpurun_out/c1_pytest_cf.txt 2>&1 )
 tail -3 gpurun_out/c1_pytest_cf.txt
