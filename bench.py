@@ -40,6 +40,7 @@ UNIT = "constraints/s"
 LOG_N = int(os.environ.get("SP_BENCH_LOGN", "20"))
 NUM_INPUTS = 10
 CPU_SAMPLE_LOG = int(os.environ.get("SP_BENCH_CPU_LOGN", str(LOG_N)))   # the CPU arm proves the SAME configuration as the GPU arm
+SHARDED_LEGS_DEFAULT = "0"   # flipped to "1" once the sharded prover has passed its multi-GPU parity run (tools/run_sharded.py) this round
 CPU_ARM_BUDGET_S = float(os.environ.get("SP_BENCH_CPU_BUDGET_S", "1200"))
 
 
@@ -241,7 +242,9 @@ def run_b200(args):
     import spartan_b200 as sb
     from spartan_b200 import api
     ctx = sb.Context(local if world > 1 else 0)
-    if world > 1:
+    # the intra-proof (strong-scaling) legs need the sharded prover; SP_BENCH_SHARDED=0 leaves them out (replica throughput only)
+    sharded_legs = world > 1 and os.environ.get("SP_BENCH_SHARDED", SHARDED_LEGS_DEFAULT) != "0"
+    if sharded_legs:
         sd.connect(ctx)            # IPC windows over NVLink; sharded proving is switched on only for the `strong` leg below
         ctx.set_sharding(False)
     n = 1 << LOG_N
@@ -360,7 +363,7 @@ def run_b200(args):
                         "what": "largest msm_rows launch of the step: commit_nondet_witness, 2048 rows x 4096 generators (sparse_mlpoly.rs:64-67)"}
     # ---- strong scaling: ONE proof (rank 0's instance: seed 0) sharded over all N GPUs
     strong = None
-    if world > 1 and not args.no_strong:
+    if sharded_legs and not args.no_strong:
         import hashlib
         if rank == 0:
             inst0, inputs0, comm0, dv0 = inst, inputs, comm, d_vars
@@ -395,7 +398,7 @@ def run_b200(args):
                              "streaming rounds, the commitments and the product-circuit layers shard"}
     # ---- BASELINE.json configs[2] and configs[3] at N GPUs (all ranks take part)
     msm_var, dense_sc = None, None
-    if not args.no_msm_var:
+    if not args.no_msm_var and (world == 1 or sharded_legs):
         if world > 1:
             ctx.set_sharding(True)
         try:

@@ -10,5 +10,5 @@ tail -5 gpurun_out/c2_sharded_n${N}_16.txt
 tail -3 gpurun_out/c2_sharded_n${N}_nizk16.txt
 ( timeout 900 $TR --master-port 29603 tools/run_sharded.py --logn 18 20 --golden tests/golden/snark_proof_sha256.json --reps 3 > gpurun_out/c2_sharded_n${N}_18_20.txt 2>&1 )
 tail -4 gpurun_out/c2_sharded_n${N}_18_20.txt
-( timeout 900 $TR --master-port 29604 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/c2_bench_n${N}.json 2> gpurun_out/c2_bench_n${N}.err )
+( SP_BENCH_SHARDED=1 timeout 900 $TR --master-port 29604 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/c2_bench_n${N}.json 2> gpurun_out/c2_bench_n${N}.err )
 tail -c 1500 gpurun_out/c2_bench_n${N}.json; tail -3 gpurun_out/c2_bench_n${N}.err
