@@ -723,6 +723,7 @@ void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u25
   dim3 grid((unsigned)((total + cols - 1) / cols), 2);
   if (wbits == 8) k_ipa_msm<8, GROUPS><<<grid, 128, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
   else if (wbits == 13) k_ipa_msm<13, GROUPS><<<grid, 128, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+  else if (wbits == 15) k_ipa_msm<15, GROUPS><<<grid, 128, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
   else throw std::runtime_error("spartan_b200: unsupported MSM window width");
   SP_LAUNCHED(); check("ipa_msm");
 }
@@ -772,6 +773,7 @@ void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, si
     ge* pp = partial + row0 * chunks;
     if (wbits == 8) msm_launch<8>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
     else if (wbits == 13) msm_launch<13>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
+    else if (wbits == 15) msm_launch<15>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
     else throw std::runtime_error("spartan_b200: unsupported MSM window width");
     SP_LAUNCHED();
   }

@@ -149,10 +149,11 @@ GenSet::GenSet(Ctx* c, const ge* d_points, size_t nbases_, const std::vector<siz
   finish(host_bases);
 }
 void GenSet::finish(const std::vector<size_t>& host_bases) {
-  // large generator sets get 13-bit windows (20 additions per term instead of 32; 7.9 MB of table per generator)
+  // large generator sets get 13-bit windows (20 additions per term instead of 32; 7.9 MB of table per generator); SP_MSM_WINDOW=15 trades
+  // 26.7 MB per generator for 17 additions per term (110 GB for the 4098 generators of a 2^20 SNARK: fits one B200, not a 2^22 one)
   const char* wenv = getenv("SP_MSM_WINDOW");
-  wbits = wenv ? atoi(wenv) : (nbases >= 512 ? 13 : 8);
-  if (wbits != 8 && wbits != 13) throw std::runtime_error("spartan_b200: SP_MSM_WINDOW must be 8 or 13");
+  wbits = nbases >= 512 ? (wenv ? atoi(wenv) : 13) : 8;
+  if (wbits != 8 && wbits != 13 && wbits != 15) throw std::runtime_error("spartan_b200: SP_MSM_WINDOW must be 8, 13 or 15");
   table.alloc(dev::table_entries(nbases, wbits));
   dev::build_tables(table.p, G.p, nbases, wbits, ctx->stream);
   // host copies (8-bit windows) of the few generators the sigma protocols commit against

@@ -35,6 +35,9 @@ tail -3 gpurun_out/c1_pytest_cf.txt
 ( SP_FINE_TIMERS=1 timeout 300 python tools/profile_snark.py 20 > gpurun_out/c1_profile20_cf.txt 2>&1 )
 unset SP_SC_CONSTFOLD
 ( SP_FINE_TIMERS=1 timeout 300 python tools/profile_snark.py 20 > gpurun_out/c1_profile20.txt 2>&1 )
+( SP_MSM_WINDOW=15 timeout 300 python tools/profile_snark.py 20 > gpurun_out/c1_profile20_w15.txt 2>&1 )
+( SP_MSM_WINDOW=15 timeout 300 python -m pytest tests/test_gpu_snark.py -m gpu -x -q -k "bench_configuration and 16" > gpurun_out/c1_pytest_w15.txt 2>&1 )
+tail -2 gpurun_out/c1_pytest_w15.txt
 ( timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/c1_pytest.txt 2>&1 )
 tail -3 gpurun_out/c1_pytest.txt
 tail -3 gpurun_out/c1_pytest_v2.txt
