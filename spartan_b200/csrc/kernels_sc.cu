@@ -461,6 +461,21 @@ size_t sc_scratch_bytes(int ninst) { return 256 + (size_t)ninst * SC_MAX_BLOCKS 
 #ifndef SP_SC_CONSTFOLD_DEFAULT
 #define SP_SC_CONSTFOLD_DEFAULT 0
 #endif
+// which streaming formulation of the fused round: 0 = register-resident (k_sc_fold_eval), 1 = register-lean (k_sc_fold_eval_v2), 2 = TMA-staged
+// (k_sc_fold_eval_tma); SP_SC_VARIANT overrides the default (SP_SC_V2 / SP_SC_TMA are shorthands); 1 and 2 need the constant-multiplier fold
+#ifndef SP_SC_VARIANT_DEFAULT
+#define SP_SC_VARIANT_DEFAULT 0
+#endif
+static bool sc_constfold();
+static int sc_variant() {
+  static const int v = [] {
+    if (const char* e = getenv("SP_SC_VARIANT")) return atoi(e);
+    if (getenv("SP_SC_TMA")) return 2;
+    if (getenv("SP_SC_V2")) return 1;
+    return SP_SC_VARIANT_DEFAULT;
+  }();
+  return sc_constfold() ? v : 0;
+}
 static bool sc_constfold() {
   static const bool on = [] { const char* e = getenv("SP_SC_CONSTFOLD"); return e ? atoi(e) != 0 : SP_SC_CONSTFOLD_DEFAULT != 0; }();
   return on;
@@ -521,7 +536,7 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
     SP_LAUNCHED(); check("sc_fold_eval_small");
     return;
   }
-  static const bool tma = getenv("SP_SC_TMA") != nullptr && cf;   // TMA-staged two-phase formulation (A/B switch)
+  const bool tma = sc_variant() == 2;   // TMA-staged two-phase formulation
   if (tma && len / 4 >= 64 * SC_TMA_TI) {
     const int nt = kind == SC_QUAD ? 2 : kind == SC_CUBIC3 ? 3 : 4;
     const size_t smem = (size_t)2 * nt * 4 * SC_TMA_TI * 32 + 64;
@@ -543,7 +558,7 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
     SP_LAUNCHED(); check("sc_fold_eval_tma");
     return;
   }
-  static const bool v2 = getenv("SP_SC_V2") != nullptr && cf;   // register-lean formulation (A/B switch)
+  const bool v2 = sc_variant() == 1;   // register-lean formulation
   if (v2) {
     dim3 grid(grid_for(len / 4, SC_V2_THREADS, SC_V2_BLOCKS), ninst);
     if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;

@@ -179,7 +179,10 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
   DevBuf<u256> cpar0(std::max<size_t>(max_half, 1));
   std::vector<Fq> rand;
   // persistent tail (dev::sc_persist): once a layer's tables are small, one launch runs all its remaining rounds; A/B switch
-  static const bool persist_on = [] { const char* e = getenv("SP_SC_PERSIST"); return e && atoi(e) != 0; }();
+#ifndef SP_SC_PERSIST_DEFAULT
+#define SP_SC_PERSIST_DEFAULT 0
+#endif
+  static const bool persist_on = [] { const char* e = getenv("SP_SC_PERSIST"); return e ? atoi(e) != 0 : SP_SC_PERSIST_DEFAULT != 0; }();
   DevBuf<u256> persist_c;
   if (persist_on) persist_c.alloc(np * (size_t)SC_PERSIST_MAX_LEN);
   u256* d_out = ctx.small.p + 64;   // ninst * 3 scalars
