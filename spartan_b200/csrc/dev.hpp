@@ -35,6 +35,7 @@ void d2h(void* h, const void* d, size_t bytes, cudaStream_t s);
 void d2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
 void dzero(void* d, size_t bytes, cudaStream_t s);
 int sm_count();
+void mem_info(size_t* free_bytes, size_t* total_bytes);
 // event timing of the kernels launched through these wrappers (bench.py roofline leg)
 void* event_create();
 void event_record(void* ev, cudaStream_t s);

@@ -135,6 +135,7 @@ int sm_count() {
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
   return n;
 }
+void mem_info(size_t* free_bytes, size_t* total_bytes) { ck(cudaMemGetInfo(free_bytes, total_bytes), "cudaMemGetInfo"); }
 void* event_create() { cudaEvent_t e; ck(cudaEventCreate(&e), "cudaEventCreate"); return (void*)e; }
 void event_record(void* ev, cudaStream_t s) { ck(cudaEventRecord((cudaEvent_t)ev, s), "cudaEventRecord"); }
 float event_elapsed_ms(void* a, void* b) {

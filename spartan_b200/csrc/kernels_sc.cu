@@ -459,7 +459,7 @@ size_t sc_scratch_bytes(int ninst) { return 256 + (size_t)ninst * SC_MAX_BLOCKS 
 
 // A/B switch for the constant-multiplier fold (tools/bench_kernels.py): SP_SC_CONSTFOLD=0/1 overrides the default
 #ifndef SP_SC_CONSTFOLD_DEFAULT
-#define SP_SC_CONSTFOLD_DEFAULT 0
+#define SP_SC_CONSTFOLD_DEFAULT 1   // measured on the B200 (profiles/r02_tuning.md): cubic-4 2^22 round 366 -> 311 us, parity suite green
 #endif
 // which streaming formulation of the fused round: 0 = register-resident (k_sc_fold_eval), 1 = register-lean (k_sc_fold_eval_v2), 2 = TMA-staged
 // (k_sc_fold_eval_tma); SP_SC_VARIANT overrides the default (SP_SC_V2 / SP_SC_TMA are shorthands); 1 and 2 need the constant-multiplier fold

@@ -152,7 +152,18 @@ void GenSet::finish(const std::vector<size_t>& host_bases) {
   // large generator sets get 13-bit windows (20 additions per term instead of 32; 7.9 MB of table per generator); SP_MSM_WINDOW=15 trades
   // 26.7 MB per generator for 17 additions per term (110 GB for the 4098 generators of a 2^20 SNARK: fits one B200, not a 2^22 one)
   const char* wenv = getenv("SP_MSM_WINDOW");
-  wbits = nbases >= 512 ? (wenv ? atoi(wenv) : 13) : 8;
+  if (nbases < 512) wbits = 8;
+  else if (wenv) wbits = atoi(wenv);
+  else {
+    // 15-bit windows for the big SPARK generator set when the table fits comfortably in what is free now (measured: msm_rows 14.3 -> 13.1 ms per
+    // 2^20 proof); the 1026-generator witness set stays at 13 bits (its tables would triple for 0.3 ms)
+    wbits = 13;
+    if (nbases >= 2048) {
+      size_t free_b = 0, total_b = 0;
+      dev::mem_info(&free_b, &total_b);
+      if ((double)dev::table_entries(nbases, 15) * sizeof(ge_niels) <= 0.65 * (double)free_b) wbits = 15;
+    }
+  }
   if (wbits != 8 && wbits != 13 && wbits != 15) throw std::runtime_error("spartan_b200: SP_MSM_WINDOW must be 8, 13 or 15");
   table.alloc(dev::table_entries(nbases, wbits));
   dev::build_tables(table.p, G.p, nbases, wbits, ctx->stream);
