@@ -54,8 +54,10 @@ def build(force=False, verbose=False):
         if p.wait() != 0:
             raise RuntimeError("build failed: " + " ".join(cmd))
     if force or procs or _stale(OUT, objs):
-        cmd = [NVCC, "-ccbin", CXX] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs
+        # link next to the target and rename: a snapshot of the tree (gpurun) never sees a half-written library
+        cmd = [NVCC, "-ccbin", CXX] + ARCH + ["-shared", "-cudart", "static", "-o", OUT + ".tmp"] + objs
         subprocess.check_call(cmd)
+        os.replace(OUT + ".tmp", OUT)
     with open(stamp, "w") as f:
         f.write(flags)
     return OUT

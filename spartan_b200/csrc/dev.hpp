@@ -101,9 +101,11 @@ void sc_fold_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, con
 // the next challenge from the transcript.  After the last bind it publishes the bound heads A[0], B[0], C[0] instead.  No launch, no cold
 // caches and no kernel drain between rounds: a round costs the PCIe round trip plus a few microseconds of arithmetic.
 struct PersistMail { u256 r; unsigned int seq; unsigned int pad[7]; };
-#define SC_PERSIST_MAX_LEN 4096
+// One CTA (one SM) per instance: worth it only while a round is latency, not throughput (<= 256 entries: one bind task per thread)
+#define SC_PERSIST_MAX_LEN 256
+// dmail: a device-memory copy of the mailbox (zero-initialised, reused across launches): only CTA 0 polls the host over PCIe and forwards the challenge
 void sc_persist(const ScInst* insts, int ninst, int n_shared_c /* instances [0, n_shared_c) read the shared C table */, u256* c_scratch /* n_shared_c * len */,
-                size_t len, const u256& r0, const PersistMail* mail, unsigned int mail_seq0, u256* out, cudaStream_t s, HostSig sig);
+                size_t len, const u256& r0, const PersistMail* mail, PersistMail* dmail, unsigned int mail_seq0, u256* out, cudaStream_t s, HostSig sig);
 // fold only (bound_poly_var_top, dense_mlpoly.rs:215-223): tables[k][i] += r*(tables[k][i+len/2]-tables[k][i])
 void fold_top(u256* const* d_tables, int ntables, size_t len, const u256& r, cudaStream_t s);
 void fold_top_single(u256* table, size_t len, const u256& r, cudaStream_t s);

@@ -101,6 +101,7 @@ struct Ctx {
   void wait_sig(const dev::HostSig& s);   // spins on the flag; falls back to a stream synchronise to surface CUDA errors
   // host -> persistent-kernel mailbox (dev::sc_persist): the next challenge and its sequence number, in mapped pinned memory
   dev::PersistMail* mail = nullptr;
+  DevBuf<dev::PersistMail> dmail;      // device-side copy the polling CTA forwards the challenge through
   unsigned int mail_seq = 0;
   void post_challenge(const Fq& r) {
     memcpy((void*)&mail->r, &r.m, sizeof(u256));

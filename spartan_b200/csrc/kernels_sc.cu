@@ -358,15 +358,21 @@ __global__ void __launch_bounds__(SC_SMALL_Q * 8) k_sc_fold_eval_small(ScBatch b
 }
 
 // ---- persistent tail (dev.hpp: sc_persist)
-__device__ __forceinline__ u256 ld256_sys(const u256* p) {   // mapped host memory: volatile, never cached in L1
-  const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(p);
+__device__ __forceinline__ u256 ld256_sys(const u256* p) {   // mapped host memory: two 16-byte volatile loads (two PCIe reads), never cached
   u256 r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = q[i];
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%8];\n\tld.volatile.global.v4.u32 {%4, %5, %6, %7}, [%8+16];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p)
+               : "memory");
   return r;
 }
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __global__ void __launch_bounds__(512) k_sc_persist(ScBatch batch, int n_shared_c, u256* c_scratch, size_t len, const u256 r0, const PersistMail* mail,
-                                                    unsigned int mail_seq0, u256* out, HostSig sig) {
+                                                    PersistMail* dmail, unsigned int mail_seq0, u256* out, HostSig sig) {
   __shared__ u256 ws[16][3];
   __shared__ u256 s_r;
   const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -430,9 +436,19 @@ __global__ void __launch_bounds__(512) k_sc_persist(ScBatch batch, int n_shared_
       __threadfence_system();
       const unsigned int done = atomicAdd(sig.done, 1u) + 1;
       if (done == gridDim.x) { *sig.done = 0; __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq + (unsigned int)f; }
-      if (f + 1 < nfold) {   // wait for the host's next challenge
-        wait_flag_sys(&mail->seq, mail_seq0 + (unsigned int)f + 1);
-        s_r = ld256_sys(&mail->r);
+      if (f + 1 < nfold) {   // wait for the host's next challenge: CTA 0 polls the host mailbox over PCIe and forwards it through device memory
+        const unsigned int want = mail_seq0 + (unsigned int)f + 1;
+        if (inst == 0) {
+          wait_flag_sys(&mail->seq, want);
+          s_r = ld256_sys(&mail->r);
+          if (gridDim.x > 1) { st256(&dmail->r, s_r); __threadfence(); *((volatile unsigned int*)&dmail->seq) = want; }
+        } else {
+          const unsigned long long t0 = global_timer_ns();
+          unsigned int spins = 0;
+          while ((int)(ld_acquire_gpu(&dmail->seq) - want) < 0)
+            if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 30000000000ull) __trap();
+          s_r = ld256_cg(&dmail->r);
+        }
       }
     }
     __syncthreads();
@@ -597,12 +613,12 @@ void fold_top(u256* const* tables, int ntables, size_t len, const u256& r, cudaS
 void fold_top_single(u256* table, size_t len, const u256& r, cudaStream_t s) { u256* t[1] = {table}; fold_top(t, 1, len, r, s); }
 
 
-void sc_persist(const ScInst* insts, int ninst, int n_shared_c, u256* c_scratch, size_t len, const u256& r0, const PersistMail* mail, unsigned int mail_seq0,
-                u256* out, cudaStream_t s, HostSig sig) {
+void sc_persist(const ScInst* insts, int ninst, int n_shared_c, u256* c_scratch, size_t len, const u256& r0, const PersistMail* mail, PersistMail* dmail,
+                unsigned int mail_seq0, u256* out, cudaStream_t s, HostSig sig) {
   ProfScope ps("sc_persist", sc_bytes(insts, ninst, SC_CUBIC3, len, 96.0), s);
   if (len < 4 || len > SC_PERSIST_MAX_LEN || (len & (len - 1)) || !sig.flag || !sig.done || !sig.host_out) throw std::runtime_error("spartan_b200: sc_persist: bad arguments");
   ScBatch b; fill_batch(b, insts, ninst);
-  k_sc_persist<<<ninst, 512, 0, s>>>(b, n_shared_c, c_scratch, len, r0, mail, mail_seq0, out, sig);
+  k_sc_persist<<<ninst, 512, 0, s>>>(b, n_shared_c, c_scratch, len, r0, mail, dmail, mail_seq0, out, sig);
   SP_LAUNCHED(); check("sc_persist");
 }
 

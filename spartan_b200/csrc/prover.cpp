@@ -40,6 +40,8 @@ Ctx::Ctx(int dev_) : device(dev_) {
   *host_flag = 0;
   mail = reinterpret_cast<dev::PersistMail*>(pinned + (900 << 10));
   memset(mail, 0, sizeof(dev::PersistMail));
+  dmail.alloc(1);
+  dev::dzero(dmail.p, sizeof(dev::PersistMail), stream);
   sig_done.alloc(4);
   dev::dzero(sig_done.p, 16, stream);
   small.alloc(4096);
@@ -57,7 +59,7 @@ void Ctx::comm_create() {
 }
 Ctx::~Ctx() {
   try { sync(); } catch (...) {}
-  scratch.release(); red.release(); small.release();
+  scratch.release(); red.release(); small.release(); dmail.release();
   if (ev_a) { dev::event_destroy(ev_a); dev::event_destroy(ev_b); }
   dev::hfree_pinned(pinned);
   dev::stream_destroy(stream);

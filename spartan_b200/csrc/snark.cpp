@@ -264,7 +264,7 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
         const unsigned int nfold = (unsigned int)log2_ceil(cur);
         sig = ctx.next_sig();
         ctx.sig_seq += nfold - 1;        // one sequence number per publication: nfold-1 round evaluations, then the bound heads
-        dev::sc_persist(insts.data(), (int)ninst, (int)np, persist_c.p, cur, r_j.m, ctx.mail, ctx.mail_seq, d_out, ctx.stream, sig);
+        dev::sc_persist(insts.data(), (int)ninst, (int)np, persist_c.p, cur, r_j.m, ctx.mail, ctx.dmail.p, ctx.mail_seq, d_out, ctx.stream, sig);
         persist = true; persist_seq0 = sig.seq; persist_j0 = j;
         cur >>= 1;
         e = poly.evaluate(r_j);

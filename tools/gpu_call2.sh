@@ -12,3 +12,9 @@ tail -3 gpurun_out/c2_sharded_n${N}_nizk16.txt
 tail -4 gpurun_out/c2_sharded_n${N}_18_20.txt
 ( SP_BENCH_SHARDED=1 timeout 900 $TR --master-port 29604 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/c2_bench_n${N}.json 2> gpurun_out/c2_bench_n${N}.err )
 tail -c 1500 gpurun_out/c2_bench_n${N}.json; tail -3 gpurun_out/c2_bench_n${N}.err
+# piggy-back (one process, GPU 0): persistent-tail v2 of the small batched rounds
+( SP_SC_PERSIST=1 timeout 300 python -m pytest tests/test_gpu_snark.py tests/test_gpu_golden.py -m gpu -x -q -k "not 20" > gpurun_out/c2_pytest_persist.txt 2>&1 )
+tail -2 gpurun_out/c2_pytest_persist.txt
+( SP_SC_PERSIST=1 SP_FINE_TIMERS=1 timeout 300 python tools/profile_snark.py 20 > gpurun_out/c2_profile20_persist.txt 2>&1 )
+( SP_FINE_TIMERS=1 timeout 300 python tools/profile_snark.py 20 > gpurun_out/c2_profile20.txt 2>&1 )
+grep -E "SNARK 2|sc_persist|sc_fold_eval" gpurun_out/c2_profile20_persist.txt gpurun_out/c2_profile20.txt
