@@ -40,7 +40,7 @@ UNIT = "constraints/s"
 LOG_N = int(os.environ.get("SP_BENCH_LOGN", "20"))
 NUM_INPUTS = 10
 CPU_SAMPLE_LOG = int(os.environ.get("SP_BENCH_CPU_LOGN", str(LOG_N)))   # the CPU arm proves the SAME configuration as the GPU arm
-SHARDED_LEGS_DEFAULT = "0"   # flipped to "1" once the sharded prover has passed its multi-GPU parity run (tools/run_sharded.py) this round
+SHARDED_LEGS_DEFAULT = "1"   # the sharded prover passed its multi-GPU parity runs (tools/run_sharded.py; profiles/r02_sharded.md)
 CPU_ARM_BUDGET_S = float(os.environ.get("SP_BENCH_CPU_BUDGET_S", "1200"))
 
 
@@ -328,7 +328,8 @@ def run_b200(args):
         roof = rl("sc_fold_eval", fold) if fold else None
         if roof:
             roof["note"] = ("algorithmic bytes = 48 B x len per table per launch (read len*32, write len/2*32); CUDA-event time per launch on the prover stream; "
-                            "ncu --set full of the same kernel: profiles/r01_ncu_full_sc_fold_eval.txt")
+                            "ncu --set full of the same kernel: profiles/r02_ncu_full_sc_fold_eval.txt; the multiplications are FMA-pipe bound (IMAD.WIDE at quarter rate, "
+                            "profiles/r02_tuning.md section 1): the pipe ceiling of the cubic-4 round is ~0.55 of the HBM copy bandwidth")
         if roof:
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's first launch of a step, from the committed ncu capture (written by
             # tools/ncu_summary.py full ... --json); null when no capture of the current build is committed
