@@ -41,6 +41,9 @@ LOG_N = int(os.environ.get("SP_BENCH_LOGN", "20"))
 NUM_INPUTS = 10
 CPU_SAMPLE_LOG = int(os.environ.get("SP_BENCH_CPU_LOGN", str(LOG_N)))   # the CPU arm proves the SAME configuration as the GPU arm
 SHARDED_LEGS_DEFAULT = "1"   # the sharded prover passed its multi-GPU parity runs (tools/run_sharded.py; profiles/r02_sharded.md)
+# world sizes at which the sharded prover has been byte-validated on hardware (profiles/r02_sharded.md).  At any other N the sharded legs stay off
+# unless SP_BENCH_SHARDED=1 forces them: an unvalidated collective that stalls would take the whole bench line (the replica throughput) down with it.
+SHARDED_VALIDATED_WORLDS = (2,)
 CPU_ARM_BUDGET_S = float(os.environ.get("SP_BENCH_CPU_BUDGET_S", "1200"))
 
 
@@ -243,7 +246,8 @@ def run_b200(args):
     from spartan_b200 import api
     ctx = sb.Context(local if world > 1 else 0)
     # the intra-proof (strong-scaling) legs need the sharded prover; SP_BENCH_SHARDED=0 leaves them out (replica throughput only)
-    sharded_legs = world > 1 and os.environ.get("SP_BENCH_SHARDED", SHARDED_LEGS_DEFAULT) != "0"
+    sharded_env = os.environ.get("SP_BENCH_SHARDED")
+    sharded_legs = world > 1 and (sharded_env == "1" or (sharded_env is None and SHARDED_LEGS_DEFAULT != "0" and world in SHARDED_VALIDATED_WORLDS))
     if sharded_legs:
         sd.connect(ctx)            # IPC windows over NVLink; sharded proving is switched on only for the `strong` leg below
         ctx.set_sharding(False)
@@ -364,6 +368,8 @@ def run_b200(args):
                         "what": "largest msm_rows launch of the step: commit_nondet_witness, 2048 rows x 4096 generators (sparse_mlpoly.rs:64-67)"}
     # ---- strong scaling: ONE proof (rank 0's instance: seed 0) sharded over all N GPUs
     strong = None
+    if world > 1 and not sharded_legs:
+        strong = {"skipped": "sharded legs are on by default only at the world sizes validated on hardware %s; SP_BENCH_SHARDED=1 forces them" % (SHARDED_VALIDATED_WORLDS,)}
     if sharded_legs and not args.no_strong:
         import hashlib
         if rank == 0:

@@ -436,7 +436,7 @@ int sp_ipa_begin(sp_ctx* ctx, const sp_gens* gens, const sp_poly* a_vec, const s
   dev::d2d(h->a.p, a_vec->d.p, n * sizeof(u256), ctx->c.stream);
   dev::d2d(h->b.p, b_vec->d.p, n * sizeof(u256), ctx->c.stream);
   dev::fill_one(h->svec.p, n, ctx->c.stream);
-  ctx->c.ensure_scratch(dev::msm_scratch_bytes(4, n) + 64);
+  ctx->c.ensure_scratch(std::max(dev::msm_scratch_bytes(4, n), dev::ipa_msm_scratch_points(n, gens->set->wbits) * sizeof(sp::ge)) + 64);
   ctx->c.sync();
   *out = h.release();
   SP_CATCH(ctx)

@@ -19,6 +19,8 @@ void check(const char* what);  // throws std::runtime_error on a pending CUDA er
 int device_count();
 void set_device(int dev);
 cudaStream_t stream_create();
+cudaStream_t stream_create_prio(int level);   // > 0: greatest priority of the device, < 0: least
+void stream_wait_event(cudaStream_t s, void* ev);
 void stream_destroy(cudaStream_t s);
 void stream_sync(cudaStream_t s);
 void* dmalloc(size_t bytes);
@@ -172,12 +174,16 @@ void build_tables(ge_niels* table, const ge* G, size_t nbases, int wbits, cudaSt
 // out[row] = sum_{j<R} scalars[row*stride + j] * G_j  (+ blinds[row] * G_{blind_base} when blinds != null)
 // scalars are Montgomery-form; partial: scratch >= msm_scratch_bytes(L, R)
 size_t msm_scratch_bytes(size_t L, size_t R);
+// launch shape overrides for an MSM that runs in the background of latency-bound work: cpt = column passes per CTA (0: automatic, 1 or 4: short- or
+// long-lived CTAs), smem_pad = bytes of unused dynamic shared memory per CTA (caps the resident CTAs per SM)
+struct MsmTune { int cpt = 0; size_t smem_pad = 0; };
 void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
-              void* scratch, cudaStream_t s);
+              void* scratch, cudaStream_t s, const MsmTune& tune = MsmTune());
 
 void sum_points(ge* out, const ge* in, int n, cudaStream_t s);   // out[0] = in[0] + ... + in[n-1], n <= 32
 // both MSMs of an inner-product round (L, R -> out[0], out[1]) over unfolded generators: scalar of generator j is a[.]*svec[j].
-// scratch >= 2 * ceil(n_full/32) points; ticket: one zero-initialised word (self-resetting)
+// scratch >= ipa_msm_scratch_points(n_full, wbits) points; ticket: one zero-initialised word (self-resetting)
+size_t ipa_msm_scratch_points(size_t n_full, int wbits);
 void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
              cudaStream_t s, HostSig sig = HostSig());
 

@@ -78,7 +78,12 @@ struct Ctx {
   // a table of `global_len` elements is worth sharding when every rank keeps at least one streaming-size fused round (see sc_fold_eval)
   static constexpr size_t SHARD_MIN_LOCAL = 8192;
   bool shard_table(size_t global_len) const { return shard_world() > 1 && global_len >= 2 * SHARD_MIN_LOCAL * (size_t)shard_world(); }
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // the prover's stream (greatest priority: its kernels are short and the transcript waits for each of them)
+  // background stream (least priority) for throughput work whose inputs are known early and whose result the transcript needs late: the commitment
+  // to the dereferenced SPARK values runs there under the second sumcheck phase and the witness evaluation proof (snark.cpp)
+  cudaStream_t stream2 = nullptr;
+  void* ev_fork = nullptr; void* ev_join = nullptr;
+  DevBuf<uint8_t> scratch2;        // MSM partial sums of the background stream
   uint8_t* pinned = nullptr;       // staging for small host<->device exchanges
   size_t pinned_bytes = 0;
   DevBuf<uint8_t> scratch;         // MSM partial sums (growable)

@@ -74,6 +74,15 @@ static void ck(cudaError_t e, const char* what) {
 int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 void set_device(int d) { ck(cudaSetDevice(d), "cudaSetDevice"); }
 cudaStream_t stream_create() { cudaStream_t s; ck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate"); return s; }
+// level > 0: the device's greatest priority (the transcript-serialised stream of small kernels), level < 0: its least (background MSMs)
+cudaStream_t stream_create_prio(int level) {
+  int least = 0, greatest = 0;
+  ck(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange");
+  cudaStream_t s;
+  ck(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, level > 0 ? greatest : (level < 0 ? least : (least + greatest) / 2)), "cudaStreamCreateWithPriority");
+  return s;
+}
+void stream_wait_event(cudaStream_t s, void* ev) { ck(cudaStreamWaitEvent(s, (cudaEvent_t)ev, 0), "cudaStreamWaitEvent"); }
 void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
 void stream_sync(cudaStream_t s) { ck(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
 void* dmalloc(size_t b) { void* p = nullptr; ck(cudaMalloc(&p, b ? b : 16), "cudaMalloc"); return p; }
@@ -716,9 +725,184 @@ __global__ void __launch_bounds__(128, SP_IPA_LB) k_ipa_msm(ge* partial, const g
     if (sig.flag) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
   }
 }
+// ---- quad-lane point arithmetic for latency-bound reductions.
+// A lone warp gains nothing from the four independent field products of a point addition (profiles/r02_probe_latency.txt: 4473 cycles = 9 products
+// back to back), so a reduction tree of point additions costs 2.3 us per level.  Here FOUR LANES share one point — lane c of a quad holds coordinate
+// c (0: X, 1: Y, 2: Z, 3: T) — and run the products of add-2008-hwcd-3 side by side: three product latencies per addition (A | B | Z1 Z2 | T1 T2, then
+// 2d on the T lane, then X3 | Y3 | Z3 | T3) and a few 8-word shuffles instead of nine products in a row.  Same formulas, same field values as
+// ge_add / ge_madd; every lane of the warp must take part in every call (full-mask shuffles).
+__device__ __forceinline__ u256 shfl_idx_256(const u256& x, int src) {
+  u256 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, x.v[i], src);
+  return r;
+}
+__device__ __forceinline__ u256 shfl_xor_256(const u256& x, int m) {
+  u256 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, x.v[i], m);
+  return r;
+}
+__device__ __forceinline__ u256 quad_identity(int c) { return (c == 1 || c == 2) ? fp_one() : fp_zero(); }
+// coordinates -> operands of the first products: lane 0: Y - X, lane 1: Y + X, lane 2: Z, lane 3: T
+__device__ __forceinline__ u256 quad_prep(const u256& v, int c) {
+  const u256 o = shfl_xor_256(v, 1);
+  if (c == 0) return fp_sub(o, v);
+  if (c == 1) return fp_add(v, o);
+  return v;
+}
+// m = (A, B, D, C) on lanes 0..3  ->  the sum's coordinates (X3, Y3, Z3, T3) on lanes 0..3
+static __device__ __noinline__ u256 quad_finish(u256 m, int c, int lane) {
+  const u256 o = shfl_xor_256(m, 1);                       // lane 0 <- B, lane 1 <- A, lane 2 <- C, lane 3 <- D
+  u256 w;
+  if (c == 0) w = fp_sub(o, m);                            // E = B - A
+  else if (c == 1) w = fp_add(m, o);                       // H = B + A
+  else if (c == 2) w = fp_sub(m, o);                       // F = D - C
+  else w = fp_add(o, m);                                   // G = D + C
+  const int base = lane & ~3;
+  const u256 x = shfl_idx_256(w, base + ((0x2031 >> (4 * c)) & 3));   // lane 0 (E) <- H, lane 1 (H) <- G, lane 2 (F) <- E, lane 3 (G) <- F
+  const u256 r = fp_mul(w, x);                             // lane 0: T3 = E H, lane 1: Y3 = H G, lane 2: X3 = F E, lane 3: Z3 = G F
+  return shfl_idx_256(r, base + ((0x0312 >> (4 * c)) & 3));            // lane 0 <- X3 (lane 2), lane 1: Y3, lane 2 <- Z3 (lane 3), lane 3 <- T3 (lane 0)
+}
+static __device__ __noinline__ u256 quad_add(u256 p, u256 q, int c, int lane) {   // P + Q (ge_add)
+  const u256 up = quad_prep(p, c), uq = quad_prep(q, c);
+  u256 m = fp_mul(up, uq);                                 // A | B | Z1 Z2 | T1 T2
+  if (c == 3) m = fp_mul(m, fp_2D());                      // C
+  else if (c == 2) m = fp_add(m, m);                       // D
+  return quad_finish(m, c, lane);
+}
+// P + q for an affine niels operand given per lane as (y - x, y + x, -, 2d x y) of +/-q (ge_madd)
+__device__ __forceinline__ u256 quad_madd(const u256& p, const u256& nq, int c, int lane) {
+  const u256 up = quad_prep(p, c);
+  u256 m;
+  if (c == 2) m = fp_add(up, up);                          // D = 2 Z1
+  else m = fp_mul(up, nq);                                 // A | B | C
+  return quad_finish(m, c, lane);
+}
+// sum over the 8 quads of a warp -> quad 0
+__device__ __forceinline__ u256 quad_warp_sum(u256 P, int c, int lane) {
+#pragma unroll 1
+  for (int d = 16; d >= 4; d >>= 1) P = quad_add(P, shfl_down_256(P, d), c, lane);
+  return P;
+}
+// Both MSMs of an inner-product round, quad-lane formulation of k_ipa_msm (same inputs, same outputs).  grid = (chunks, 2 sides), 512 threads =
+// 128 quads; a quad owns two adjacent windows (2p, 2p+1) of one scalar: the first table entry is lifted to extended coordinates (one product:
+// (4x, 4y, 4, 4xy) from y+x, y-x), the second joins by a mixed addition, then 3 tree levels inside the warp, 4 across the 16 warps, and the last
+// block to finish sums the blocks' partial points of both sides: ~17 dependent quad additions of ~1 us instead of ~19 additions of 2.3 us.
+template <int WBITS>
+__global__ void __launch_bounds__(512, 2) k_ipa_msm_quad(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ a, const u256* __restrict__ sv,
+                                                         size_t n_cur, size_t n_full, unsigned int* ticket, ge* out, HostSig sig) {
+  constexpr int NWIN = (253 + WBITS - 1) / WBITS;
+  constexpr int QPS = (NWIN + 1) / 2;                      // quads per scalar
+  constexpr uint32_t HALF = 1u << (WBITS - 1);
+  constexpr size_t DEPTH = (size_t)1 << (WBITS - 1);
+  const int side = blockIdx.y, tid = threadIdx.x, lane = tid & 31, c = lane & 3, warp = tid >> 5;
+  const size_t half = n_cur >> 1, total = n_full >> 1;
+  const size_t gq = (size_t)blockIdx.x * 128 + (tid >> 2);
+  const size_t t = gq / QPS;
+  const int w0 = 2 * (int)(gq - t * QPS);
+  u256 P = quad_identity(c);
+  u256 nq = c == 3 ? fp_zero() : fp_one();                 // the identity as a niels operand
+  if (t < total) {                                         // uniform inside a quad; no shuffles in here
+    const size_t blk = t / half, off = t - blk * half;
+    const size_t j = blk * n_cur + off + (side == 0 ? half : 0);
+    u256 k = fq_mul(ld256_ro(a + (side == 0 ? off : off + half)), ld256_ro(sv + j));
+    if (!fq_is_zero(k)) {
+      k = fq_from_mont(k);
+      uint32_t carry = 0;
+      for (int w = 0; w < w0; w++) carry = (msm_window<WBITS>(k, w) + carry) > HALF ? 1u : 0u;
+      const ge_niels* tb = table + (j * NWIN + (size_t)w0) * DEPTH;
+      {
+        uint32_t v = msm_window<WBITS>(k, w0) + carry;
+        int d;
+        if (v > HALF) { d = (int)v - (int)(2 * HALF); carry = 1; } else { d = (int)v; carry = 0; }
+        if (d != 0) {
+          const ge_niels* e = tb + ((d < 0 ? -d : d) - 1);
+          const u256 pl = ld256_ro(d < 0 ? &e->ymx : &e->ypx), mi = ld256_ro(d < 0 ? &e->ypx : &e->ymx);   // y + x, y - x of +/-q
+          if (c == 0) { u256 x = fp_sub(pl, mi); P = fp_add(x, x); }            // 4x
+          else if (c == 1) { u256 y = fp_add(pl, mi); P = fp_add(y, y); }       // 4y
+          else if (c == 2) { P = fp_zero(); P.v[0] = 4; }                       // 4
+          else P = fp_mul(fp_sub(pl, mi), fp_add(pl, mi));                      // 4xy
+        }
+      }
+      if (w0 + 1 < NWIN) {
+        uint32_t v = msm_window<WBITS>(k, w0 + 1) + carry;
+        int d = v > HALF ? (int)v - (int)(2 * HALF) : (int)v;
+        if (d != 0) {
+          const ge_niels* e = tb + DEPTH + ((d < 0 ? -d : d) - 1);
+          if (c == 0) nq = ld256_ro(d < 0 ? &e->ypx : &e->ymx);
+          else if (c == 1) nq = ld256_ro(d < 0 ? &e->ymx : &e->ypx);
+          else if (c == 3) { nq = ld256_ro(&e->t2d); if (d < 0) nq = fp_neg(nq); }
+        }
+      }
+    }
+  }
+  P = quad_madd(P, nq, c, lane);
+  P = quad_warp_sum(P, c, lane);
+  __shared__ u256 sm[16][4];
+  __shared__ bool is_last;
+  if (lane < 4) sm[warp][c] = P;
+  __syncthreads();
+  if (warp == 0) {
+    const int q = lane >> 2;
+    P = quad_add(sm[q][c], sm[q + 8][c], c, lane);
+    P = quad_warp_sum(P, c, lane);
+    if (lane < 4) { st256(reinterpret_cast<u256*>(partial + (size_t)side * gridDim.x + blockIdx.x) + c, P); __threadfence(); }
+    __syncwarp();
+    if (lane == 0) is_last = atomicAdd(ticket, 1u) == 2 * gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last block: quads 0..63 finish L, 64..127 finish R
+  const int s2 = tid >> 8, qq = (tid >> 2) & 63;
+  const unsigned int nparts = gridDim.x;
+  P = quad_identity(c);
+  for (unsigned int base = 0; base < nparts; base += 64) {   // same trip count for every quad; out-of-range slots contribute the identity
+    const unsigned int idx = base + qq;
+    u256 Q = quad_identity(c);
+    if (idx < nparts) Q = ld256_cg(reinterpret_cast<const u256*>(partial + (size_t)s2 * nparts + idx) + c);
+    P = base == 0 ? Q : quad_add(P, Q, c, lane);
+  }
+  P = quad_warp_sum(P, c, lane);
+  if (lane < 4) sm[warp][c] = P;
+  __syncthreads();
+  if (warp == 0 || warp == 8) {
+    const int q = lane >> 2;
+    P = quad_warp_sum(sm[warp + q][c], c, lane);
+    if (lane < 4) {
+      st256(reinterpret_cast<u256*>(out + s2) + c, P);
+      if (sig.host_out) { st256(sig.host_out + 4 * s2 + c, P); __threadfence_system(); }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *ticket = 0;
+    if (sig.flag) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
+  }
+}
+#ifndef SP_IPA_QUAD_DEFAULT
+#define SP_IPA_QUAD_DEFAULT 1
+#endif
+size_t ipa_msm_scratch_points(size_t n_full, int wbits) {   // partial points of either formulation
+  const size_t nwin = (size_t)msm_nwin(wbits), total = n_full / 2;
+  const size_t quad_chunks = (total * ((nwin + 1) / 2) + 127) / 128, plain_chunks = (total + 15) / 16;
+  return 2 * std::max(quad_chunks, plain_chunks);
+}
 void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
              cudaStream_t s, HostSig sig) {
   ProfScope ps("ipa_msm", 64.0 * (double)n_full, s);
+  static const bool quad = [] { const char* e = getenv("SP_IPA_QUAD"); return e ? atoi(e) != 0 : SP_IPA_QUAD_DEFAULT != 0; }();
+  if (quad) {
+    const size_t nwin = (size_t)msm_nwin(wbits), quads = (n_full / 2) * ((nwin + 1) / 2);
+    dim3 grid((unsigned)((quads + 127) / 128), 2);
+    if (wbits == 8) k_ipa_msm_quad<8><<<grid, 512, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+    else if (wbits == 13) k_ipa_msm_quad<13><<<grid, 512, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+    else if (wbits == 15) k_ipa_msm_quad<15><<<grid, 512, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+    else throw std::runtime_error("spartan_b200: unsupported MSM window width");
+    SP_LAUNCHED(); check("ipa_msm_quad");
+    return;
+  }
   constexpr int GROUPS = 8;
   const size_t cols = 128 / GROUPS, total = n_full / 2;
   dim3 grid((unsigned)((total + cols - 1) / cols), 2);
@@ -747,24 +931,33 @@ static size_t msm_chunks(size_t R1, int groups, int cpt) { size_t cols = (128 / 
 size_t msm_scratch_bytes(size_t L, size_t R) { return L * msm_chunks(R + 1, 8, 1) * sizeof(ge); }
 template <int WBITS, int GROUPS>
 static void msm_launch2(int cpt, dim3 grid, cudaStream_t s, ge* pp, const ge_niels* table, const u256* sc, size_t stride, size_t R, const u256* bl,
-                        size_t blind_base) {
-  if (cpt == 4) k_msm_rows<WBITS, GROUPS, 4><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
-  else k_msm_rows<WBITS, GROUPS, 1><<<grid, 128, 0, s>>>(pp, table, sc, stride, R, bl, blind_base);
+                        size_t blind_base, size_t smem_pad) {
+  // smem_pad: unused dynamic shared memory that only lowers the number of resident CTAs per SM (a background MSM leaves room for the
+  // latency-bound kernels of the main stream)
+  if (cpt == 4) {
+    if (smem_pad > (48u << 10)) cudaFuncSetAttribute(k_msm_rows<WBITS, GROUPS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pad);
+    k_msm_rows<WBITS, GROUPS, 4><<<grid, 128, smem_pad, s>>>(pp, table, sc, stride, R, bl, blind_base);
+  } else {
+    if (smem_pad > (48u << 10)) cudaFuncSetAttribute(k_msm_rows<WBITS, GROUPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pad);
+    k_msm_rows<WBITS, GROUPS, 1><<<grid, 128, smem_pad, s>>>(pp, table, sc, stride, R, bl, blind_base);
+  }
 }
 template <int WBITS>
 static void msm_launch(int groups, int cpt, dim3 grid, cudaStream_t s, ge* pp, const ge_niels* table, const u256* sc, size_t stride, size_t R, const u256* bl,
-                       size_t blind_base) {
-  if (groups == 1) msm_launch2<WBITS, 1>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
-  else if (groups == 4) msm_launch2<WBITS, 4>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
-  else msm_launch2<WBITS, 8>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
+                       size_t blind_base, size_t smem_pad) {
+  if (groups == 1) msm_launch2<WBITS, 1>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base, smem_pad);
+  else if (groups == 4) msm_launch2<WBITS, 4>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base, smem_pad);
+  else msm_launch2<WBITS, 8>(cpt, grid, s, pp, table, sc, stride, R, bl, blind_base, smem_pad);
 }
 void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
-              void* scratch, cudaStream_t s) {
+              void* scratch, cudaStream_t s, const MsmTune& tune) {
   ProfScope ps("msm_rows", 32.0 * (double)L * (double)R + 32.0 * (double)R, s);
   const size_t ncols = R + (blinds ? 1 : 0);
   int groups = msm_pick_groups(L, R);
-  int cpt = msm_pick_cpt(L, ncols, groups);
+  int cpt = tune.cpt ? tune.cpt : msm_pick_cpt(L, ncols, groups);
+  if (cpt != 4) cpt = 1;
   size_t chunks = msm_chunks(ncols, groups, cpt);
+  const size_t smem_pad = tune.smem_pad;
   ge* partial = (ge*)scratch;
   for (size_t row0 = 0; row0 < L; row0 += 32768) {   // gridDim.y limit 65535
     size_t rows = L - row0 < 32768 ? L - row0 : 32768;
@@ -772,9 +965,9 @@ void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, si
     const u256* sc = scalars + row0 * stride;
     const u256* bl = blinds ? blinds + row0 : nullptr;
     ge* pp = partial + row0 * chunks;
-    if (wbits == 8) msm_launch<8>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
-    else if (wbits == 13) msm_launch<13>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
-    else if (wbits == 15) msm_launch<15>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base);
+    if (wbits == 8) msm_launch<8>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base, smem_pad);
+    else if (wbits == 13) msm_launch<13>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base, smem_pad);
+    else if (wbits == 15) msm_launch<15>(groups, cpt, grid, s, pp, table, sc, stride, R, bl, blind_base, smem_pad);
     else throw std::runtime_error("spartan_b200: unsupported MSM window width");
     SP_LAUNCHED();
   }

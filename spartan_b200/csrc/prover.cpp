@@ -32,7 +32,9 @@ void shake256(uint8_t* out, size_t outlen, const uint8_t* in, size_t inlen) {
 Ctx::Ctx(int dev_) : device(dev_) {
   if (dev::device_count() <= dev_) throw std::runtime_error("spartan_b200: no CUDA device " + std::to_string(dev_) + " (the prover has no CPU fallback)");
   dev::set_device(dev_);
-  stream = dev::stream_create();
+  stream = dev::stream_create_prio(+1);
+  stream2 = dev::stream_create_prio(-1);
+  ev_fork = dev::event_create(); ev_join = dev::event_create();
   pinned_bytes = 1 << 20;
   pinned = (uint8_t*)dev::hmalloc_pinned(pinned_bytes);
   host_res = reinterpret_cast<u256*>(pinned + (512 << 10));
@@ -59,7 +61,10 @@ void Ctx::comm_create() {
 }
 Ctx::~Ctx() {
   try { sync(); } catch (...) {}
-  scratch.release(); red.release(); small.release(); dmail.release();
+  try { dev::stream_sync(stream2); } catch (...) {}
+  scratch.release(); scratch2.release(); red.release(); small.release(); dmail.release();
+  dev::event_destroy(ev_fork); dev::event_destroy(ev_join);
+  dev::stream_destroy(stream2);
   if (ev_a) { dev::event_destroy(ev_a); dev::event_destroy(ev_b); }
   dev::hfree_pinned(pinned);
   dev::stream_destroy(stream);
@@ -698,7 +703,7 @@ struct PhaseTimer {
 };
 
 void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T,
-                RandomTape& tape, R1CSProof& proof, std::vector<Fq>& rx, std::vector<Fq>& ry) {
+                RandomTape& tape, R1CSProof& proof, std::vector<Fq>& rx, std::vector<Fq>& ry, const R1csHooks* hooks) {
   PhaseTimer t_all(ctx, "R1CSProof::prove");
   T.append_protocol_name("R1CS proof");
   const size_t num_vars = inst.num_vars, num_cons = inst.num_cons;
@@ -755,6 +760,7 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
     zk_sumcheck_prove(ctx, dev::SC_CUBIC4, Fq::zero(), Fq::zero(), num_rounds_x, tabs, 4, gens.gens_1, gens.gens_4, T, tape, proof.sc_proof_phase1, rx, claims1,
                       blind_claim_postsc1, sh1);
   }
+  if (hooks && hooks->on_rx) hooks->on_rx(rx);
   const Fq tau_claim = claims1[0], Az_claim = claims1[1], Bz_claim = claims1[2], Cz_claim = claims1[3];
   Fq Az_blind = tape.random_scalar("Az_blind"), Bz_blind = tape.random_scalar("Bz_blind"), Cz_blind = tape.random_scalar("Cz_blind"),
      prod_Az_Bz_blind = tape.random_scalar("prod_Az_Bz_blind");
@@ -794,6 +800,7 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
     zk_sumcheck_prove(ctx, dev::SC_QUAD, claim_phase2, blind_claim_phase2, num_rounds_y, tabs, 2, gens.gens_1, gens.gens_3, T, tape, proof.sc_proof_phase2, ry, claims2,
                       blind_claim_postsc2, sh2);
   }
+  if (hooks && hooks->on_ry) hooks->on_ry(ry);
   {
     PhaseTimer t(ctx, "polyeval");
     // eval_vars_at_ry = poly_vars.evaluate(ry[1..]) (dense_mlpoly.rs:236-242)

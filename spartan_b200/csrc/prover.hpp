@@ -1,6 +1,7 @@
 // spartan_b200 — host prover: the reference's proof structs (wire order) and the GPU-driven provers.
 // Struct and field names follow /root/reference/src so the bincode layout can be checked line by line.
 #pragma once
+#include <functional>
 #include <array>
 #include "engine.hpp"
 
@@ -116,8 +117,11 @@ struct NizkProof { R1CSProof r1cs_sat_proof; std::vector<Fq> rx, ry;
   void ser(Writer& w) const { r1cs_sat_proof.ser(w); w.scalars(rx); w.scalars(ry); } };
 
 // R1CSProof::prove (r1csproof.rs:144-349).  d_vars: device array of num_vars Montgomery scalars (consumed read-only).
+// hooks: called (when set) as soon as the first / the second sumcheck phase has produced its point, so that the caller can start work that
+// depends only on rx / ry on another stream while the rest of the proof runs (SNARK::prove: the dereferenced SPARK values and their commitment)
+struct R1csHooks { std::function<void(const std::vector<Fq>&)> on_rx, on_ry; };
 void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T,
-                RandomTape& tape, R1CSProof& proof, std::vector<Fq>& rx, std::vector<Fq>& ry);
+                RandomTape& tape, R1CSProof& proof, std::vector<Fq>& rx, std::vector<Fq>& ry, const R1csHooks* hooks = nullptr);
 // NIZK::prove (lib.rs:501-546)
 void nizk_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::vector<Fq>& input, const R1CSGens& gens, Transcript& T,
                 const Fq& tape_seed, NizkProof& out);

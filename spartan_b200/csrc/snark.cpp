@@ -2,6 +2,7 @@
 // (src/sparse_mlpoly.rs:1447-1514, src/product_tree.rs:259-383) driven on the device.  Every table of the memory-checking network
 // (hash layers, 16 product trees with all their layers, dereferenced values) lives in HBM; the host only runs the transcript.
 #include "snark.hpp"
+#include <cstdlib>
 #include <algorithm>
 #include "../../include/spartan_b200.h"
 
@@ -376,14 +377,75 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   append_poly_commitment(T, "comm_comb_ops", enc.comm_comb_ops);
   append_poly_commitment(T, "comm_comb_mem", enc.comm_comb_mem);
 
-  R1CSProof sat;
-  std::vector<Fq> rx, ry;
-  r1cs_prove(ctx, inst, d_vars, input, *gens.gens_r1cs_sat, T, tape, sat, rx, ry);
-
   const DenseView dv(enc);
   const size_t N = dv.N, cells = dv.cells;
   const size_t lgN = log2_ceil(N), lgC = log2_ceil(cells);
   DevBuf<u256> d_chal(64), eq_small(2 * ((size_t)1 << ((std::max(lgN + 4, lgC + 1) + 1) / 2)) + 8);
+
+  // ---- dereferenced values and their commitment (sparse_mlpoly.rs:507-512, :213-219), started EARLY on the background stream.
+  // comb = row_ops_val[3] | col_ops_val[3] | zero pad, committed as an L x R matrix (dense_mlpoly.rs:165-177).  row_ops_val depends only on rx
+  // (known after the first sumcheck phase), col_ops_val only on ry (after the second), and the transcript needs the commitment only after the
+  // whole R1CS proof: the two 3N-term MSMs (ALU-bound, the longest kernels of the proof) run on ctx.stream2 underneath the latency-bound rounds
+  // of phase two and of the witness evaluation proof, which keep the greatest stream priority.  Same values, same bytes, different timing.
+  DevBuf<u256> mem_rx(cells), mem_ry(cells), derefs(8 * N);
+  dev::dzero(derefs.p + 6 * N, 2 * N * sizeof(u256), ctx.stream);
+  u256 *row_val[3], *col_val[3];
+  for (int m = 0; m < 3; m++) { row_val[m] = derefs.p + (size_t)m * N; col_val[m] = derefs.p + (size_t)(3 + m) * N; }
+  const size_t ell_d = log2_ceil(8 * N), L_d = (size_t)1 << (ell_d / 2), R_d = (size_t)1 << (ell_d - ell_d / 2);
+  if (R_d != gens.gens_derefs.n) throw SpError(SP_ERR_INVALID_ARG, "polynomial size does not match the commitment generators (num_nz_entries too small?)");
+  static const bool early_ok = getenv("SP_NO_EARLY_DEREFS") == nullptr;
+  const bool early = early_ok && N % R_d == 0;                    // each of the two parts is a whole number of matrix rows
+  const size_t n_part = early ? 3 * N / R_d : 0;                  // rows per part; rows [2 n_part, L_d) are zero: the identity, 32 zero bytes
+  const size_t Wd = (size_t)ctx.shard_world();
+  const bool shard_rows = early && Wd > 1 && n_part % Wd == 0;    // rank r commits rows [r n_part/W, (r+1) n_part/W) of either part
+  const size_t cnt = shard_rows ? n_part / Wd : n_part;
+  const size_t nx = log2_ceil(inst.num_cons), ny = log2_ceil(2 * inst.num_vars), nxy = std::max(nx, ny);
+  DevBuf<u256> d_chal2, eq_small2;
+  DevBuf<ge> early_rows;
+  DevBuf<uint8_t> early_comp;
+  struct ForkGuard {   // an exception between fork and join must not release buffers the background stream still works on
+    Ctx& c; bool forked = false;
+    ~ForkGuard() { if (forked) { try { dev::stream_sync(c.stream2); } catch (...) {} } }
+  } fork_guard{ctx};
+  static const dev::MsmTune early_tune = [] {
+    dev::MsmTune t;
+    if (const char* e = getenv("SP_EARLY_MSM_CPT")) t.cpt = atoi(e);
+    if (const char* e = getenv("SP_EARLY_MSM_SMEM")) t.smem_pad = (size_t)atol(e);
+    return t;
+  }();
+  if (early) {
+    d_chal2.alloc(64); eq_small2.alloc(eq_small.n); early_rows.alloc(2 * cnt); early_comp.alloc(64 * cnt);
+    const size_t need = dev::msm_scratch_bytes(cnt, R_d) + 64;
+    if (ctx.scratch2.n < need) { dev::stream_sync(ctx.stream2); ctx.scratch2.alloc(need); }
+  }
+  auto early_part = [&](int part, const std::vector<Fq>& pt) {   // part 0: rows from rx, part 1: columns from ry
+    // equalize (sparse_mlpoly.rs:1429-1445): left-pad the shorter point with zeros; staged in pinned memory so that the copy never waits for the stream
+    Fq* ext = reinterpret_cast<Fq*>(ctx.pinned + (960 << 10) + (size_t)part * 4096);
+    for (size_t i = 0; i < nxy - pt.size(); i++) ext[i] = Fq::zero();
+    for (size_t i = 0; i < pt.size(); i++) ext[nxy - pt.size() + i] = pt[i];
+    dev::event_record(ctx.ev_fork, ctx.stream);
+    dev::stream_wait_event(ctx.stream2, ctx.ev_fork);
+    fork_guard.forked = true;
+    cudaStream_t s2 = ctx.stream2;
+    u256* chal = d_chal2.p + 32 * part;
+    u256* mem = part ? mem_ry.p : mem_rx.p;
+    dev::h2d(chal, ext, nxy * sizeof(u256), s2);
+    dev::eq_evals(mem, chal, (int)nxy, eq_small2.p, s2);
+    for (int m = 0; m < 3; m++) dev::gather(part ? col_val[m] : row_val[m], mem, (part ? enc.col : enc.row).ops_addr_idx[m].p, N, s2);
+    const size_t first = (size_t)part * n_part + (shard_rows ? (size_t)ctx.rank() * cnt : 0);
+    const CommitKey& key = gens.gens_derefs.gens_n;
+    dev::msm_rows(early_rows.p + (size_t)part * cnt, key.set->table.p, key.set->wbits, derefs.p + first * R_d, R_d, cnt, R_d, nullptr, key.h, ctx.scratch2.p, s2, early_tune);
+    dev::compress_batch(early_comp.p + 32 * (size_t)part * cnt, early_rows.p + (size_t)part * cnt, cnt, s2);
+  };
+  R1csHooks hooks;
+  if (early) {
+    hooks.on_rx = [&](const std::vector<Fq>& p) { early_part(0, p); };
+    hooks.on_ry = [&](const std::vector<Fq>& p) { early_part(1, p); };
+  }
+
+  R1CSProof sat;
+  std::vector<Fq> rx, ry;
+  r1cs_prove(ctx, inst, d_vars, input, *gens.gens_r1cs_sat, T, tape, sat, rx, ry, early ? &hooks : nullptr);
 
   // ---- inst.evaluate(rx, ry) (r1cs.rs:300-303 -> multi_evaluate sparse_mlpoly.rs:440-452)
   auto t0 = std::chrono::steady_clock::now();
@@ -407,27 +469,37 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   auto t_eval = std::chrono::steady_clock::now();
   SparseMatPolyEvalProof ep;
   T.append_protocol_name("Sparse polynomial evaluation proof");
-  // equalize (sparse_mlpoly.rs:1429-1445): left-pad the shorter point with zeros
-  std::vector<Fq> rx_ext = rx, ry_ext = ry;
-  if (rx.size() < ry.size()) rx_ext.insert(rx_ext.begin(), ry.size() - rx.size(), Fq::zero());
-  if (ry.size() < rx.size()) ry_ext.insert(ry_ext.begin(), rx.size() - ry.size(), Fq::zero());
-  DevBuf<u256> mem_rx(cells), mem_ry(cells);
-  dev::h2d(d_chal.p, rx_ext.data(), rx_ext.size() * sizeof(u256), ctx.stream);
-  dev::eq_evals(mem_rx.p, d_chal.p, (int)rx_ext.size(), eq_small.p, ctx.stream);
-  dev::h2d(d_chal.p + 32, ry_ext.data(), ry_ext.size() * sizeof(u256), ctx.stream);
-  dev::eq_evals(mem_ry.p, d_chal.p + 32, (int)ry_ext.size(), eq_small.p, ctx.stream);
-  // derefs (sparse_mlpoly.rs:507-512): comb = row_ops_val[3] | col_ops_val[3] | zero pad
-  DevBuf<u256> derefs(8 * N);
-  dev::dzero(derefs.p + 6 * N, 2 * N * sizeof(u256), ctx.stream);
-  u256 *row_val[3], *col_val[3];
-  for (int m = 0; m < 3; m++) {
-    row_val[m] = derefs.p + (size_t)m * N; col_val[m] = derefs.p + (size_t)(3 + m) * N;
-    dev::gather(row_val[m], mem_rx.p, enc.row.ops_addr_idx[m].p, N, ctx.stream);
-    dev::gather(col_val[m], mem_ry.p, enc.col.ops_addr_idx[m].p, N, ctx.stream);
-  }
+  if (nx != rx.size() || ny != ry.size()) throw std::runtime_error("spartan_b200: unexpected sumcheck point lengths");
   {
     auto tc = std::chrono::steady_clock::now();
-    commit_poly(ctx, derefs.p, 8 * N, gens.gens_derefs, ep.comm_derefs);
+    if (early) {
+      // join: the prover's stream continues after the background commitments; gather the rank shares when the rows were split
+      dev::event_record(ctx.ev_join, ctx.stream2);
+      dev::stream_wait_event(ctx.stream, ctx.ev_join);
+      std::vector<uint8_t> hb(64 * cnt * (shard_rows ? Wd : 1));
+      if (shard_rows) dev::d2h(hb.data(), ctx.allgather_block(early_comp.p, 64 * cnt), hb.size(), ctx.stream);
+      else dev::d2h(hb.data(), early_comp.p, hb.size(), ctx.stream);
+      ctx.sync();
+      fork_guard.forked = false;
+      ep.comm_derefs.C.assign(L_d, Cp{});                                  // value-initialised: 32 zero bytes = the identity's encoding
+      for (size_t r = 0; r < (shard_rows ? Wd : 1); r++)
+        for (int part = 0; part < 2; part++)
+          memcpy(ep.comm_derefs.C[(size_t)part * n_part + r * cnt].b, hb.data() + (r * 2 + part) * 32 * cnt, 32 * cnt);
+    } else {
+      // equalize (sparse_mlpoly.rs:1429-1445): left-pad the shorter point with zeros
+      std::vector<Fq> rx_ext = rx, ry_ext = ry;
+      if (rx.size() < ry.size()) rx_ext.insert(rx_ext.begin(), ry.size() - rx.size(), Fq::zero());
+      if (ry.size() < rx.size()) ry_ext.insert(ry_ext.begin(), rx.size() - ry.size(), Fq::zero());
+      dev::h2d(d_chal.p, rx_ext.data(), rx_ext.size() * sizeof(u256), ctx.stream);
+      dev::eq_evals(mem_rx.p, d_chal.p, (int)rx_ext.size(), eq_small.p, ctx.stream);
+      dev::h2d(d_chal.p + 32, ry_ext.data(), ry_ext.size() * sizeof(u256), ctx.stream);
+      dev::eq_evals(mem_ry.p, d_chal.p + 32, (int)ry_ext.size(), eq_small.p, ctx.stream);
+      for (int m = 0; m < 3; m++) {
+        dev::gather(row_val[m], mem_rx.p, enc.row.ops_addr_idx[m].p, N, ctx.stream);
+        dev::gather(col_val[m], mem_ry.p, enc.col.ops_addr_idx[m].p, N, ctx.stream);
+      }
+      commit_poly(ctx, derefs.p, 8 * N, gens.gens_derefs, ep.comm_derefs);
+    }
     T.append_message("derefs_commitment", "begin_derefs_commitment");  // sparse_mlpoly.rs:213-219
     append_poly_commitment(T, "comm_poly_row_col_ops_val", ep.comm_derefs);
     T.append_message("derefs_commitment", "end_derefs_commitment");

@@ -173,3 +173,18 @@ def test_snark_caller_owned_transcript(sb):
     # a label is shorthand for a fresh transcript
     assert sb.SNARK.prove(inst, comm, vars_, inputs, gens, sb.Transcript(b"snark_example"), sb.tape_seed(seed)).bytes == \
         sb.SNARK.prove(inst, comm, vars_, inputs, gens, b"snark_example", sb.tape_seed(seed)).bytes
+
+
+def test_scheduling_switches_do_not_change_bytes():
+    """The background-stream commitment of the dereferenced values (snark.cpp) and the quad-lane inner-product MSM (kernels.cu) only change WHEN and
+    HOW things are computed: the proof bytes with either switched off must equal the default build's (each variant is its own process: the
+    switches are read once per process)."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shas = {}
+    for name, env in [("default", {}), ("no_early", {"SP_NO_EARLY_DEREFS": "1"}), ("no_quad", {"SP_IPA_QUAD": "0"}), ("cpt1_smem", {"SP_EARLY_MSM_CPT": "1", "SP_EARLY_MSM_SMEM": "61440"})]:
+        e = dict(os.environ); e.update(env)
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "ab_prove.py"), name, "12", "1"], env=e, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        shas[name] = json.loads(out.stdout.strip().splitlines()[-1])["sha256"]
+    assert len(set(shas.values())) == 1, shas
