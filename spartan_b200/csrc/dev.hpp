@@ -180,6 +180,7 @@ struct MsmTune { int cpt = 0; size_t smem_pad = 0; };
 void msm_rows(ge* out, const ge_niels* table, int wbits, const u256* scalars, size_t stride, size_t L, size_t R, const u256* blinds, size_t blind_base,
               void* scratch, cudaStream_t s, const MsmTune& tune = MsmTune());
 
+void add_points(ge* a, const ge* b, size_t n, cudaStream_t s);   // a[i] += b[i]
 void sum_points(ge* out, const ge* in, int n, cudaStream_t s);   // out[0] = in[0] + ... + in[n-1], n <= 32
 // both MSMs of an inner-product round (L, R -> out[0], out[1]) over unfolded generators: scalar of generator j is a[.]*svec[j].
 // scratch >= ipa_msm_scratch_points(n_full, wbits) points; ticket: one zero-initialised word (self-resetting)

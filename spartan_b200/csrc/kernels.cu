@@ -637,6 +637,16 @@ __global__ void __launch_bounds__(32) k_msm_reduce_small(ge* out, const ge* __re
   for (int d = 16; d > 0; d >>= 1) if (d < 2 * chunks) acc = ge_add(acc, shfl_down_ge(acc, d));
   if (threadIdx.x == 0) st_ge(out + row, acc);
 }
+__global__ void __launch_bounds__(128) k_ge_add_arrays(ge* a, const ge* __restrict__ b, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st_ge(a + i, ge_add(ld_ge(a + i), ld_ge(b + i)));
+}
+// a[i] += b[i] (the blind term of a row commitment, added after the row's MSM: the blinds are drawn on the host while the MSM runs)
+void add_points(ge* a, const ge* b, size_t n, cudaStream_t s) {
+  if (!n) return;
+  k_ge_add_arrays<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a, b, n);
+  SP_LAUNCHED(); check("add_points");
+}
 // out[0] = sum of n <= 32 points (the "point-add allreduce" of a sharded MSM, after the all-gather of the partial results)
 void sum_points(ge* out, const ge* in, int n, cudaStream_t s) {
   if (n < 1 || n > 32) throw std::runtime_error("spartan_b200: sum_points supports 1..32 points");

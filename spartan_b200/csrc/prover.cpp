@@ -457,28 +457,32 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
 
 // ================================================================================================ polynomial commitment / evaluation proof
 Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalars, size_t stride, size_t L, size_t R, const Fq* blinds,
-                            std::vector<Cp>& out) {
+                            std::vector<Cp>& out, const std::function<const Fq*()>& blinds_late) {
   // DensePolynomial::commit_inner (dense_mlpoly.rs:148-177): C_i = (MSM(Z[iR..(i+1)R], G) + blinds[i]*h).compress()
+  // blinds_late (instead of blinds): called AFTER the rows' MSM is in flight, so that the host draws the blinds from the random tape (0.8 us per
+  // scalar of Keccak) while the device works; the blind terms blinds[i]*h are then a second, tiny launch added onto the rows.
   if (key.off != 0 || R > key.n) throw std::runtime_error("spartan_b200: commit_rows key mismatch");
   ctx.ensure_scratch(dev::msm_scratch_bytes(L, R) + 64);
-  DevBuf<ge> rows(L);
+  DevBuf<ge> rows(L), bh;
   DevBuf<u256> d_bl;
   if (blinds) { d_bl.alloc(L); dev::h2d(d_bl.p, blinds, L * sizeof(u256), ctx.stream); }
   DevBuf<uint8_t> comp(32 * L);
   out.resize(L);
   const size_t W = (size_t)ctx.shard_world();
-  if (W > 1 && L >= 2 * W && L % W == 0) {
-    // rows are independent MSMs over the same generators: rank r commits rows [r*L/W, (r+1)*L/W) and the 32-byte encodings are all-gathered
-    const size_t Lr = L / W, row0 = (size_t)ctx.rank() * Lr;
-    dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars + row0 * stride, stride, Lr, R, blinds ? d_bl.p + row0 : nullptr, key.h, ctx.scratch.p, ctx.stream);
-    dev::compress_batch(comp.p, rows.p, Lr, ctx.stream);
-    const uint8_t* all = ctx.allgather_block(comp.p, 32 * Lr);
-    dev::d2h(out.data(), all, 32 * L, ctx.stream);
-  } else {
-    dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars, stride, L, R, blinds ? d_bl.p : nullptr, key.h, ctx.scratch.p, ctx.stream);
-    dev::compress_batch(comp.p, rows.p, L, ctx.stream);
-    dev::d2h(out.data(), comp.p, 32 * L, ctx.stream);
+  // rows are independent MSMs over the same generators: when sharded, rank r commits rows [r*L/W, (r+1)*L/W) and the 32-byte encodings are all-gathered
+  const bool split = W > 1 && L >= 2 * W && L % W == 0;
+  const size_t Lr = split ? L / W : L, row0 = split ? (size_t)ctx.rank() * Lr : 0;
+  dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars + row0 * stride, stride, Lr, R, blinds ? d_bl.p + row0 : nullptr, key.h, ctx.scratch.p, ctx.stream);
+  if (!blinds && blinds_late) {
+    const Fq* bl = blinds_late();
+    d_bl.alloc(L); bh.alloc(Lr);
+    dev::h2d(d_bl.p, bl, L * sizeof(u256), ctx.stream);
+    dev::msm_rows(bh.p, key.set->table.p, key.set->wbits, d_scalars, 0, Lr, 0, d_bl.p + row0, key.h, ctx.scratch.p, ctx.stream);   // blinds[i]*h (rows without generator terms)
+    dev::add_points(rows.p, bh.p, Lr, ctx.stream);
   }
+  dev::compress_batch(comp.p, rows.p, Lr, ctx.stream);
+  if (split) dev::d2h(out.data(), ctx.allgather_block(comp.p, 32 * Lr), 32 * L, ctx.stream);
+  else dev::d2h(out.data(), comp.p, 32 * L, ctx.stream);
   ctx.sync();
   return out.empty() ? Cp() : out[0];
 }
@@ -716,8 +720,9 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
   std::vector<Fq> blinds_vars;
   {
     PhaseTimer t(ctx, "polycommit");
-    blinds_vars = tape.random_vector("poly_blinds", L_size);  // dense_mlpoly.rs:193-196
-    commit_rows_and_compress(ctx, gens.gens_pc.gens_n, d_vars, R_size, L_size, R_size, blinds_vars.data(), proof.comm_vars.C);
+    // dense_mlpoly.rs:193-196; the blinds are the tape's first draw and are made while the rows' MSM already runs
+    commit_rows_and_compress(ctx, gens.gens_pc.gens_n, d_vars, R_size, L_size, R_size, nullptr, proof.comm_vars.C,
+                             [&]() { blinds_vars = tape.random_vector("poly_blinds", L_size); return blinds_vars.data(); });
     append_poly_commitment(T, "poly_commitment", proof.comm_vars);
   }
 

@@ -170,7 +170,7 @@ void polyeval_prove(Ctx& ctx, const u256* d_Z, const std::vector<Fq>* blinds_opt
 
 // exposed pieces (C-ABI operator level and tests)
 Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalars, size_t stride, size_t L, size_t R, const Fq* blinds,
-                            std::vector<Cp>& out);
+                            std::vector<Cp>& out, const std::function<const Fq*()>& blinds_late = nullptr);
 std::vector<Fq> host_eq_evals(const std::vector<Fq>& r);
 
 }  // namespace sp
