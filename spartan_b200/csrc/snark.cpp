@@ -409,6 +409,9 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   } fork_guard{ctx};
   static const dev::MsmTune early_tune = [] {
     dev::MsmTune t;
+    // measured on the B200 (profiles/r02_tuning.md section 6): three resident MSM CTAs per SM instead of four leave a quarter of every register file
+    // to the prover's stream; its rounds still slow down (they share the FMA pipes) but the proof as a whole is fastest this way
+    t.smem_pad = 60 << 10;
     if (const char* e = getenv("SP_EARLY_MSM_CPT")) t.cpt = atoi(e);
     if (const char* e = getenv("SP_EARLY_MSM_SMEM")) t.smem_pad = (size_t)atol(e);
     return t;
