@@ -311,10 +311,12 @@ def run_b200(args):
     # ---- roofline leg: CUDA-event timing of every kernel family over one more step (separate from the timed regions above)
     roof = None
     if rank == 0:
+        ctx.set_overlap(False)     # every kernel on the prover's stream: per-launch event times free of the background MSM (not a timed region)
         api.prof_enable(True)
         step_resident()
         rep = api.prof_report()
         api.prof_enable(False)
+        ctx.set_overlap(True)
         pk, which = peaks()
         tot = sum(v["ms"] for v in rep.values())
         dom = max(rep.items(), key=lambda kv: kv[1]["ms"])
@@ -326,12 +328,14 @@ def run_b200(args):
             return {"kernel": name, "bound": bound, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
                     "launches": v["launches"], "ms_per_step": v["ms"], "share_of_kernel_time": v["ms"] / tot if tot else None, "peak_source": which,
                     "largest_launch": {"algorithmic_bytes": v["largest_bytes"], "us": v["largest_ms"] * 1e3, "achieved": big, "frac": big / pk["hbm_gbs"]}}
-        # BASELINE.json asks for the fraction of the HBM roofline of the sumcheck fold: `roofline` is that kernel (fused fold + round evaluation,
-        # 48*len algorithmic bytes per table per launch).  `achieved` averages over all launches of a step, most of which are the tiny late rounds
-        # of the 41 product-tree layers (latency-bound); `largest_launch` is the 18-instance first round of the ops proof.
+        # BASELINE.json asks for the fraction of the HBM roofline of the sumcheck fold: `roofline` is that kernel, k_sc_fold_eval (fused fold + round
+        # evaluation on tables of >= 8192 entries, 48*len algorithmic bytes per distinct table per launch).  `achieved` averages over all its launches of
+        # a step; `largest_launch` is the 18-instance first round of the ops proof.  The tiny late rounds run a different, latency-bound kernel
+        # (k_sc_fold_eval_small, family sc_fold_eval_small in kernels_ms_per_step).
         roof = rl("sc_fold_eval", fold) if fold else None
         if roof:
-            roof["note"] = ("algorithmic bytes = 48 B x len per table per launch (read len*32, write len/2*32); CUDA-event time per launch on the prover stream; "
+            roof["note"] = ("algorithmic bytes = 48 B x len per table per launch (read len*32, write len/2*32); CUDA-event time per launch on the prover stream, measured in one extra "
+                            "step with the background-stream overlap switched off (sp_ctx_set_overlap(0)) so that no other kernel shares the GPU; "
                             "ncu --set full of the same kernel: profiles/r02_ncu_full_sc_fold_eval.txt; the multiplications are FMA-pipe bound (IMAD.WIDE at quarter rate, "
                             "profiles/r02_tuning.md section 1): the pipe ceiling of the cubic-4 round is ~0.55 of the HBM copy bandwidth")
         if roof:

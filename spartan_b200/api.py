@@ -97,6 +97,10 @@ class Context:
         """switch sharded proving off / on for a connected context (every rank must switch together)"""
         lib.sp_comm_set_enabled(self.h, C.c_int(1 if enabled else 0))
 
+    def set_overlap(self, enabled):
+        """background-stream commitment of the dereferenced values in SNARK.prove on / off (off: every kernel on one stream, for per-kernel profiling)"""
+        lib.sp_ctx_set_overlap(self.h, C.c_int(1 if enabled else 0))
+
     def timings(self):
         buf = C.create_string_buffer(8192)
         lib.sp_timings(self.h, buf, _sz(8192))

@@ -78,6 +78,7 @@ int sp_comm_connect(sp_ctx* ctx, int rank, int world, const uint8_t* handles) {
   SP_CATCH(ctx)
 }
 int sp_comm_set_enabled(sp_ctx* ctx, int enabled) { ctx->c.shard_enabled = enabled != 0; return SP_OK; }
+int sp_ctx_set_overlap(sp_ctx* ctx, int enabled) { ctx->c.overlap = enabled != 0; return SP_OK; }
 int sp_comm_info(const sp_ctx* ctx, int* rank, int* world) { *rank = ctx->c.rank(); *world = ctx->c.world(); return SP_OK; }
 
 void sp_io_bytes(unsigned long long* h, unsigned long long* d) { dev::io_bytes(h, d); }

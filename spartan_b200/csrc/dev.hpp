@@ -20,6 +20,8 @@ int device_count();
 void set_device(int dev);
 cudaStream_t stream_create();
 cudaStream_t stream_create_prio(int level);   // > 0: greatest priority of the device, < 0: least
+// a stream confined to `sms` SMs (green context); nullptr when unsupported; *sms_granted = the SM count of the partition
+cudaStream_t stream_create_partition(int sms, int level, int* sms_granted);
 void stream_wait_event(cudaStream_t s, void* ev);
 void stream_destroy(cudaStream_t s);
 void stream_sync(cudaStream_t s);
@@ -186,7 +188,7 @@ void sum_points(ge* out, const ge* in, int n, cudaStream_t s);   // out[0] = in[
 // scratch >= ipa_msm_scratch_points(n_full, wbits) points; ticket: one zero-initialised word (self-resetting)
 size_t ipa_msm_scratch_points(size_t n_full, int wbits);
 void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
-             cudaStream_t s, HostSig sig = HostSig());
+             cudaStream_t s, HostSig sig = HostSig(), int max_ctas = 0 /* > 0: cap on the blocks of the quad-lane kernel (both sides together) */);
 
 // ---- variable-base MSM on arbitrary points (bucket method; kernels_pip.cu).  pts: affine-niels form of the caller's points.
 struct PipPlan { size_t n = 0; int c = 0, nwin = 0, G = 32; uint32_t nb = 0; size_t tile = 0, ntiles = 0, S = 0, max_items = 0; };

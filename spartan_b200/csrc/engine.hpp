@@ -82,6 +82,9 @@ struct Ctx {
   // background stream (least priority) for throughput work whose inputs are known early and whose result the transcript needs late: the commitment
   // to the dereferenced SPARK values runs there under the second sumcheck phase and the witness evaluation proof (snark.cpp)
   cudaStream_t stream2 = nullptr;
+  bool overlap = true;                 // sp_ctx_set_overlap: 0 keeps every kernel on the prover's stream (profiling: per-kernel event times free of concurrent work)
+  bool bg_busy = false;                // between fork and join of background work (snark.cpp): latency kernels shape their grids for the free SMs
+  int stream2_sms = 0;                 // > 0: stream2 is confined to that many SMs (green context); 0: it shares every SM with the prover's stream
   void* ev_fork = nullptr; void* ev_join = nullptr;
   DevBuf<uint8_t> scratch2;        // MSM partial sums of the background stream
   uint8_t* pinned = nullptr;       // staging for small host<->device exchanges

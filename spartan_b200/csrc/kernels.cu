@@ -13,6 +13,7 @@
 //   K7     eq_evals, dot, bound_rows, lincomb3, hadamard, spmv, SPARK hash layer, IPA helpers.
 // All arithmetic is exact 256-bit integer work on the INT32 pipe; no tensor-core formulation exists.
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <stdexcept>
 #include <string>
 #include <map>
@@ -81,6 +82,50 @@ cudaStream_t stream_create_prio(int level) {
   cudaStream_t s;
   ck(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, level > 0 ? greatest : (level < 0 ? least : (least + greatest) / 2)), "cudaStreamCreateWithPriority");
   return s;
+}
+// A stream whose kernels run on a fixed subset of `sms` SMs (a CUDA green context carved out of the device's SM resource; driver entry points are
+// resolved at run time so that the library has no link-time dependency on libcuda).  The remaining SMs are never touched by work on this stream, so
+// the short kernels of the prover's stream find idle SMs however long the background MSMs run.  Returns nullptr when the driver cannot do it.
+cudaStream_t stream_create_partition(int sms, int level, int* sms_granted) {
+  typedef CUresult (*GetRes)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*Split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*GenDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*GreenCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*GreenStream)(CUstream*, CUgreenCtx, unsigned int, int);
+  typedef CUresult (*DevGet)(CUdevice*, int);
+  auto ep = [](const char* name) -> void* {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+    return f;
+  };
+  GetRes get_res = (GetRes)ep("cuDeviceGetDevResource");
+  Split split = (Split)ep("cuDevSmResourceSplitByCount");
+  GenDesc gen = (GenDesc)ep("cuDevResourceGenerateDesc");
+  GreenCreate gcreate = (GreenCreate)ep("cuGreenCtxCreate");
+  GreenStream gstream = (GreenStream)ep("cuGreenCtxStreamCreate");
+  DevGet devget = (DevGet)ep("cuDeviceGet");
+  if (!get_res || !split || !gen || !gcreate || !gstream || !devget) return nullptr;
+  int ord = 0;
+  cudaGetDevice(&ord);
+  cudaFree(0);   // the primary context must exist
+  CUdevice dev;
+  if (devget(&dev, ord) != CUDA_SUCCESS) return nullptr;
+  CUdevResource all, grp, rem;
+  if (get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return nullptr;
+  if (sms < 8 || (unsigned)sms >= all.sm.smCount) return nullptr;
+  unsigned int nb = 1;
+  if (split(&grp, &nb, &all, &rem, 0, (unsigned)sms) != CUDA_SUCCESS || nb < 1) return nullptr;
+  CUdevResourceDesc desc;
+  if (gen(&desc, &grp, 1) != CUDA_SUCCESS) return nullptr;
+  CUgreenCtx g;
+  if (gcreate(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return nullptr;   // lives as long as the process (one per prover context)
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  CUstream st;
+  if (gstream(&st, g, CU_STREAM_NON_BLOCKING, level > 0 ? greatest : least) != CUDA_SUCCESS) return nullptr;
+  if (sms_granted) *sms_granted = (int)grp.sm.smCount;
+  return (cudaStream_t)st;
 }
 void stream_wait_event(cudaStream_t s, void* ev) { ck(cudaStreamWaitEvent(s, (cudaEvent_t)ev, 0), "cudaStreamWaitEvent"); }
 void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
@@ -795,67 +840,68 @@ __device__ __forceinline__ u256 quad_warp_sum(u256 P, int c, int lane) {
   for (int d = 16; d >= 4; d >>= 1) P = quad_add(P, shfl_down_256(P, d), c, lane);
   return P;
 }
-// Both MSMs of an inner-product round, quad-lane formulation of k_ipa_msm (same inputs, same outputs).  grid = (chunks, 2 sides), 512 threads =
-// 128 quads; a quad owns two adjacent windows (2p, 2p+1) of one scalar: the first table entry is lifted to extended coordinates (one product:
-// (4x, 4y, 4, 4xy) from y+x, y-x), the second joins by a mixed addition, then 3 tree levels inside the warp, 4 across the 16 warps, and the last
-// block to finish sums the blocks' partial points of both sides: ~17 dependent quad additions of ~1 us instead of ~19 additions of 2.3 us.
-template <int WBITS>
-__global__ void __launch_bounds__(512, 2) k_ipa_msm_quad(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ a, const u256* __restrict__ sv,
-                                                         size_t n_cur, size_t n_full, unsigned int* ticket, ge* out, HostSig sig) {
+// Both MSMs of an inner-product round, quad-lane formulation of k_ipa_msm (same inputs, same outputs).  grid = (chunks, 2 sides), IPAQ_THREADS
+// threads = IPAQ_THREADS/4 quads; a quad owns WPQ adjacent windows of one scalar and chains their table entries by mixed additions (two product
+// latencies each), then 3 tree levels inside the warp, one gather + 3 levels across the warps, and the last block to finish sums the blocks' partial
+// points of both sides.  WPQ balances the two costs measured on the B200 (profiles/r02_tuning.md section 7): a lone warp already keeps its
+// sub-partition's FMA pipe 64 % busy, so the first quad formulation (two windows per quad, 4608 warps for 4096 generators) was throughput-bound at the
+// old kernel's time; six or seven windows per quad need a quarter of the warps and add only ~3 us to the dependent chain.
+#define IPAQ_THREADS 256
+template <int WBITS, int WPQ>
+__global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ a, const u256* __restrict__ sv,
+                                                                  size_t n_cur, size_t n_full, unsigned int* ticket, ge* out, HostSig sig) {
   constexpr int NWIN = (253 + WBITS - 1) / WBITS;
-  constexpr int QPS = (NWIN + 1) / 2;                      // quads per scalar
+  constexpr int QPS = (NWIN + WPQ - 1) / WPQ;              // quads per scalar
+  constexpr int QPB = IPAQ_THREADS / 4, NWARP = IPAQ_THREADS / 32;   // quads per block, warps per block
   constexpr uint32_t HALF = 1u << (WBITS - 1);
   constexpr size_t DEPTH = (size_t)1 << (WBITS - 1);
   const int side = blockIdx.y, tid = threadIdx.x, lane = tid & 31, c = lane & 3, warp = tid >> 5;
   const size_t half = n_cur >> 1, total = n_full >> 1;
-  const size_t gq = (size_t)blockIdx.x * 128 + (tid >> 2);
-  const size_t t = gq / QPS;
-  const int w0 = 2 * (int)(gq - t * QPS);
+  const size_t total_quads = total * QPS, stride = (size_t)gridDim.x * QPB;
   u256 P = quad_identity(c);
-  u256 nq = c == 3 ? fp_zero() : fp_one();                 // the identity as a niels operand
-  if (t < total) {                                         // uniform inside a quad; no shuffles in here
-    const size_t blk = t / half, off = t - blk * half;
-    const size_t j = blk * n_cur + off + (side == 0 ? half : 0);
-    u256 k = fq_mul(ld256_ro(a + (side == 0 ? off : off + half)), ld256_ro(sv + j));
-    if (!fq_is_zero(k)) {
-      k = fq_from_mont(k);
-      uint32_t carry = 0;
-      for (int w = 0; w < w0; w++) carry = (msm_window<WBITS>(k, w) + carry) > HALF ? 1u : 0u;
-      const ge_niels* tb = table + (j * NWIN + (size_t)w0) * DEPTH;
-      {
-        uint32_t v = msm_window<WBITS>(k, w0) + carry;
+  // grid-stride over the (scalar, window group) work items with the same trip count in every quad (the shuffles inside quad_madd need the whole
+  // warp): a launch may be capped to fewer blocks than work items (the prover does that while a background MSM occupies most SMs)
+  for (size_t g0 = (size_t)blockIdx.x * QPB; g0 < total_quads; g0 += stride) {
+    const size_t gq = g0 + (tid >> 2);
+    const size_t t = gq / QPS;
+    const int w0 = WPQ * (int)(gq - t * QPS);
+    const bool live = t < total;                           // uniform inside a quad
+    u256 k = fq_zero();
+    size_t j = 0;
+    if (live) {
+      const size_t blk = t / half, off = t - blk * half;
+      j = blk * n_cur + off + (side == 0 ? half : 0);
+      k = fq_mul(ld256_ro(a + (side == 0 ? off : off + half)), ld256_ro(sv + j));
+      if (!fq_is_zero(k)) k = fq_from_mont(k);
+    }
+    uint32_t carry = 0;
+    for (int w = 0; w < w0; w++) carry = (msm_window<WBITS>(k, w) + carry) > HALF ? 1u : 0u;
+    const ge_niels* tb = table + (j * NWIN + (size_t)w0) * DEPTH;
+#pragma unroll 1
+    for (int h = 0; h < WPQ; h++, tb += DEPTH) {           // the same WPQ trips everywhere; a zero digit or a window past the top adds the identity
+      u256 x = c == 3 ? fp_zero() : fp_one();              // the identity as a niels operand: (y - x, y + x, -, 2dxy) = (1, 1, -, 0)
+      if (live && w0 + h < NWIN) {
+        uint32_t v = msm_window<WBITS>(k, w0 + h) + carry;
         int d;
         if (v > HALF) { d = (int)v - (int)(2 * HALF); carry = 1; } else { d = (int)v; carry = 0; }
         if (d != 0) {
           const ge_niels* e = tb + ((d < 0 ? -d : d) - 1);
-          const u256 pl = ld256_ro(d < 0 ? &e->ymx : &e->ypx), mi = ld256_ro(d < 0 ? &e->ypx : &e->ymx);   // y + x, y - x of +/-q
-          if (c == 0) { u256 x = fp_sub(pl, mi); P = fp_add(x, x); }            // 4x
-          else if (c == 1) { u256 y = fp_add(pl, mi); P = fp_add(y, y); }       // 4y
-          else if (c == 2) { P = fp_zero(); P.v[0] = 4; }                       // 4
-          else P = fp_mul(fp_sub(pl, mi), fp_add(pl, mi));                      // 4xy
+          if (c == 0) x = ld256_ro(d < 0 ? &e->ypx : &e->ymx);          // y - x of +/-q
+          else if (c == 1) x = ld256_ro(d < 0 ? &e->ymx : &e->ypx);     // y + x of +/-q
+          else if (c == 3) { x = ld256_ro(&e->t2d); if (d < 0) x = fp_neg(x); }
         }
       }
-      if (w0 + 1 < NWIN) {
-        uint32_t v = msm_window<WBITS>(k, w0 + 1) + carry;
-        int d = v > HALF ? (int)v - (int)(2 * HALF) : (int)v;
-        if (d != 0) {
-          const ge_niels* e = tb + DEPTH + ((d < 0 ? -d : d) - 1);
-          if (c == 0) nq = ld256_ro(d < 0 ? &e->ypx : &e->ymx);
-          else if (c == 1) nq = ld256_ro(d < 0 ? &e->ymx : &e->ypx);
-          else if (c == 3) { nq = ld256_ro(&e->t2d); if (d < 0) nq = fp_neg(nq); }
-        }
-      }
+      P = quad_madd(P, x, c, lane);
     }
   }
-  P = quad_madd(P, nq, c, lane);
   P = quad_warp_sum(P, c, lane);
-  __shared__ u256 sm[16][4];
+  __shared__ u256 sm[NWARP][4];
   __shared__ bool is_last;
   if (lane < 4) sm[warp][c] = P;
   __syncthreads();
   if (warp == 0) {
-    const int q = lane >> 2;
-    P = quad_add(sm[q][c], sm[q + 8][c], c, lane);
+    const int q = lane >> 2;                               // NWARP = 8: one warp's sum per quad
+    P = q < NWARP ? sm[q][c] : quad_identity(c);
     P = quad_warp_sum(P, c, lane);
     if (lane < 4) { st256(reinterpret_cast<u256*>(partial + (size_t)side * gridDim.x + blockIdx.x) + c, P); __threadfence(); }
     __syncwarp();
@@ -864,11 +910,12 @@ __global__ void __launch_bounds__(512, 2) k_ipa_msm_quad(ge* partial, const ge_n
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // last block: quads 0..63 finish L, 64..127 finish R
-  const int s2 = tid >> 8, qq = (tid >> 2) & 63;
+  // last block: the first half of its quads finishes L, the second half R
+  constexpr int QH = QPB / 2;
+  const int s2 = (tid >> 2) / QH, qq = (tid >> 2) % QH;
   const unsigned int nparts = gridDim.x;
   P = quad_identity(c);
-  for (unsigned int base = 0; base < nparts; base += 64) {   // same trip count for every quad; out-of-range slots contribute the identity
+  for (unsigned int base = 0; base < nparts; base += QH) {   // same trip count for every quad; out-of-range slots contribute the identity
     const unsigned int idx = base + qq;
     u256 Q = quad_identity(c);
     if (idx < nparts) Q = ld256_cg(reinterpret_cast<const u256*>(partial + (size_t)s2 * nparts + idx) + c);
@@ -877,9 +924,10 @@ __global__ void __launch_bounds__(512, 2) k_ipa_msm_quad(ge* partial, const ge_n
   P = quad_warp_sum(P, c, lane);
   if (lane < 4) sm[warp][c] = P;
   __syncthreads();
-  if (warp == 0 || warp == 8) {
+  if (warp == 0 || warp == NWARP / 2) {                    // NWARP/2 = 4 warp sums per side
     const int q = lane >> 2;
-    P = quad_warp_sum(sm[warp + q][c], c, lane);
+    P = q < NWARP / 2 ? sm[warp + q][c] : quad_identity(c);
+    P = quad_warp_sum(P, c, lane);
     if (lane < 4) {
       st256(reinterpret_cast<u256*>(out + s2) + c, P);
       if (sig.host_out) { st256(sig.host_out + 4 * s2 + c, P); __threadfence_system(); }
@@ -891,24 +939,32 @@ __global__ void __launch_bounds__(512, 2) k_ipa_msm_quad(ge* partial, const ge_n
     if (sig.flag) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
   }
 }
+// windows per quad: the window count split into three groups (17 -> 6, 20 -> 7, 32 -> 11)
+template <int WBITS> struct IpaQ { static constexpr int NWIN = (253 + WBITS - 1) / WBITS, WPQ = (NWIN + 2) / 3, QPS = (NWIN + WPQ - 1) / WPQ; };
+template <int WBITS>
+static void ipa_msm_quad_launch(ge* out, const ge_niels* table, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
+                                cudaStream_t s, HostSig sig, int max_ctas) {
+  const size_t quads = (n_full / 2) * IpaQ<WBITS>::QPS, qpb = IPAQ_THREADS / 4;
+  dim3 grid((unsigned)((quads + qpb - 1) / qpb), 2);
+  if (max_ctas >= 2 && grid.x > (unsigned)max_ctas / 2) grid.x = (unsigned)max_ctas / 2;   // the kernel strides over the work items
+  k_ipa_msm_quad<WBITS, IpaQ<WBITS>::WPQ><<<grid, IPAQ_THREADS, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+}
 #ifndef SP_IPA_QUAD_DEFAULT
 #define SP_IPA_QUAD_DEFAULT 1
 #endif
 size_t ipa_msm_scratch_points(size_t n_full, int wbits) {   // partial points of either formulation
-  const size_t nwin = (size_t)msm_nwin(wbits), total = n_full / 2;
-  const size_t quad_chunks = (total * ((nwin + 1) / 2) + 127) / 128, plain_chunks = (total + 15) / 16;
+  const size_t nwin = (size_t)msm_nwin(wbits), total = n_full / 2, wpq = (nwin + 2) / 3, qps = (nwin + wpq - 1) / wpq;
+  const size_t quad_chunks = (total * qps + IPAQ_THREADS / 4 - 1) / (IPAQ_THREADS / 4), plain_chunks = (total + 15) / 16;
   return 2 * std::max(quad_chunks, plain_chunks);
 }
 void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
-             cudaStream_t s, HostSig sig) {
+             cudaStream_t s, HostSig sig, int max_ctas) {
   ProfScope ps("ipa_msm", 64.0 * (double)n_full, s);
   static const bool quad = [] { const char* e = getenv("SP_IPA_QUAD"); return e ? atoi(e) != 0 : SP_IPA_QUAD_DEFAULT != 0; }();
   if (quad) {
-    const size_t nwin = (size_t)msm_nwin(wbits), quads = (n_full / 2) * ((nwin + 1) / 2);
-    dim3 grid((unsigned)((quads + 127) / 128), 2);
-    if (wbits == 8) k_ipa_msm_quad<8><<<grid, 512, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
-    else if (wbits == 13) k_ipa_msm_quad<13><<<grid, 512, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
-    else if (wbits == 15) k_ipa_msm_quad<15><<<grid, 512, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+    if (wbits == 8) ipa_msm_quad_launch<8>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas);
+    else if (wbits == 13) ipa_msm_quad_launch<13>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas);
+    else if (wbits == 15) ipa_msm_quad_launch<15>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas);
     else throw std::runtime_error("spartan_b200: unsupported MSM window width");
     SP_LAUNCHED(); check("ipa_msm_quad");
     return;

@@ -532,17 +532,19 @@ void sc_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, u256* out,
 }
 void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s, HostSig sig, const XRank& xr) {
   if (xr.world > 1 && (len / 4 <= SC_SMALL_MAX || !sig.done)) throw std::runtime_error("spartan_b200: a sharded sumcheck round needs a streaming-size table and a completion counter");
-  ProfScope ps("sc_fold_eval", sc_bytes(insts, ninst, kind, len, 48.0), s);
+  static const bool small_ok = getenv("SP_SC_NO_SMALL") == nullptr;
+  // two kernels, two profiler families: the streaming kernel (HBM roofline) and the latency-bound small-table kernel (k_sc_fold_eval_small)
+  const bool small = small_ok && len / 4 <= SC_SMALL_MAX && len >= 4;
+  ProfScope ps(small ? "sc_fold_eval_small" : "sc_fold_eval", sc_bytes(insts, ninst, kind, len, 48.0), s);
   ScBatch b; fill_batch(b, insts, ninst);
   unsigned int* counters = (unsigned int*)scratch;
   u256* partials = (u256*)((char*)scratch + 256);
-  static const bool small_ok = getenv("SP_SC_NO_SMALL") == nullptr;
   static const bool cf = sc_constfold();
   const FqConst rc = cf ? fq_const_table(r) : FqConst();
 #define SP_SC_LAUNCH(KERNEL, K, THREADS, ...) \
   do { if (cf) KERNEL<K, true><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig, ##__VA_ARGS__); \
        else KERNEL<K, false><<<grid, THREADS, 0, s>>>(b, len, r, rc, partials, counters, out, sig, ##__VA_ARGS__); } while (0)
-  if (small_ok && len / 4 <= SC_SMALL_MAX && len >= 4) {
+  if (small) {
     dim3 grid((unsigned)((len / 4 + SC_SMALL_Q - 1) / SC_SMALL_Q), ninst);
     switch (kind) {
       case SC_QUAD: SP_SC_LAUNCH(k_sc_fold_eval_small, SC_QUAD, SC_SMALL_Q * 4); break;

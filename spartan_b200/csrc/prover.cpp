@@ -29,11 +29,20 @@ void shake256(uint8_t* out, size_t outlen, const uint8_t* in, size_t inlen) {
   }
 }
 
+#ifndef SP_BG_SMS_DEFAULT
+#define SP_BG_SMS_DEFAULT 0
+#endif
 Ctx::Ctx(int dev_) : device(dev_) {
   if (dev::device_count() <= dev_) throw std::runtime_error("spartan_b200: no CUDA device " + std::to_string(dev_) + " (the prover has no CPU fallback)");
   dev::set_device(dev_);
   stream = dev::stream_create_prio(+1);
-  stream2 = dev::stream_create_prio(-1);
+  {
+    // SP_BG_SMS: SMs of the background partition (0: no partition, the background stream shares all SMs at the least priority)
+    const char* e = getenv("SP_BG_SMS");
+    const int want = e ? atoi(e) : SP_BG_SMS_DEFAULT;
+    if (want > 0) stream2 = dev::stream_create_partition(want, -1, &stream2_sms);
+    if (!stream2) { stream2_sms = 0; stream2 = dev::stream_create_prio(-1); }
+  }
   ev_fork = dev::event_create(); ev_join = dev::event_create();
   pinned_bytes = 1 << 20;
   pinned = (uint8_t*)dev::hmalloc_pinned(pinned_bytes);
@@ -527,7 +536,9 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
     // L = <a_L, G_R>, R = <a_R, G_L> over the unfolded generators (scalars a[.]*s[j] formed inside the kernel), results published to the host
     dev::HostSig sig2 = ctx.next_sig();
     sig2.host_out = ctx.host_res + 8;
-    dev::ipa_msm(pts.p, gs.table.p, gs.wbits, d_a, svec.p, cur, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sig2);
+    // while a background MSM owns most SMs (partitioned stream2), two blocks per free SM is all that can start at once: cap the grid, the kernel strides
+    const int ipa_cap = ctx.bg_busy && ctx.stream2_sms > 0 ? 2 * std::max(4, dev::sm_count() - ctx.stream2_sms) : 0;
+    dev::ipa_msm(pts.p, gs.table.p, gs.wbits, d_a, svec.p, cur, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sig2, ipa_cap);
     f1.stop();
     // the transcript work that precedes the first round (absorbing a_vec, deriving r) runs while the device computes round 0
     if (k == 0) r_scale = get_r_scale();

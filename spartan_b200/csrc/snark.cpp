@@ -364,6 +364,7 @@ static std::vector<Fq> bound_bot_all(std::vector<Fq> v, const std::vector<Fq>& c
 void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const u256* d_vars, const std::vector<Fq>& input, const SnarkGens& gens,
                  Transcript& T, const Fq& tape_seed, Writer& w) {
   ctx.timings.clear();
+  ctx.timings.push_back({"info:background_stream_sms", (double)ctx.stream2_sms});
   ShardScope shard(ctx);   // on a connected multi-GPU context every rank runs this same function on the same inputs (see DESIGN.md "Multi-GPU")
   auto t_start = std::chrono::steady_clock::now();
   auto mark = [&](const char* name, std::chrono::steady_clock::time_point t0) {
@@ -394,7 +395,7 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   const size_t ell_d = log2_ceil(8 * N), L_d = (size_t)1 << (ell_d / 2), R_d = (size_t)1 << (ell_d - ell_d / 2);
   if (R_d != gens.gens_derefs.n) throw SpError(SP_ERR_INVALID_ARG, "polynomial size does not match the commitment generators (num_nz_entries too small?)");
   static const bool early_ok = getenv("SP_NO_EARLY_DEREFS") == nullptr;
-  const bool early = early_ok && N % R_d == 0;                    // each of the two parts is a whole number of matrix rows
+  const bool early = early_ok && ctx.overlap && N % R_d == 0;                    // each of the two parts is a whole number of matrix rows
   const size_t n_part = early ? 3 * N / R_d : 0;                  // rows per part; rows [2 n_part, L_d) are zero: the identity, 32 zero bytes
   const size_t Wd = (size_t)ctx.shard_world();
   const bool shard_rows = early && Wd > 1 && n_part % Wd == 0;    // rank r commits rows [r n_part/W, (r+1) n_part/W) of either part
@@ -405,17 +406,18 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
   DevBuf<uint8_t> early_comp;
   struct ForkGuard {   // an exception between fork and join must not release buffers the background stream still works on
     Ctx& c; bool forked = false;
-    ~ForkGuard() { if (forked) { try { dev::stream_sync(c.stream2); } catch (...) {} } }
+    ~ForkGuard() { c.bg_busy = false; if (forked) { try { dev::stream_sync(c.stream2); } catch (...) {} } }
   } fork_guard{ctx};
-  static const dev::MsmTune early_tune = [] {
-    dev::MsmTune t;
-    // measured on the B200 (profiles/r02_tuning.md section 6): three resident MSM CTAs per SM instead of four leave a quarter of every register file
-    // to the prover's stream; its rounds still slow down (they share the FMA pipes) but the proof as a whole is fastest this way
-    t.smem_pad = 60 << 10;
-    if (const char* e = getenv("SP_EARLY_MSM_CPT")) t.cpt = atoi(e);
-    if (const char* e = getenv("SP_EARLY_MSM_SMEM")) t.smem_pad = (size_t)atol(e);
-    return t;
-  }();
+  dev::MsmTune early_tune;
+  {
+    // measured on the B200 (profiles/r02_tuning.md section 6).  Shared SMs: three resident MSM CTAs per SM instead of four leave a quarter of every
+    // register file to the prover's stream.  Partitioned (ctx.stream2_sms > 0): the background stream owns its SMs, full occupancy there.
+    static const char* e_cpt = getenv("SP_EARLY_MSM_CPT");
+    static const char* e_smem = getenv("SP_EARLY_MSM_SMEM");
+    early_tune.smem_pad = ctx.stream2_sms > 0 ? 0 : (60 << 10);
+    if (e_cpt) early_tune.cpt = atoi(e_cpt);
+    if (e_smem) early_tune.smem_pad = (size_t)atol(e_smem);
+  }
   if (early) {
     d_chal2.alloc(64); eq_small2.alloc(eq_small.n); early_rows.alloc(2 * cnt); early_comp.alloc(64 * cnt);
     const size_t need = dev::msm_scratch_bytes(cnt, R_d) + 64;
@@ -429,6 +431,7 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
     dev::event_record(ctx.ev_fork, ctx.stream);
     dev::stream_wait_event(ctx.stream2, ctx.ev_fork);
     fork_guard.forked = true;
+    ctx.bg_busy = true;
     cudaStream_t s2 = ctx.stream2;
     u256* chal = d_chal2.p + 32 * part;
     u256* mem = part ? mem_ry.p : mem_rx.p;
@@ -484,6 +487,7 @@ void snark_prove(Ctx& ctx, const Instance& inst, const SnarkEncoding& enc, const
       else dev::d2h(hb.data(), early_comp.p, hb.size(), ctx.stream);
       ctx.sync();
       fork_guard.forked = false;
+      ctx.bg_busy = false;
       ep.comm_derefs.C.assign(L_d, Cp{});                                  // value-initialised: 32 zero bytes = the identity's encoding
       for (size_t r = 0; r < (shard_rows ? Wd : 1); r++)
         for (int part = 0; part < 2; part++)
