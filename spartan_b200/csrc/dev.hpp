@@ -188,7 +188,11 @@ void sum_points(ge* out, const ge* in, int n, cudaStream_t s);   // out[0] = in[
 // scratch >= ipa_msm_scratch_points(n_full, wbits) points; ticket: one zero-initialised word (self-resetting)
 size_t ipa_msm_scratch_points(size_t n_full, int wbits);
 void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
-             cudaStream_t s, HostSig sig = HostSig(), int max_ctas = 0 /* > 0: cap on the blocks of the quad-lane kernel (both sides together) */);
+             cudaStream_t s, HostSig sig = HostSig(), int max_ctas = 0 /* > 0: cap on the blocks of the quad-lane kernel (both sides together) */,
+             // b != null (only when ipa_msm_fuses_dots()): the same launch also computes c_out[0] = <a_L, b_R>, c_out[1] = <a_R, b_L> of the round and
+             // publishes them through sigc (its own flag word and completion counter), instead of a separate dot_pairs launch in front of the MSM
+             const u256* b = nullptr, u256* c_out = nullptr, HostSig sigc = HostSig());
+bool ipa_msm_fuses_dots();
 
 // ---- variable-base MSM on arbitrary points (bucket method; kernels_pip.cu).  pts: affine-niels form of the caller's points.
 struct PipPlan { size_t n = 0; int c = 0, nwin = 0, G = 32; uint32_t nb = 0; size_t tile = 0, ntiles = 0, S = 0, max_items = 0; };

@@ -105,6 +105,7 @@ struct Ctx {
   unsigned int* host_flag = nullptr;
   DevBuf<unsigned int> sig_done;
   unsigned int sig_seq = 0;
+  unsigned int sigc_seq = 0;           // sequence of the second flag word (host_flag + 16)
   dev::HostSig next_sig() { dev::HostSig s; s.host_out = host_res; s.flag = host_flag; s.done = sig_done.p; s.seq = ++sig_seq; return s; }
   void wait_sig(const dev::HostSig& s);   // spins on the flag; falls back to a stream synchronise to surface CUDA errors
   // host -> persistent-kernel mailbox (dev::sc_persist): the next challenge and its sequence number, in mapped pinned memory

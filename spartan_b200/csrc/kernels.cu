@@ -849,7 +849,36 @@ __device__ __forceinline__ u256 quad_warp_sum(u256 P, int c, int lane) {
 #define IPAQ_THREADS 256
 template <int WBITS, int WPQ>
 __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ a, const u256* __restrict__ sv,
-                                                                  size_t n_cur, size_t n_full, unsigned int* ticket, ge* out, HostSig sig) {
+                                                                  size_t n_cur, size_t n_full, unsigned int* ticket, ge* out, HostSig sig,
+                                                                  const u256* __restrict__ b, u256* c_out, HostSig sigc) {
+  if (blockIdx.y == 2) {
+    // fused dot products of the round (bullet.rs:78-79), two blocks beside the MSM's: c_L = <a_L, b_R> (block 0), c_R = <a_R, b_L> (block 1); published
+    // through their own flag word (sigc), long before the MSM finishes: the host turns them into c*Q while the MSM runs
+    if (blockIdx.x >= 2) return;
+    const size_t hn = n_cur >> 1;
+    const u256* pa = a + (blockIdx.x == 0 ? 0 : hn);
+    const u256* pb = b + (blockIdx.x == 0 ? hn : 0);
+    u256 acc = fq_zero();
+    for (size_t i = threadIdx.x; i < hn; i += IPAQ_THREADS) acc = fq_add(acc, fq_mul(ld256_ro(pa + i), ld256_ro(pb + i)));
+    acc = warp_sum_fq(acc);
+    __shared__ u256 ds[IPAQ_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) ds[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      u256 v = threadIdx.x < IPAQ_THREADS / 32 ? ds[threadIdx.x] : fq_zero();
+      v = warp_sum_fq(v);
+      if (threadIdx.x == 0) {
+        st256(c_out + blockIdx.x, v);
+        if (sigc.host_out) st256(sigc.host_out + blockIdx.x, v);
+        __threadfence_system();
+        if (atomicAdd(sigc.done, 1u) == 1u) {                 // the second of the two blocks publishes
+          *sigc.done = 0;
+          if (sigc.flag) { __threadfence_system(); *((volatile unsigned int*)sigc.flag) = sigc.seq; }
+        }
+      }
+    }
+    return;
+  }
   constexpr int NWIN = (253 + WBITS - 1) / WBITS;
   constexpr int QPS = (NWIN + WPQ - 1) / WPQ;              // quads per scalar
   constexpr int QPB = IPAQ_THREADS / 4, NWARP = IPAQ_THREADS / 32;   // quads per block, warps per block
@@ -877,22 +906,26 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
     uint32_t carry = 0;
     for (int w = 0; w < w0; w++) carry = (msm_window<WBITS>(k, w) + carry) > HALF ? 1u : 0u;
     const ge_niels* tb = table + (j * NWIN + (size_t)w0) * DEPTH;
-#pragma unroll 1
-    for (int h = 0; h < WPQ; h++, tb += DEPTH) {           // the same WPQ trips everywhere; a zero digit or a window past the top adds the identity
-      u256 x = c == 3 ? fp_zero() : fp_one();              // the identity as a niels operand: (y - x, y + x, -, 2dxy) = (1, 1, -, 0)
+    // all WPQ table entries are fetched up front (independent gathers from a table of up to 110 GB: DRAM + TLB latency paid once, not once per
+    // link of the chain); a zero digit or a window past the top contributes the identity as a niels operand: (y - x, y + x, -, 2dxy) = (1, 1, -, 0)
+    u256 x[WPQ];
+#pragma unroll
+    for (int h = 0; h < WPQ; h++) {
+      x[h] = c == 3 ? fp_zero() : fp_one();
       if (live && w0 + h < NWIN) {
         uint32_t v = msm_window<WBITS>(k, w0 + h) + carry;
         int d;
         if (v > HALF) { d = (int)v - (int)(2 * HALF); carry = 1; } else { d = (int)v; carry = 0; }
         if (d != 0) {
-          const ge_niels* e = tb + ((d < 0 ? -d : d) - 1);
-          if (c == 0) x = ld256_ro(d < 0 ? &e->ypx : &e->ymx);          // y - x of +/-q
-          else if (c == 1) x = ld256_ro(d < 0 ? &e->ymx : &e->ypx);     // y + x of +/-q
-          else if (c == 3) { x = ld256_ro(&e->t2d); if (d < 0) x = fp_neg(x); }
+          const ge_niels* e = tb + (size_t)h * DEPTH + ((d < 0 ? -d : d) - 1);
+          if (c == 0) x[h] = ld256_ro(d < 0 ? &e->ypx : &e->ymx);          // y - x of +/-q
+          else if (c == 1) x[h] = ld256_ro(d < 0 ? &e->ymx : &e->ypx);     // y + x of +/-q
+          else if (c == 3) { x[h] = ld256_ro(&e->t2d); if (d < 0) x[h] = fp_neg(x[h]); }
         }
       }
-      P = quad_madd(P, x, c, lane);
     }
+#pragma unroll
+    for (int h = 0; h < WPQ; h++) P = quad_madd(P, x[h], c, lane);
   }
   P = quad_warp_sum(P, c, lane);
   __shared__ u256 sm[NWARP][4];
@@ -943,32 +976,39 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
 template <int WBITS> struct IpaQ { static constexpr int NWIN = (253 + WBITS - 1) / WBITS, WPQ = (NWIN + 2) / 3, QPS = (NWIN + WPQ - 1) / WPQ; };
 template <int WBITS>
 static void ipa_msm_quad_launch(ge* out, const ge_niels* table, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
-                                cudaStream_t s, HostSig sig, int max_ctas) {
+                                cudaStream_t s, HostSig sig, int max_ctas, const u256* b, u256* c_out, HostSig sigc) {
   const size_t quads = (n_full / 2) * IpaQ<WBITS>::QPS, qpb = IPAQ_THREADS / 4;
   dim3 grid((unsigned)((quads + qpb - 1) / qpb), 2);
   if (max_ctas >= 2 && grid.x > (unsigned)max_ctas / 2) grid.x = (unsigned)max_ctas / 2;   // the kernel strides over the work items
-  k_ipa_msm_quad<WBITS, IpaQ<WBITS>::WPQ><<<grid, IPAQ_THREADS, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig);
+  if (b) { grid.y = 3; if (grid.x < 2) grid.x = 2; }        // a third row of blocks, of which two compute the round's dot products
+  k_ipa_msm_quad<WBITS, IpaQ<WBITS>::WPQ><<<grid, IPAQ_THREADS, 0, s>>>((ge*)scratch, table, a, svec, n_cur, n_full, ticket, out, sig, b, c_out, sigc);
 }
 #ifndef SP_IPA_QUAD_DEFAULT
 #define SP_IPA_QUAD_DEFAULT 1
 #endif
+bool ipa_msm_fuses_dots() {   // true when ipa_msm can compute the round's two dot products in the same launch (quad-lane kernel)
+  static const bool quad = [] { const char* e = getenv("SP_IPA_QUAD"); return e ? atoi(e) != 0 : SP_IPA_QUAD_DEFAULT != 0; }();
+  static const bool fuse = getenv("SP_IPA_NO_FUSED_DOT") == nullptr;
+  return quad && fuse;
+}
 size_t ipa_msm_scratch_points(size_t n_full, int wbits) {   // partial points of either formulation
   const size_t nwin = (size_t)msm_nwin(wbits), total = n_full / 2, wpq = (nwin + 2) / 3, qps = (nwin + wpq - 1) / wpq;
   const size_t quad_chunks = (total * qps + IPAQ_THREADS / 4 - 1) / (IPAQ_THREADS / 4), plain_chunks = (total + 15) / 16;
   return 2 * std::max(quad_chunks, plain_chunks);
 }
 void ipa_msm(ge* out, const ge_niels* table, int wbits, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
-             cudaStream_t s, HostSig sig, int max_ctas) {
+             cudaStream_t s, HostSig sig, int max_ctas, const u256* b, u256* c_out, HostSig sigc) {
   ProfScope ps("ipa_msm", 64.0 * (double)n_full, s);
   static const bool quad = [] { const char* e = getenv("SP_IPA_QUAD"); return e ? atoi(e) != 0 : SP_IPA_QUAD_DEFAULT != 0; }();
   if (quad) {
-    if (wbits == 8) ipa_msm_quad_launch<8>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas);
-    else if (wbits == 13) ipa_msm_quad_launch<13>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas);
-    else if (wbits == 15) ipa_msm_quad_launch<15>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas);
+    if (wbits == 8) ipa_msm_quad_launch<8>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas, b, c_out, sigc);
+    else if (wbits == 13) ipa_msm_quad_launch<13>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas, b, c_out, sigc);
+    else if (wbits == 15) ipa_msm_quad_launch<15>(out, table, a, svec, n_cur, n_full, scratch, ticket, s, sig, max_ctas, b, c_out, sigc);
     else throw std::runtime_error("spartan_b200: unsupported MSM window width");
     SP_LAUNCHED(); check("ipa_msm_quad");
     return;
   }
+  if (b) throw std::runtime_error("spartan_b200: the fused dot products need the quad-lane inner-product kernel");
   constexpr int GROUPS = 8;
   const size_t cols = 128 / GROUPS, total = n_full / 2;
   dim3 grid((unsigned)((total + cols - 1) / cols), 2);

@@ -49,6 +49,7 @@ Ctx::Ctx(int dev_) : device(dev_) {
   host_res = reinterpret_cast<u256*>(pinned + (512 << 10));
   host_flag = reinterpret_cast<unsigned int*>(pinned + (768 << 10));
   *host_flag = 0;
+  host_flag[16] = 0;   // second flag word (its own cache line): the dot products fused into the inner-product MSM launch
   mail = reinterpret_cast<dev::PersistMail*>(pinned + (900 << 10));
   memset(mail, 0, sizeof(dev::PersistMail));
   dmail.alloc(1);
@@ -531,14 +532,24 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
     FineTimer f1(ctx, "ipa launch");
     const u256* da[2] = {d_a, d_a + half};
     const u256* db[2] = {d_b + half, d_b};
-    dev::HostSig sig = ctx.next_sig();
-    dev::dot_pairs(d_c, da, db, 2, half, ctx.red.p, ctx.stream, sig);     // c_L = <a_L, b_R>, c_R = <a_R, b_L>   bullet.rs:78-79
-    // L = <a_L, G_R>, R = <a_R, G_L> over the unfolded generators (scalars a[.]*s[j] formed inside the kernel), results published to the host
-    dev::HostSig sig2 = ctx.next_sig();
-    sig2.host_out = ctx.host_res + 8;
+    // c_L = <a_L, b_R>, c_R = <a_R, b_L> (bullet.rs:78-79) and L = <a_L, G_R>, R = <a_R, G_L> over the unfolded generators (scalars a[.]*s[j] formed
+    // inside the kernel), all published to the host.  With the quad-lane kernel the dot products ride in the MSM's launch (two extra blocks with
+    // their own flag word); otherwise a dot_pairs launch precedes the MSM.
+    dev::HostSig sig, sig2;
     // while a background MSM owns most SMs (partitioned stream2), two blocks per free SM is all that can start at once: cap the grid, the kernel strides
     const int ipa_cap = ctx.bg_busy && ctx.stream2_sms > 0 ? 2 * std::max(4, dev::sm_count() - ctx.stream2_sms) : 0;
-    dev::ipa_msm(pts.p, gs.table.p, gs.wbits, d_a, svec.p, cur, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sig2, ipa_cap);
+    if (dev::ipa_msm_fuses_dots()) {
+      sig.host_out = ctx.host_res; sig.flag = ctx.host_flag + 16; sig.done = ctx.sig_done.p + 2; sig.seq = ++ctx.sigc_seq;
+      sig2 = ctx.next_sig();
+      sig2.host_out = ctx.host_res + 8;
+      dev::ipa_msm(pts.p, gs.table.p, gs.wbits, d_a, svec.p, cur, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sig2, ipa_cap, d_b, d_c, sig);
+    } else {
+      sig = ctx.next_sig();
+      dev::dot_pairs(d_c, da, db, 2, half, ctx.red.p, ctx.stream, sig);
+      sig2 = ctx.next_sig();
+      sig2.host_out = ctx.host_res + 8;
+      dev::ipa_msm(pts.p, gs.table.p, gs.wbits, d_a, svec.p, cur, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sig2, ipa_cap);
+    }
     f1.stop();
     // the transcript work that precedes the first round (absorbing a_vec, deriving r) runs while the device computes round 0
     if (k == 0) r_scale = get_r_scale();
