@@ -43,7 +43,7 @@ CPU_SAMPLE_LOG = int(os.environ.get("SP_BENCH_CPU_LOGN", str(LOG_N)))   # the CP
 SHARDED_LEGS_DEFAULT = "1"   # the sharded prover passed its multi-GPU parity runs (tools/run_sharded.py; profiles/r02_sharded.md)
 # world sizes at which the sharded prover has been byte-validated on hardware (profiles/r02_sharded.md).  At any other N the sharded legs stay off
 # unless SP_BENCH_SHARDED=1 forces them: an unvalidated collective that stalls would take the whole bench line (the replica throughput) down with it.
-SHARDED_VALIDATED_WORLDS = (2,)
+SHARDED_VALIDATED_WORLDS = (2, 4, 8)
 CPU_ARM_BUDGET_S = float(os.environ.get("SP_BENCH_CPU_BUDGET_S", "1200"))
 
 
