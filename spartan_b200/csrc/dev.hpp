@@ -99,6 +99,14 @@ void sc_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, u256* ou
 // fold every table of every instance by r (len -> len/2, in place) and evaluate the next round on the result; r travels as a kernel argument
 void sc_fold_eval(ScKind kind, const ScInst* d_insts, int ninst, size_t len, const u256& r, u256* out, void* scratch, cudaStream_t s,
                   HostSig sig = HostSig(), const XRank& xr = XRank());
+// ---- eq-factored streaming rounds of a batched A*B*eq sumcheck (kernels_sc.cu: k_sc_eval_g): instances use t[0] = A, t[1] = B; E: the suffix eq table
+// of the round (len/2 entries for sc_eval_g, len/4 for sc_fold_eval_g); out[3*i + 0] = q(0), out[3*i + 1] = q(inf) of instance i
+void sc_eval_g(const ScInst* d_insts, int ninst, size_t len, const u256* E, u256* out, void* scratch, cudaStream_t s, HostSig sig = HostSig(), const XRank& xr = XRank());
+void sc_fold_eval_g(const ScInst* d_insts, int ninst, size_t len, const u256& r, const u256* E, u256* out, void* scratch, cudaStream_t s, HostSig sig = HostSig(),
+                    const XRank& xr = XRank());
+// levels[k-1] (k = 1..K, back to back, n0 >> k entries each) = eq(tau[k+1..], .) from E0 = eq(tau[1..], .) of n0 entries
+size_t eq_suffix_entries(size_t n0, int K);
+void eq_suffix(u256* levels, const u256* E0, size_t n0, int K, cudaStream_t s);
 // ---- persistent tail of a batched cubic sumcheck (prove_cubic_batched, sumcheck.rs:254-424, once the tables are small): ONE launch runs all the
 // remaining rounds.  CTA i owns instance i (tables A, B and a private copy of C); after every bind it publishes the instance's evaluations to
 // the host (HostSig, sequence numbers sig.seq, sig.seq+1, ...), then spins on a mailbox in mapped pinned host memory until the host has derived

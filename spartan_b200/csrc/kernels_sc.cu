@@ -96,6 +96,65 @@ __global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval(ScBatch batch, s
   block_reduce_finish<3>(acc, partials, counters, out, 3, sig, xr);
 }
 
+// ---- eq-factored rounds of the batched product-circuit sumchecks (prove_cubic_batched with the shared C = eq(tau, .): product_tree.rs:279-286).
+// The round polynomial of sum_x eq(tau, x) A(x) B(x) factors: s_j(t) = prefix_j * eq(tau_j, t) * q_j(t) with prefix_j = prod_{i<j} eq(tau_i, r_i) and
+//   q_j(t) = sum_{x'} E_j[x'] * A(t, x') * B(t, x'),   E_j = eq(tau[j+1..], .)  (the suffix table: half the length, never bound, never written),
+// a QUADRATIC whose value at 1 follows from the running claim (q_j(1) = (c_j - (1 - tau_j) q_j(0)) / tau_j, c_{j+1} = q_j(r_j)), so a round needs
+// q_j(0) and the leading coefficient q_j(inf) only: 4 field products per index (a0 b0, da db, and the two weights) instead of the 6 of the three
+// cubic evaluations, no C table to bind, 2 values per instance to reduce.  The host rebuilds s_j(0), s_j(2), s_j(3) — the field elements the
+// reference computes (sumcheck.rs:296-355) — so the proof bytes do not change.  Streaming rounds only; the small-table tail runs the standard
+// kernels on C = prefix * eq(tau[j..], .).   out[3*inst + 0] = q(0), out[3*inst + 1] = q(inf).
+__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_eval_g(ScBatch batch, size_t len, const u256* __restrict__ E, u256* partials, unsigned int* counters,
+                                                              u256* out, HostSig sig, const __grid_constant__ XRank xr) {
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1;
+  u256 acc[2] = {fq_zero(), fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    const u256 a0 = ld256(in.t[0] + i), a1 = ld256(in.t[0] + i + half), b0 = ld256(in.t[1] + i), b1 = ld256(in.t[1] + i + half);
+    const u256 w = ld256_ro(E + i);
+    acc[0] = fq_add(acc[0], fq_mul(w, fq_mul(a0, b0)));
+    acc[1] = fq_add(acc[1], fq_mul(w, fq_mul(fq_sub(a1, a0), fq_sub(b1, b0))));
+  }
+  block_reduce_finish<2>(acc, partials, counters, out, 3, sig, xr);
+}
+// fused: bind A and B with r (len -> len/2, in place, constant-multiplier fold) and evaluate the next round's q(0), q(inf) with the weights
+// E = eq(tau[j+2..], .) of len/4 entries
+__global__ void __launch_bounds__(256, SP_SC_LB) k_sc_fold_eval_g(ScBatch batch, size_t len, const __grid_constant__ FqConst rc, const u256* __restrict__ E,
+                                                                   u256* partials, unsigned int* counters, u256* out, HostSig sig, const __grid_constant__ XRank xr) {
+  const ScInst& in = batch.inst[blockIdx.y];
+  const size_t half = len >> 1, quarter = len >> 2;
+  u256 acc[2] = {fq_zero(), fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quarter; i += (size_t)gridDim.x * blockDim.x) {
+    u256 lo[2], hi[2];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const u256 a0 = ld256(in.t[t] + i), a1 = ld256(in.t[t] + i + half), b0 = ld256(in.t[t] + i + quarter), b1 = ld256(in.t[t] + i + quarter + half);
+      lo[t] = fq_fold_const(a0, a1, rc);   // dense_mlpoly.rs:218
+      hi[t] = fq_fold_const(b0, b1, rc);
+      st256(in.t[t] + i, lo[t]); st256(in.t[t] + i + quarter, hi[t]);
+    }
+    const u256 w = ld256_ro(E + i);
+    acc[0] = fq_add(acc[0], fq_mul(w, fq_mul(lo[0], lo[1])));
+    acc[1] = fq_add(acc[1], fq_mul(w, fq_mul(fq_sub(hi[0], lo[0]), fq_sub(hi[1], lo[1]))));
+  }
+  block_reduce_finish<2>(acc, partials, counters, out, 3, sig, xr);
+}
+// suffix tables below E0 = eq(tau[1..], .) (n0 entries): level k (1 <= k <= K) = eq(tau[k+1..], .) = sum over the top k index bits of E0
+// (eq(tau_i, 0) + eq(tau_i, 1) = 1), n0 >> k entries, stored back to back in `levels`
+__global__ void __launch_bounds__(256) k_eq_suffix(u256* levels, const u256* __restrict__ E0, size_t n0, int K) {
+  size_t total = 0;
+  for (int k = 1; k <= K; k++) total += n0 >> k;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    size_t off = 0, y = g;
+    int k = 1;
+    while (y >= (n0 >> k)) { y -= n0 >> k; off += n0 >> k; k++; }
+    const size_t sz = n0 >> k;
+    u256 acc = fq_zero();
+    for (size_t b = 0; b < ((size_t)1 << k); b++) acc = fq_add(acc, ld256_ro(E0 + b * sz + y));
+    st256(levels + off + y, acc);
+  }
+}
+
 // ---- register-lean formulation of the fused round (3 CTAs of 256 threads per SM instead of 2).
 // The tables of an index are visited one after the other: bind (lo, hi), store, form the three evaluation arguments lo, 2hi-lo, 3hi-2lo and
 // fold them straight into three running products, so that only ONE table's values are live at a time; the three per-thread sums live in
@@ -597,6 +656,36 @@ void sc_fold_eval(ScKind kind, const ScInst* insts, int ninst, size_t len, const
   }
 #undef SP_SC_LAUNCH
   SP_LAUNCHED(); check("sc_fold_eval");
+}
+void sc_eval_g(const ScInst* insts, int ninst, size_t len, const u256* E, u256* out, void* scratch, cudaStream_t s, HostSig sig, const XRank& xr) {
+  ProfScope ps("sc_eval", (double)ninst * 2.0 * (double)len * 32.0 + (double)len * 16.0, s);
+  ScBatch b; fill_batch(b, insts, ninst);
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  dim3 grid(grid_for(len / 2, 256, 2), ninst);
+  if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
+  k_sc_eval_g<<<grid, 256, 0, s>>>(b, len, E, partials, counters, out, sig, xr);
+  SP_LAUNCHED(); check("sc_eval_g");
+}
+void sc_fold_eval_g(const ScInst* insts, int ninst, size_t len, const u256& r, const u256* E, u256* out, void* scratch, cudaStream_t s, HostSig sig, const XRank& xr) {
+  if (len / 4 <= SC_SMALL_MAX) throw std::runtime_error("spartan_b200: sc_fold_eval_g is a streaming kernel");
+  if (xr.world > 1 && !sig.done) throw std::runtime_error("spartan_b200: a sharded sumcheck round needs a completion counter");
+  ProfScope ps("sc_fold_eval", (double)ninst * 2.0 * (double)len * 48.0 + (double)len * 8.0, s);
+  ScBatch b; fill_batch(b, insts, ninst);
+  unsigned int* counters = (unsigned int*)scratch;
+  u256* partials = (u256*)((char*)scratch + 256);
+  const FqConst rc = fq_const_table(r);
+  dim3 grid(grid_for(len / 4, 256, SP_SC_LB), ninst);
+  if (grid.x > SC_MAX_BLOCKS) grid.x = SC_MAX_BLOCKS;
+  k_sc_fold_eval_g<<<grid, 256, 0, s>>>(b, len, rc, E, partials, counters, out, sig, xr);
+  SP_LAUNCHED(); check("sc_fold_eval_g");
+}
+size_t eq_suffix_entries(size_t n0, int K) { size_t t = 0; for (int k = 1; k <= K; k++) t += n0 >> k; return t; }
+void eq_suffix(u256* levels, const u256* E0, size_t n0, int K, cudaStream_t s) {
+  if (K < 1) return;
+  ProfScope ps("eq_evals", 64.0 * (double)n0, s);
+  k_eq_suffix<<<grid_for(eq_suffix_entries(n0, K), 256, 4), 256, 0, s>>>(levels, E0, n0, K);
+  SP_LAUNCHED(); check("eq_suffix");
 }
 void fold_top(u256* const* tables, int ntables, size_t len, const u256& r, cudaStream_t s) {
   ProfScope ps("fold_top", (double)ntables * len * 48.0, s);

@@ -183,6 +183,11 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
 #ifndef SP_SC_PERSIST_DEFAULT
 #define SP_SC_PERSIST_DEFAULT 0
 #endif
+#ifndef SP_SC_EQFACTOR_DEFAULT
+#define SP_SC_EQFACTOR_DEFAULT 0
+#endif
+  static const bool eqfactor_on = [] { const char* e = getenv("SP_SC_EQFACTOR"); return e ? atoi(e) != 0 : SP_SC_EQFACTOR_DEFAULT != 0; }();
+  const size_t G_MIN = 2 * Ctx::SHARD_MIN_LOCAL;   // 16384 entries per table: the fused G kernel then always streams >= 32768
   static const bool persist_on = [] { const char* e = getenv("SP_SC_PERSIST"); return e ? atoi(e) != 0 : SP_SC_PERSIST_DEFAULT != 0; }();
   DevBuf<u256> persist_c;
   if (persist_on) persist_c.alloc(np * (size_t)SC_PERSIST_MAX_LEN);
@@ -196,11 +201,29 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     const size_t lhalf = sh ? half / W : half;         // ... of this many entries per rank
     // poly_C_par = eq(rand)                                                  (product_tree.rs:279-280)
     if (!rand.empty()) dev::h2d(d_rand.p, rand.data(), rand.size() * sizeof(u256), ctx.stream);
-    if (sh) {
-      int logW = 0;
-      while ((1 << logW) < W) logW++;
+    int logW = 0;
+    if (sh) while ((1 << logW) < W) logW++;
+    const Fq c_rank = sh ? shard_eq_scale(rand, W, rk) : Fq::one();   // factor of eq(rand, .) that this rank's low index bits fix (cyclic shards)
+    // eq-factored streaming rounds (kernels_sc.cu: k_sc_eval_g): rounds 0 .. jG-1, i.e. those whose evaluation streams >= G_MIN entries per table;
+    // the suffix tables E_j = eq(rand[j+1..], .) live in cpar0 (E_0, then the levels 1 .. jG-1); from round jG on the standard kernels run on
+    // C = prefix * eq(rand[jG..], .), built at the switch.  Off / not applicable: the standard method from round 0.
+    size_t jG = 0;
+    if (eqfactor_on && num_rounds >= 2) {
+      while (jG + 1 < num_rounds && (lhalf >> jG) >= G_MIN) jG++;
+      for (size_t j = 0; j < jG; j++) if (rand[j].is_zero()) jG = 0;   // q(1) is recovered by a division by tau_j
+    }
+    std::vector<const u256*> Elev(jG);
+    if (jG) {
+      const size_t n0 = lhalf / 2;
+      dev::eq_evals(cpar0.p, d_rand.p + 1, (int)rand.size() - 1 - logW, eq_small.p, ctx.stream);
+      if (sh) dev::scale(cpar0.p, c_rank.m, n0, ctx.stream);
+      if (jG > 1) dev::eq_suffix(cpar0.p + n0, cpar0.p, n0, (int)jG - 1, ctx.stream);
+      Elev[0] = cpar0.p;
+      size_t off = n0;
+      for (size_t k = 1; k < jG; k++) { Elev[k] = cpar0.p + off; off += n0 >> k; }
+    } else if (sh) {
       dev::eq_evals(cpar0.p, d_rand.p, (int)rand.size() - logW, eq_small.p, ctx.stream);
-      dev::scale(cpar0.p, shard_eq_scale(rand, W, rk).m, lhalf, ctx.stream);
+      dev::scale(cpar0.p, c_rank.m, lhalf, ctx.stream);
     } else dev::eq_evals(cpar0.p, d_rand.p, (int)rand.size(), eq_small.p, ctx.stream);
     std::vector<dev::ScInst> insts;
     for (size_t i = 0; i < np; i++) {
@@ -230,14 +253,86 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
     Fq e = claim;
     size_t cur = lhalf;                                // current length of the tables this rank holds
     dev::HostSig sig;
-    if (num_rounds > 0) { sig = ctx.next_sig(); dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream, sig, sh ? ctx.comm->next_xr() : dev::XRank()); }
+    auto xr_next = [&]() { return sh ? ctx.comm->next_xr() : dev::XRank(); };
+    if (jG) {
+      // ---- eq-factored rounds: the np product instances through the G kernels (2 values each), the dot-product circuits (their third table is not an
+      // eq table) through the standard kernels in a second launch whose results land behind the first's
+      const size_t ndi = ninst - np;
+      auto launch_dotp = [&](bool first, const Fq& r) {
+        if (!ndi) return;
+        sig = ctx.next_sig();
+        sig.host_out = ctx.host_res + 3 * np;
+        if (first) dev::sc_eval(dev::SC_CUBIC3, insts.data() + np, (int)ndi, cur, d_out + 3 * np, ctx.red.p, ctx.stream, sig, xr_next());
+        else dev::sc_fold_eval(dev::SC_CUBIC3, insts.data() + np, (int)ndi, cur, r.m, d_out + 3 * np, ctx.red.p, ctx.stream, sig, xr_next());
+      };
+      std::vector<Fq> tau_inv(jG);   // batch inversion of tau_0 .. tau_{jG-1}
+      {
+        std::vector<Fq> pre(jG);
+        Fq acc = Fq::one();
+        for (size_t j = 0; j < jG; j++) { pre[j] = acc; acc *= rand[j]; }
+        Fq inv = acc.inv();
+        for (size_t j = jG; j-- > 0;) { tau_inv[j] = inv * pre[j]; inv *= rand[j]; }
+      }
+      Fq cP = Fq::zero(), eD = Fq::zero(), prefix = Fq::one();
+      for (size_t i = 0; i < np; i++) cP += claims_to_verify[i] * coeff_vec[i];
+      for (size_t i = np; i < ninst; i++) eD += claims_to_verify[i] * coeff_vec[i];
+      sig = ctx.next_sig();
+      dev::sc_eval_g(insts.data(), (int)np, cur, Elev[0], d_out, ctx.red.p, ctx.stream, sig, xr_next());
+      launch_dotp(true, Fq::zero());
+      const Fq one = Fq::one();
+      for (size_t j = 0; j < jG; j++) {
+        std::vector<Fq> ev(3 * ninst);
+        FineTimer fw(ctx, "batched wait evals");
+        ctx.wait_sig(sig);
+        fw.stop();
+        FineTimer fh(ctx, "batched host round");
+        memcpy(ev.data(), ctx.host_res, 3 * ninst * sizeof(u256));
+        Fq Q0 = Fq::zero(), Qinf = Fq::zero(), D0 = Fq::zero(), D2 = Fq::zero(), D3 = Fq::zero();
+        for (size_t i = 0; i < np; i++) { Q0 += ev[3 * i] * coeff_vec[i]; Qinf += ev[3 * i + 1] * coeff_vec[i]; }
+        for (size_t i = np; i < ninst; i++) { D0 += ev[3 * i] * coeff_vec[i]; D2 += ev[3 * i + 1] * coeff_vec[i]; D3 += ev[3 * i + 2] * coeff_vec[i]; }
+        const Fq& tau = rand[j];
+        const Fq omt = one - tau;
+        const Fq Q1 = (cP - omt * Q0) * tau_inv[j];            // c_j = (1 - tau_j) q(0) + tau_j q(1)
+        const Fq qb = Q1 - Q0 - Qinf;
+        auto q_at = [&](const Fq& t) { return (Qinf * t + qb) * t + Q0; };
+        const Fq slope = tau - omt;                              // eq(tau_j, t) = (1 - tau_j) + t (2 tau_j - 1)
+        std::vector<Fq> sD = {D0, eD - D0, D2, D3}, evals(4);
+        Fq t = Fq::zero(), lin = omt;
+        for (int k = 0; k < 4; k++) { evals[k] = prefix * lin * q_at(t) + (ndi ? sD[k] : Fq::zero()); t += one; lin += slope; }
+        UniPoly poly = UniPoly::from_evals(evals);             // the same cubic the reference interpolates from its evaluations at 0, 1, 2, 3
+        poly.append_to_transcript("poly", T);
+        Fq r_j = T.challenge_scalar("challenge_nextround");
+        rand_prod.push_back(r_j);
+        cP = q_at(r_j);
+        prefix *= omt + r_j * slope;
+        if (ndi) eD = UniPoly::from_evals(sD).evaluate(r_j);
+        e = poly.evaluate(r_j);
+        lp.proof.compressed_polys.push_back(poly.compress());
+        if (j + 1 < jG) {
+          sig = ctx.next_sig();
+          dev::sc_fold_eval_g(insts.data(), (int)np, cur, r_j.m, Elev[j + 1], d_out, ctx.red.p, ctx.stream, sig, xr_next());
+          launch_dotp(false, r_j);
+          cur >>= 1;
+        } else {
+          // switch: bind with r_j, build C = prefix * eq(rand[jG..], .) (this rank's slice when sharded) and evaluate round jG the standard way
+          std::vector<u256*> tabs;
+          for (size_t i = 0; i < ninst; i++) { tabs.push_back(insts[i].t[0]); tabs.push_back(insts[i].t[1]); if (i >= np) tabs.push_back(insts[i].t[2]); }
+          dev::fold_top(tabs.data(), (int)tabs.size(), cur, r_j.m, ctx.stream);
+          cur >>= 1;
+          dev::eq_evals(cpar0.p, d_rand.p + jG, (int)rand.size() - (int)jG - logW, eq_small.p, ctx.stream);
+          dev::scale(cpar0.p, (prefix * c_rank).m, cur, ctx.stream);
+          sig = ctx.next_sig();
+          dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream, sig, xr_next());
+        }
+      }
+    } else if (num_rounds > 0) { sig = ctx.next_sig(); dev::sc_eval(dev::SC_CUBIC3, insts.data(), (int)ninst, cur, d_out, ctx.red.p, ctx.stream, sig, xr_next()); }
     u256* cin = cpar0.p;
     u256* cpp[2] = {cpar_a.p, cpar_b.p};
     int flip = 0;
     bool persist = false;
     unsigned int persist_seq0 = 0;
     size_t persist_j0 = 0;
-    for (size_t j = 0; j < num_rounds; j++) {
+    for (size_t j = jG; j < num_rounds; j++) {
       std::vector<Fq> ev(3 * ninst);
       FineTimer fw(ctx, "batched wait evals");
       ctx.wait_sig(sig);
