@@ -184,7 +184,7 @@ static void batched_prove(Ctx& ctx, std::vector<ProdCircuit*>& prods, std::vecto
 #define SP_SC_PERSIST_DEFAULT 0
 #endif
 #ifndef SP_SC_EQFACTOR_DEFAULT
-#define SP_SC_EQFACTOR_DEFAULT 0
+#define SP_SC_EQFACTOR_DEFAULT 1   // measured on the B200 (profiles/r02_tuning.md section 8): -1.3 ms per 2^20 proof, parity suite green
 #endif
   static const bool eqfactor_on = [] { const char* e = getenv("SP_SC_EQFACTOR"); return e ? atoi(e) != 0 : SP_SC_EQFACTOR_DEFAULT != 0; }();
   const size_t G_MIN = 2 * Ctx::SHARD_MIN_LOCAL;   // 16384 entries per table: the fused G kernel then always streams >= 32768
