@@ -13,6 +13,7 @@
 //   K7     eq_evals, dot, bound_rows, lincomb3, hadamard, spmv, SPARK hash layer, IPA helpers.
 // All arithmetic is exact 256-bit integer work on the INT32 pipe; no tensor-core formulation exists.
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <cuda.h>
 #include <stdexcept>
 #include <string>
@@ -846,7 +847,13 @@ __device__ __forceinline__ u256 quad_warp_sum(u256 P, int c, int lane) {
 // points of both sides.  WPQ balances the two costs measured on the B200 (profiles/r02_tuning.md section 7): a lone warp already keeps its
 // sub-partition's FMA pipe 64 % busy, so the first quad formulation (two windows per quad, 4608 warps for 4096 generators) was throughput-bound at the
 // old kernel's time; six or seven windows per quad need a quarter of the warps and add only ~3 us to the dependent chain.
-#define IPAQ_THREADS 256
+#ifndef SP_IPAQ_THREADS
+#define SP_IPAQ_THREADS 256
+#endif
+#ifndef SP_IPAQ_SPLIT
+#define SP_IPAQ_SPLIT 3   // window groups per scalar
+#endif
+#define IPAQ_THREADS SP_IPAQ_THREADS
 template <int WBITS, int WPQ>
 __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, const ge_niels* __restrict__ table, const u256* __restrict__ a, const u256* __restrict__ sv,
                                                                   size_t n_cur, size_t n_full, unsigned int* ticket, ge* out, HostSig sig,
@@ -887,6 +894,14 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
   const int side = blockIdx.y, tid = threadIdx.x, lane = tid & 31, c = lane & 3, warp = tid >> 5;
   const size_t half = n_cur >> 1, total = n_full >> 1;
   const size_t total_quads = total * QPS, stride = (size_t)gridDim.x * QPB;
+#ifdef SP_IPA_TIMELINE
+  unsigned long long tl[10];
+  int tli = 0;
+#define SP_TL() do { if (tid == 0) tl[tli++] = global_timer_ns(); } while (0)
+#else
+#define SP_TL() do { } while (0)
+#endif
+  SP_TL();
   u256 P = quad_identity(c);
   // grid-stride over the (scalar, window group) work items with the same trip count in every quad (the shuffles inside quad_madd need the whole
   // warp): a launch may be capped to fewer blocks than work items (the prover does that while a background MSM occupies most SMs)
@@ -903,6 +918,7 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
       k = fq_mul(ld256_ro(a + (side == 0 ? off : off + half)), ld256_ro(sv + j));
       if (!fq_is_zero(k)) k = fq_from_mont(k);
     }
+    SP_TL();
     uint32_t carry = 0;
     for (int w = 0; w < w0; w++) carry = (msm_window<WBITS>(k, w) + carry) > HALF ? 1u : 0u;
     const ge_niels* tb = table + (j * NWIN + (size_t)w0) * DEPTH;
@@ -924,10 +940,13 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
         }
       }
     }
+    SP_TL();
 #pragma unroll
     for (int h = 0; h < WPQ; h++) P = quad_madd(P, x[h], c, lane);
   }
+  SP_TL();
   P = quad_warp_sum(P, c, lane);
+  SP_TL();
   __shared__ u256 sm[NWARP][4];
   __shared__ bool is_last;
   if (lane < 4) sm[warp][c] = P;
@@ -941,6 +960,12 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
     if (lane == 0) is_last = atomicAdd(ticket, 1u) == 2 * gridDim.x - 1;
   }
   __syncthreads();
+  SP_TL();
+#ifdef SP_IPA_TIMELINE
+  if (tid == 0 && (is_last || (blockIdx.x == 0 && blockIdx.y == 0)) && n_cur == n_full)
+    printf("ipa_tl %s blk(%d,%d) n=%llu: prep %llu loads+digits %llu madds %llu warp_tree %llu cross+ticket %llu ns (start %llu)\n", is_last ? "LAST" : "first", blockIdx.x, blockIdx.y,
+           (unsigned long long)n_full, tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3], tl[5] - tl[4], tl[0]);
+#endif
   if (!is_last) return;
   __threadfence();
   // last block: the first half of its quads finishes L, the second half R
@@ -967,13 +992,17 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
     }
   }
   __syncthreads();
+#ifdef SP_IPA_TIMELINE
+  if (tid == 0 && n_cur == n_full) { unsigned long long te = global_timer_ns(); printf("ipa_tl LAST final stage %llu ns, kernel span from this block's start %llu ns\n", te - tl[5], te - tl[0]); }
+#endif
   if (tid == 0) {
     *ticket = 0;
     if (sig.flag) { __threadfence_system(); *((volatile unsigned int*)sig.flag) = sig.seq; }
   }
 }
+#undef SP_TL
 // windows per quad: the window count split into three groups (17 -> 6, 20 -> 7, 32 -> 11)
-template <int WBITS> struct IpaQ { static constexpr int NWIN = (253 + WBITS - 1) / WBITS, WPQ = (NWIN + 2) / 3, QPS = (NWIN + WPQ - 1) / WPQ; };
+template <int WBITS> struct IpaQ { static constexpr int NWIN = (253 + WBITS - 1) / WBITS, WPQ = (NWIN + SP_IPAQ_SPLIT - 1) / SP_IPAQ_SPLIT, QPS = (NWIN + WPQ - 1) / WPQ; };
 template <int WBITS>
 static void ipa_msm_quad_launch(ge* out, const ge_niels* table, const u256* a, const u256* svec, size_t n_cur, size_t n_full, void* scratch, unsigned int* ticket,
                                 cudaStream_t s, HostSig sig, int max_ctas, const u256* b, u256* c_out, HostSig sigc) {
@@ -992,7 +1021,7 @@ bool ipa_msm_fuses_dots() {   // true when ipa_msm can compute the round's two d
   return quad && fuse;
 }
 size_t ipa_msm_scratch_points(size_t n_full, int wbits) {   // partial points of either formulation
-  const size_t nwin = (size_t)msm_nwin(wbits), total = n_full / 2, wpq = (nwin + 2) / 3, qps = (nwin + wpq - 1) / wpq;
+  const size_t nwin = (size_t)msm_nwin(wbits), total = n_full / 2, wpq = (nwin + SP_IPAQ_SPLIT - 1) / SP_IPAQ_SPLIT, qps = (nwin + wpq - 1) / wpq;
   const size_t quad_chunks = (total * qps + IPAQ_THREADS / 4 - 1) / (IPAQ_THREADS / 4), plain_chunks = (total + 15) / 16;
   return 2 * std::max(quad_chunks, plain_chunks);
 }
