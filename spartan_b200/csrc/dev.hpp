@@ -144,6 +144,7 @@ void ipa_fold_ab(u256* a, u256* b, size_t n, const u256& u, const u256& uinv, cu
 // scalars for the L / R commitments against the UNFOLDED generators: see DESIGN.md "IPA without folding G"
 void ipa_lr_scalars(u256* outL, u256* outR, const u256* a, const u256* svec, size_t n_cur, size_t n_full, cudaStream_t s);
 void ipa_update_s(u256* svec, size_t n_cur_half, size_t n_full, const u256& u, const u256& uinv, cudaStream_t s);
+void ipa_fold_update(u256* a, u256* b, u256* svec, size_t n_cur_half, size_t n_full, const u256& u, const u256& uinv, cudaStream_t s);   // ipa_fold_ab + ipa_update_s in one launch
 void fill_one(u256* out, size_t n, cudaStream_t s);
 
 // windows: IPC-exportable device allocations and their mappings in the peers

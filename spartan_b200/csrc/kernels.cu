@@ -493,6 +493,26 @@ __global__ void k_ipa_update_s(u256* sv, size_t half, size_t n_full, const u256 
     st256(sv + j, fq_mul(ld256(sv + j), right ? u : ui));   // G_L[i] <- u^-1 G_L[i] + u G_R[i], bullet.rs:108
   }
 }
+// both updates of an inner-product round in one launch: rows of blocks y = 0: s[j] *= u^(+-1); y = 1: fold a; y = 2: fold b (one or two products per thread)
+__global__ void k_ipa_fold_update(u256* a, u256* b, u256* sv, size_t half, size_t n_full, const u256 u, const u256 ui) {
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  if (blockIdx.y == 0) {
+    for (size_t j = t0; j < n_full; j += step) {
+      const bool right = (j & (2 * half - 1)) >= half;
+      st256(sv + j, fq_mul(ld256(sv + j), right ? u : ui));   // bullet.rs:108 on the unfolded generators
+    }
+  } else if (blockIdx.y == 1) {
+    for (size_t i = t0; i < half; i += step) st256(a + i, fq_add(fq_mul(ld256(a + i), u), fq_mul(ui, ld256(a + i + half))));   // bullet.rs:106
+  } else {
+    for (size_t i = t0; i < half; i += step) st256(b + i, fq_add(fq_mul(ld256(b + i), ui), fq_mul(u, ld256(b + i + half))));   // bullet.rs:107
+  }
+}
+void ipa_fold_update(u256* a, u256* b, u256* svec, size_t half, size_t n_full, const u256& u, const u256& uinv, cudaStream_t s) {
+  ProfScope ps("ipa_fold_ab", 192.0 * (double)half + 64.0 * (double)n_full, s);
+  dim3 grid(grid_for(n_full, 128, 8), 3);
+  k_ipa_fold_update<<<grid, 128, 0, s>>>(a, b, svec, half, n_full, u, uinv);
+  SP_LAUNCHED(); check("ipa_fold_update");
+}
 void ipa_update_s(u256* svec, size_t half, size_t n_full, const u256& u, const u256& uinv, cudaStream_t s) {
   k_ipa_update_s<<<grid_for(n_full, 128, 8), 128, 0, s>>>(svec, half, n_full, u, uinv);
   SP_LAUNCHED(); check("ipa_update_s");
@@ -800,21 +820,26 @@ __device__ __forceinline__ u256 shfl_xor_256(const u256& x, int m) {
   return r;
 }
 __device__ __forceinline__ u256 quad_identity(int c) { return (c == 1 || c == 2) ? fp_one() : fp_zero(); }
+// lane-dependent choice without a branch: the sums / differences below are computed by every lane and selected, because a divergent
+// `if (c == k)` makes the warp run each arm one after the other (measured: the four arms of quad_finish cost as much as a field product)
+__device__ __forceinline__ u256 sel256(bool p, const u256& a, const u256& b) {
+  u256 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = p ? a.v[i] : b.v[i];
+  return r;
+}
 // coordinates -> operands of the first products: lane 0: Y - X, lane 1: Y + X, lane 2: Z, lane 3: T
 __device__ __forceinline__ u256 quad_prep(const u256& v, int c) {
   const u256 o = shfl_xor_256(v, 1);
-  if (c == 0) return fp_sub(o, v);
-  if (c == 1) return fp_add(v, o);
-  return v;
+  const u256 d = fp_sub(o, v), sm = fp_add(v, o);          // lane 0: Y - X = o - v; lane 1: Y + X
+  return c >= 2 ? v : sel256(c == 0, d, sm);
 }
 // m = (A, B, D, C) on lanes 0..3  ->  the sum's coordinates (X3, Y3, Z3, T3) on lanes 0..3
 static __device__ __noinline__ u256 quad_finish(u256 m, int c, int lane) {
   const u256 o = shfl_xor_256(m, 1);                       // lane 0 <- B, lane 1 <- A, lane 2 <- C, lane 3 <- D
-  u256 w;
-  if (c == 0) w = fp_sub(o, m);                            // E = B - A
-  else if (c == 1) w = fp_add(m, o);                       // H = B + A
-  else if (c == 2) w = fp_sub(m, o);                       // F = D - C
-  else w = fp_add(o, m);                                   // G = D + C
+  // lane 0: E = B - A = o - m, lane 1: H = B + A, lane 2: F = D - C = m - o, lane 3: G = D + C
+  const u256 df = fp_sub(sel256(c == 0, o, m), sel256(c == 0, m, o)), sm = fp_add(m, o);
+  const u256 w = sel256((c & 1) != 0, sm, df);
   const int base = lane & ~3;
   const u256 x = shfl_idx_256(w, base + ((0x2031 >> (4 * c)) & 3));   // lane 0 (E) <- H, lane 1 (H) <- G, lane 2 (F) <- E, lane 3 (G) <- F
   const u256 r = fp_mul(w, x);                             // lane 0: T3 = E H, lane 1: Y3 = H G, lane 2: X3 = F E, lane 3: Z3 = G F
@@ -822,18 +847,17 @@ static __device__ __noinline__ u256 quad_finish(u256 m, int c, int lane) {
 }
 static __device__ __noinline__ u256 quad_add(u256 p, u256 q, int c, int lane) {   // P + Q (ge_add)
   const u256 up = quad_prep(p, c), uq = quad_prep(q, c);
-  u256 m = fp_mul(up, uq);                                 // A | B | Z1 Z2 | T1 T2
-  if (c == 3) m = fp_mul(m, fp_2D());                      // C
-  else if (c == 2) m = fp_add(m, m);                       // D
-  return quad_finish(m, c, lane);
+  const u256 m = fp_mul(up, uq);                           // A | B | Z1 Z2 | T1 T2
+  const u256 m2 = fp_add(m, m);                            // D on lane 2
+  const u256 mc = fp_mul(m, fp_2D());                      // C on lane 3 (every lane multiplies: one more product latency either way, no divergence)
+  return quad_finish(c == 3 ? mc : (c == 2 ? m2 : m), c, lane);
 }
 // P + q for an affine niels operand given per lane as (y - x, y + x, -, 2d x y) of +/-q (ge_madd)
 __device__ __forceinline__ u256 quad_madd(const u256& p, const u256& nq, int c, int lane) {
   const u256 up = quad_prep(p, c);
-  u256 m;
-  if (c == 2) m = fp_add(up, up);                          // D = 2 Z1
-  else m = fp_mul(up, nq);                                 // A | B | C
-  return quad_finish(m, c, lane);
+  const u256 m = fp_mul(up, nq);                           // A | B | (unused) | C
+  const u256 m2 = fp_add(up, up);                          // D = 2 Z1 on lane 2
+  return quad_finish(c == 2 ? m2 : m, c, lane);
 }
 // sum over the 8 quads of a warp -> quad 0
 __device__ __forceinline__ u256 quad_warp_sum(u256 P, int c, int lane) {
@@ -851,7 +875,7 @@ __device__ __forceinline__ u256 quad_warp_sum(u256 P, int c, int lane) {
 #define SP_IPAQ_THREADS 256
 #endif
 #ifndef SP_IPAQ_SPLIT
-#define SP_IPAQ_SPLIT 3   // window groups per scalar
+#define SP_IPAQ_SPLIT 4   // window groups per scalar (17 windows -> 5 per quad; measured best of 2 / 3 / 4 on the B200, profiles/r02_tuning.md section 7)
 #endif
 #define IPAQ_THREADS SP_IPAQ_THREADS
 template <int WBITS, int WPQ>
@@ -962,7 +986,7 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
   __syncthreads();
   SP_TL();
 #ifdef SP_IPA_TIMELINE
-  if (tid == 0 && (is_last || (blockIdx.x == 0 && blockIdx.y == 0)) && n_cur == n_full)
+  if (tid == 0 && !is_last && blockIdx.x == 0 && blockIdx.y == 0 && n_cur == n_full)
     printf("ipa_tl %s blk(%d,%d) n=%llu: prep %llu loads+digits %llu madds %llu warp_tree %llu cross+ticket %llu ns (start %llu)\n", is_last ? "LAST" : "first", blockIdx.x, blockIdx.y,
            (unsigned long long)n_full, tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3], tl[5] - tl[4], tl[0]);
 #endif
@@ -993,7 +1017,11 @@ __global__ void __launch_bounds__(IPAQ_THREADS, 2) k_ipa_msm_quad(ge* partial, c
   }
   __syncthreads();
 #ifdef SP_IPA_TIMELINE
-  if (tid == 0 && n_cur == n_full) { unsigned long long te = global_timer_ns(); printf("ipa_tl LAST final stage %llu ns, kernel span from this block's start %llu ns\n", te - tl[5], te - tl[0]); }
+  if (tid == 0 && n_cur == n_full) {
+    unsigned long long te = global_timer_ns();
+    printf("ipa_tl LAST blk(%d,%d) n=%llu: prep %llu loads+digits %llu madds %llu warp_tree %llu cross+ticket %llu final %llu ns, span %llu ns\n", blockIdx.x, blockIdx.y, (unsigned long long)n_full,
+           tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3], tl[5] - tl[4], te - tl[5], te - tl[0]);
+  }
 #endif
   if (tid == 0) {
     *ticket = 0;

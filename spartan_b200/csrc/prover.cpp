@@ -578,8 +578,7 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
     Fq u = T.challenge_scalar("u");
     Fq u_inv = u.inv();
     f5.stop();
-    dev::ipa_fold_ab(d_a, d_b, half, u.m, u_inv.m, ctx.stream);
-    dev::ipa_update_s(svec.p, half, n, u.m, u_inv.m, ctx.stream);
+    dev::ipa_fold_update(d_a, d_b, svec.p, half, n, u.m, u_inv.m, ctx.stream);
     blind_final = blind_final + blinds_vec[k].first * u * u + blinds_vec[k].second * u_inv * u_inv;  // bullet.rs:111
     proof.L_vec.push_back(Lc);
     proof.R_vec.push_back(Rc);
