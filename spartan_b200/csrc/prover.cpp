@@ -506,7 +506,7 @@ void append_poly_commitment(Transcript& T, const char* label, const PolyCommitme
 // BulletReductionProof::prove (nizk/bullet.rs:32-132) with Q = r*G1 and H = h folded into host fixed-base terms, and the
 // generator vector left unfolded (see k_ipa_lr in kernels.cu).  d_a / d_b are consumed (folded in place).
 static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens, const std::function<Fq()>& get_r_scale, u256* d_a, u256* d_b, size_t n,
-                         const Fq& blind, const std::vector<std::pair<Fq, Fq>>& blinds_vec, BulletReductionProof& proof, Fq& a_hat, Fq& b_hat, ge& g_hat,
+                         const Fq& blind, const std::vector<std::pair<Fq, Fq>>& blinds_vec, BulletReductionProof& proof, Fq& a_hat, Fq& b_hat, hge& g_hat,
                          Fq& blind_final) {
   const GenSet& gs = *gens.gens_n.set;
   const size_t rounds = blinds_vec.size();
@@ -588,12 +588,29 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
   if (k == 0) r_scale = get_r_scale();
   // g_hat = G_final[0] = <s, G>
   FineTimer f6(ctx, "ipa final");
-  dev::msm_rows(pts.p, gs.table.p, gs.wbits, svec.p, n, 1, n, nullptr, 0, ctx.scratch.p, ctx.stream);
   dev::d2h(ctx.pinned, d_a, 32, ctx.stream);
   dev::d2h(ctx.pinned + 32, d_b, 32, ctx.stream);
-  dev::d2h(ctx.pinned + 64, pts.p, sizeof(ge), ctx.stream);
-  ctx.sync();
-  memcpy(&a_hat, ctx.pinned, 32); memcpy(&b_hat, ctx.pinned + 32, 32); memcpy(&g_hat, ctx.pinned + 64, sizeof(ge));
+  if (n >= 2) {
+    // the round kernel with a = (1, 1) and blocks of two generators: "L" = sum over the odd j of s[j] G_j, "R" = over the even j; both reach the host
+    // through the kernel's own publication and are added there (one launch instead of msm_rows + reduce + copy)
+    DevBuf<u256> ones(2);
+    dev::fill_one(ones.p, 2, ctx.stream);
+    dev::HostSig sg = ctx.next_sig();
+    sg.host_out = ctx.host_res + 8;
+    dev::ipa_msm(pts.p, gs.table.p, gs.wbits, ones.p, svec.p, 2, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sg);
+    ctx.sync();
+    ge odd, even;
+    memcpy(&odd, ctx.host_res + 8, sizeof(ge)); memcpy(&even, ctx.host_res + 12, sizeof(ge));
+    g_hat = hge_add(to_hge(odd), to_hge(even));
+  } else {
+    dev::msm_rows(pts.p, gs.table.p, gs.wbits, svec.p, n, 1, n, nullptr, 0, ctx.scratch.p, ctx.stream);
+    dev::d2h(ctx.pinned + 64, pts.p, sizeof(ge), ctx.stream);
+    ctx.sync();
+    ge g;
+    memcpy(&g, ctx.pinned + 64, sizeof(ge));
+    g_hat = to_hge(g);
+  }
+  memcpy(&a_hat, ctx.pinned, 32); memcpy(&b_hat, ctx.pinned + 32, 32);
 }
 
 // DotProductProofLog::prove (nizk/mod.rs:440-525).  d_x: device x_vec (n, consumed); a_vec on the host (it is absorbed by the transcript).
@@ -625,7 +642,7 @@ static void dotproduct_log_prove(Ctx& ctx, const PolyCommitmentGens& gens, Trans
     return r;
   };
   Fq x_hat, a_hat, rhat_Gamma;
-  ge g_hat;
+  hge g_hat;
   f0.stop();
   // blind_Gamma = blind_x + r*blind_y enters the reduction only through the final blind, which is linear in it: pass blind_x and add r*blind_y after
   bullet_prove(ctx, T, gens, absorb_a, d_x, d_avec, n, blind_x, blinds_vec, proof.bullet_reduction_proof, x_hat, a_hat, g_hat, rhat_Gamma);
@@ -634,7 +651,7 @@ static void dotproduct_log_prove(Ctx& ctx, const PolyCommitmentGens& gens, Trans
   Fq y_hat = x_hat * a_hat;
   // delta = d*g_hat + r_delta*h (gens_hat, nizk/mod.rs:497-505)
   Term th[1] = {{gens.gens_1.h, r_delta}};
-  proof.delta = compress(hge_add(hge_scalarmul(d.canonical(), to_hge(g_hat)), host_commit(gs, th, 1)));
+  proof.delta = compress(hge_add(hge_scalarmul(d.canonical(), g_hat), host_commit(gs, th, 1)));
   T.append_point("delta", proof.delta.b);
   // beta = d*(r*G1) + r_beta*h (gens_1_scaled, nizk/mod.rs:507)
   proof.beta = commit1(gens.gens_1, d * r, r_beta);
