@@ -91,7 +91,8 @@ struct Ctx {
   size_t pinned_bytes = 0;
   DevBuf<uint8_t> scratch;         // MSM partial sums (growable)
   DevBuf<uint8_t> red;             // reduction tickets + per-block partials (fixed size, tickets zeroed once and self-resetting)
-  DevBuf<u256> small;              // challenges, results (device side)
+  DevBuf<u256> small;              // challenges, results (device side); [4000, 4002) = two Montgomery ones
+  const u256* ones() const { return small.p + 4000; }
   std::string last_error;
   // per-phase timers (profile feature of the reference, src/timer.rs): label -> milliseconds of the last prove
   std::vector<std::pair<std::string, double>> timings;

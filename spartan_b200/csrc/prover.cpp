@@ -57,6 +57,7 @@ Ctx::Ctx(int dev_) : device(dev_) {
   sig_done.alloc(4);
   dev::dzero(sig_done.p, 16, stream);
   small.alloc(4096);
+  dev::fill_one(small.p + 4000, 2, stream);   // ones(): two Montgomery ones
   scratch.alloc(1 << 20);
   red.alloc(dev::sc_scratch_bytes(24));
   dev::dzero(red.p, red.n, stream);
@@ -472,6 +473,24 @@ Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalar
   // blinds_late (instead of blinds): called AFTER the rows' MSM is in flight, so that the host draws the blinds from the random tape (0.8 us per
   // scalar of Keccak) while the device works; the blind terms blinds[i]*h are then a second, tiny launch added onto the rows.
   if (key.off != 0 || R > key.n) throw std::runtime_error("spartan_b200: commit_rows key mismatch");
+  if (L == 1 && R >= 2 && R % 2 == 0 && !blinds_late && ctx.shard_world() == 1) {
+    // one row (the Cx commitment of DotProductProofLog, nizk/mod.rs:466): a latency problem.  The inner-product round kernel with a = (1, 1) and
+    // blocks of two generators returns sum_{j odd} x_j G_j and sum_{j even} x_j G_j straight to the host; the blind term, the two additions and the
+    // encoding happen there (5 us instead of a 265-product chain on one GPU thread): ~60 us instead of ~200 us for msm_rows + reduce + k_compress + copy
+    ctx.ensure_scratch(std::max(dev::msm_scratch_bytes(1, R), dev::ipa_msm_scratch_points(R, key.set->wbits) * sizeof(ge)) + 64);
+    dev::HostSig sg = ctx.next_sig();
+    sg.host_out = ctx.host_res + 8;
+    DevBuf<ge> pts(2);   // the kernel's device-side copy of the two sums (the host reads its own copy); released after the wait below
+    dev::ipa_msm(pts.p, key.set->table.p, key.set->wbits, ctx.ones(), d_scalars, 2, R, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sg);
+    hge acc = hge_identity();
+    if (blinds && !blinds[0].is_zero()) { Term t[1] = {{key.h, blinds[0]}}; acc = host_commit(*key.set, t, 1); }
+    ctx.wait_sig(sg);
+    ge odd, even;
+    memcpy(&odd, ctx.host_res + 8, sizeof(ge)); memcpy(&even, ctx.host_res + 12, sizeof(ge));
+    out.resize(1);
+    out[0] = compress(hge_add(hge_add(to_hge(odd), to_hge(even)), acc));
+    return out[0];
+  }
   ctx.ensure_scratch(dev::msm_scratch_bytes(L, R) + 64);
   DevBuf<ge> rows(L), bh;
   DevBuf<u256> d_bl;
@@ -593,11 +612,9 @@ static void bullet_prove(Ctx& ctx, Transcript& T, const PolyCommitmentGens& gens
   if (n >= 2) {
     // the round kernel with a = (1, 1) and blocks of two generators: "L" = sum over the odd j of s[j] G_j, "R" = over the even j; both reach the host
     // through the kernel's own publication and are added there (one launch instead of msm_rows + reduce + copy)
-    DevBuf<u256> ones(2);
-    dev::fill_one(ones.p, 2, ctx.stream);
     dev::HostSig sg = ctx.next_sig();
     sg.host_out = ctx.host_res + 8;
-    dev::ipa_msm(pts.p, gs.table.p, gs.wbits, ones.p, svec.p, 2, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sg);
+    dev::ipa_msm(pts.p, gs.table.p, gs.wbits, ctx.ones(), svec.p, 2, n, ctx.scratch.p, ctx.sig_done.p + 1, ctx.stream, sg);
     ctx.sync();
     ge odd, even;
     memcpy(&odd, ctx.host_res + 8, sizeof(ge)); memcpy(&even, ctx.host_res + 12, sizeof(ge));
