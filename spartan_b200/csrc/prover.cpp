@@ -473,7 +473,8 @@ Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalar
   // blinds_late (instead of blinds): called AFTER the rows' MSM is in flight, so that the host draws the blinds from the random tape (0.8 us per
   // scalar of Keccak) while the device works; the blind terms blinds[i]*h are then a second, tiny launch added onto the rows.
   if (key.off != 0 || R > key.n) throw std::runtime_error("spartan_b200: commit_rows key mismatch");
-  if (L == 1 && R >= 2 && R % 2 == 0 && !blinds_late && ctx.shard_world() == 1) {
+  const bool blind_on_host = !blinds || blinds[0].is_zero() || key.set->host_tab.count(key.h) != 0;   // the blind term needs the host copy of h's table
+  if (L == 1 && R >= 2 && R % 2 == 0 && !blinds_late && ctx.shard_world() == 1 && blind_on_host) {
     // one row (the Cx commitment of DotProductProofLog, nizk/mod.rs:466): a latency problem.  The inner-product round kernel with a = (1, 1) and
     // blocks of two generators returns sum_{j odd} x_j G_j and sum_{j even} x_j G_j straight to the host; the blind term, the two additions and the
     // encoding happen there (5 us instead of a 265-product chain on one GPU thread): ~60 us instead of ~200 us for msm_rows + reduce + k_compress + copy
