@@ -335,28 +335,26 @@ std::vector<Fq> host_eq_evals(const std::vector<Fq>& r) {  // EqPolynomial::eval
 // ================================================================================================ ZK sumcheck on the device
 // prove_quad (sumcheck.rs:428-586) and prove_cubic_with_additive_term (sumcheck.rs:588-776).
 // tables: NT device arrays of length 2^num_rounds, folded in place (their first element holds the final evaluation).
-// sharded: `tables_in` are this rank's cyclic shards (length 2^num_rounds / world).  The first rounds then run on the shards — the fused
-// kernels exchange their partial sums over NVLink before handing the round's evaluations to the host — until the local tables drop below
-// streaming size; the shards are then all-gathered into replicated tables (in the window) and the latency-bound tail runs on every rank alike.
-static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const Fq& blind_claim, size_t num_rounds, u256* const* tables_in, int nt,
-                              const CommitKey& g1, const CommitKey& gn, Transcript& T, RandomTape& tape, ZKSumcheckInstanceProof& proof,
-                              std::vector<Fq>& r, std::vector<Fq>& finals, Fq& blind_post, bool sharded = false) {
-  std::vector<u256*> tabs(tables_in, tables_in + nt);
-  u256* const* tables = tabs.data();
-  bool sh = sharded && ctx.shard_world() > 1;
-  const int W = sh ? ctx.shard_world() : 1;
-  const int degree = kind == dev::SC_QUAD ? 2 : 3;
-  std::vector<Fq> blinds_poly = tape.random_vector("blinds_poly", num_rounds);
-  std::vector<Fq> blinds_evals = tape.random_vector("blinds_evals", num_rounds);
-  Fq claim_per_round = claim;
-  Cp comm_claim_per_round = commit1(g1, claim_per_round, blind_claim);
-  // The tape does not depend on the transcript: draw the per-round randomness of DotProductProof::prove (nizk/mod.rs:329-331) now, in the
-  // reference's order, and commit to everything that depends on the tape only in four batched device MSMs, off the per-round critical path:
-  //   delta_j = commit(d_vec_j; r_delta_j) and the blind halves blinds_poly[j]*h, blinds_evals[j]*h, r_beta_j*h.
-  const size_t nco = (size_t)degree + 1;
-  std::vector<DotPre> pre(num_rounds);
-  std::vector<hge> bp_h(num_rounds), be_h(num_rounds);
-  {
+// Everything of a ZK sumcheck that depends on the random tape only (RandomTape is independent of the transcript): the blinds of the round polynomials and
+// evaluations, the per-round randomness of DotProductProof::prove (nizk/mod.rs:329-331) in the reference's order, and the commitments to them —
+//   delta_j = commit(d_vec_j; r_delta_j) and the blind halves blinds_poly[j]*h, blinds_evals[j]*h, r_beta_j*h — in four batched device MSMs.
+// enqueue() draws and launches (no synchronisation: the results travel to pinned host memory), finish() converts them once the stream has been synchronised;
+// r1cs_prove enqueues phase one's behind the witness commitment's MSM, so that neither the draws nor the launches sit on the critical path.
+struct ZkPre {
+  size_t num_rounds = 0, nco = 0;
+  std::vector<Fq> blinds_poly, blinds_evals;
+  std::vector<DotPre> pre;
+  std::vector<hge> bp_h, be_h;
+  DevBuf<u256> d_s, d_b;
+  DevBuf<ge> d_pts;
+  DevBuf<uint8_t> d_c;
+  uint8_t* stage = nullptr;   // pinned: 32*num_rounds encodings, then 3*num_rounds points
+  bool enqueued = false, finished = false;
+  void enqueue(Ctx& ctx, int degree, size_t rounds, const CommitKey& g1, const CommitKey& gn, RandomTape& tape) {
+    num_rounds = rounds; nco = (size_t)degree + 1;
+    blinds_poly = tape.random_vector("blinds_poly", num_rounds);
+    blinds_evals = tape.random_vector("blinds_evals", num_rounds);
+    pre.resize(num_rounds);
     std::vector<Fq> dmat(num_rounds * nco), rdel(num_rounds), rbet(num_rounds);
     for (size_t j = 0; j < num_rounds; j++) {
       pre[j].d_vec = tape.random_vector("d_vec", nco);
@@ -365,28 +363,63 @@ static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const
       for (size_t i = 0; i < nco; i++) dmat[j * nco + i] = pre[j].d_vec[i];
       rdel[j] = pre[j].r_delta; rbet[j] = pre[j].r_beta;
     }
-    DevBuf<u256> d_s(num_rounds * nco), d_b(4 * num_rounds);
-    DevBuf<ge> d_pts(4 * num_rounds);
-    DevBuf<uint8_t> d_c(32 * num_rounds);
+    const size_t stage_bytes = num_rounds * (32 + 3 * sizeof(ge));
+    if (stage_bytes > (96u << 10)) throw std::runtime_error("spartan_b200: ZK sumcheck with too many rounds for the staging area");
+    stage = ctx.pinned + (384 << 10);
+    d_s.alloc(num_rounds * nco); d_b.alloc(4 * num_rounds); d_pts.alloc(4 * num_rounds); d_c.alloc(32 * num_rounds);
+    // pageable sources: the copies snapshot them before returning
     dev::h2d(d_s.p, dmat.data(), dmat.size() * sizeof(u256), ctx.stream);
     dev::h2d(d_b.p, rdel.data(), num_rounds * sizeof(u256), ctx.stream);
     dev::h2d(d_b.p + num_rounds, rbet.data(), num_rounds * sizeof(u256), ctx.stream);
     dev::h2d(d_b.p + 2 * num_rounds, blinds_poly.data(), num_rounds * sizeof(u256), ctx.stream);
     dev::h2d(d_b.p + 3 * num_rounds, blinds_evals.data(), num_rounds * sizeof(u256), ctx.stream);
-    ctx.ensure_scratch(dev::msm_scratch_bytes(num_rounds, nco) + 64);
+    if (ctx.scratch.n < dev::msm_scratch_bytes(num_rounds, nco) + 64) ctx.ensure_scratch(dev::msm_scratch_bytes(num_rounds, nco) + 64);
     const GenSet& gs = *gn.set;
     dev::msm_rows(d_pts.p, gs.table.p, gs.wbits, d_s.p, nco, num_rounds, nco, d_b.p, gn.h, ctx.scratch.p, ctx.stream);                    // delta_j
     dev::compress_batch(d_c.p, d_pts.p, num_rounds, ctx.stream);
     dev::msm_rows(d_pts.p + num_rounds, gs.table.p, gs.wbits, d_s.p, 0, num_rounds, 0, d_b.p + num_rounds, g1.h, ctx.scratch.p, ctx.stream);      // r_beta_j * h
     dev::msm_rows(d_pts.p + 2 * num_rounds, gs.table.p, gs.wbits, d_s.p, 0, num_rounds, 0, d_b.p + 2 * num_rounds, gn.h, ctx.scratch.p, ctx.stream);  // blinds_poly[j] * h
     dev::msm_rows(d_pts.p + 3 * num_rounds, gs.table.p, gs.wbits, d_s.p, 0, num_rounds, 0, d_b.p + 3 * num_rounds, g1.h, ctx.scratch.p, ctx.stream);  // blinds_evals[j] * h
-    std::vector<Cp> deltas(num_rounds);
-    std::vector<ge> pts(3 * num_rounds);
-    dev::d2h(deltas.data(), d_c.p, 32 * num_rounds, ctx.stream);
-    dev::d2h(pts.data(), d_pts.p + num_rounds, 3 * num_rounds * sizeof(ge), ctx.stream);
-    ctx.sync();
-    for (size_t j = 0; j < num_rounds; j++) { pre[j].delta = deltas[j]; pre[j].r_beta_h = to_hge(pts[j]); bp_h[j] = to_hge(pts[num_rounds + j]); be_h[j] = to_hge(pts[2 * num_rounds + j]); }
+    dev::d2h(stage, d_c.p, 32 * num_rounds, ctx.stream);
+    dev::d2h(stage + 32 * num_rounds, d_pts.p + num_rounds, 3 * num_rounds * sizeof(ge), ctx.stream);
+    enqueued = true;
   }
+  void finish(Ctx& ctx) {   // the stream must have been synchronised after enqueue()
+    if (finished) return;
+    bp_h.resize(num_rounds); be_h.resize(num_rounds);
+    const ge* pts = reinterpret_cast<const ge*>(stage + 32 * num_rounds);
+    for (size_t j = 0; j < num_rounds; j++) {
+      memcpy(pre[j].delta.b, stage + 32 * j, 32);
+      pre[j].r_beta_h = to_hge(pts[j]); bp_h[j] = to_hge(pts[num_rounds + j]); be_h[j] = to_hge(pts[2 * num_rounds + j]);
+    }
+    d_s.release(); d_b.release(); d_pts.release(); d_c.release();
+    finished = true;
+  }
+};
+
+// sharded: `tables_in` are this rank's cyclic shards (length 2^num_rounds / world).  The first rounds then run on the shards — the fused
+// kernels exchange their partial sums over NVLink before handing the round's evaluations to the host — until the local tables drop below
+// streaming size; the shards are then all-gathered into replicated tables (in the window) and the latency-bound tail runs on every rank alike.
+static void zk_sumcheck_prove(Ctx& ctx, dev::ScKind kind, const Fq& claim, const Fq& blind_claim, size_t num_rounds, u256* const* tables_in, int nt,
+                              const CommitKey& g1, const CommitKey& gn, Transcript& T, RandomTape& tape, ZKSumcheckInstanceProof& proof,
+                              std::vector<Fq>& r, std::vector<Fq>& finals, Fq& blind_post, bool sharded = false, ZkPre* pre_in = nullptr) {
+  std::vector<u256*> tabs(tables_in, tables_in + nt);
+  u256* const* tables = tabs.data();
+  bool sh = sharded && ctx.shard_world() > 1;
+  const int W = sh ? ctx.shard_world() : 1;
+  const int degree = kind == dev::SC_QUAD ? 2 : 3;
+  ZkPre pre_local;
+  ZkPre& zp = pre_in ? *pre_in : pre_local;
+  if (!zp.enqueued) zp.enqueue(ctx, degree, num_rounds, g1, gn, tape);
+  if (zp.num_rounds != num_rounds || zp.nco != (size_t)degree + 1) throw std::runtime_error("spartan_b200: ZK sumcheck pre-computation of the wrong shape");
+  if (!zp.finished) { ctx.sync(); zp.finish(ctx); }
+  const std::vector<Fq>& blinds_poly = zp.blinds_poly;
+  const std::vector<Fq>& blinds_evals = zp.blinds_evals;
+  const std::vector<DotPre>& pre = zp.pre;
+  const std::vector<hge>& bp_h = zp.bp_h;
+  const std::vector<hge>& be_h = zp.be_h;
+  Fq claim_per_round = claim;
+  Cp comm_claim_per_round = commit1(g1, claim_per_round, blind_claim);
   auto commit_poly_pre = [&](const std::vector<Fq>& coeffs, size_t j) {   // commit(coeffs; blinds_poly[j]; gens_n) = sum coeff_i*G_i + (blinds_poly[j]*h)
     std::vector<Term> t;
     for (size_t i = 0; i < coeffs.size(); i++) t.push_back({gn.off + i, coeffs[i]});
@@ -774,11 +807,18 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
   while (((size_t)1 << ell) < num_vars) ell++;
   const size_t L_size = (size_t)1 << (ell / 2), R_size = (size_t)1 << (ell - ell / 2);
   std::vector<Fq> blinds_vars;
+  ZkPre zk_pre1;
+  size_t log2_rounds_x = 0;
+  while (((size_t)1 << log2_rounds_x) < num_cons) log2_rounds_x++;
   {
     PhaseTimer t(ctx, "polycommit");
     // dense_mlpoly.rs:193-196; the blinds are the tape's first draw and are made while the rows' MSM already runs
-    commit_rows_and_compress(ctx, gens.gens_pc.gens_n, d_vars, R_size, L_size, R_size, nullptr, proof.comm_vars.C,
-                             [&]() { blinds_vars = tape.random_vector("poly_blinds", L_size); return blinds_vars.data(); });
+    commit_rows_and_compress(ctx, gens.gens_pc.gens_n, d_vars, R_size, L_size, R_size, nullptr, proof.comm_vars.C, [&]() {
+      blinds_vars = tape.random_vector("poly_blinds", L_size);
+      // the tape's next draws are phase one's (nothing in between touches the tape): draw them and queue their commitments behind the rows' MSM too
+      zk_pre1.enqueue(ctx, 3, log2_rounds_x, gens.gens_1, gens.gens_4, tape);
+      return blinds_vars.data();
+    });
     append_poly_commitment(T, "poly_commitment", proof.comm_vars);
   }
 
@@ -819,7 +859,7 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
     }
     u256* tabs[4] = {d_tau.p, d_Az.p, d_Bz.p, d_Cz.p};
     zk_sumcheck_prove(ctx, dev::SC_CUBIC4, Fq::zero(), Fq::zero(), num_rounds_x, tabs, 4, gens.gens_1, gens.gens_4, T, tape, proof.sc_proof_phase1, rx, claims1,
-                      blind_claim_postsc1, sh1);
+                      blind_claim_postsc1, sh1, &zk_pre1);
   }
   if (hooks && hooks->on_rx) hooks->on_rx(rx);
   const Fq tau_claim = claims1[0], Az_claim = claims1[1], Bz_claim = claims1[2], Cz_claim = claims1[3];
