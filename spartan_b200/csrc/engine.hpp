@@ -1,6 +1,10 @@
 // spartan_b200 — device context, buffers and generator sets shared by the host prover.
 #pragma once
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <chrono>
 #include <cstdlib>
 #include <map>
@@ -178,6 +182,33 @@ struct GenSet {
 struct CommitKey {
   const GenSet* set = nullptr;
   size_t off = 0, n = 0, h = 0;
+};
+
+// A few helper threads for the host's single-point commitments (process-wide, created on first use).  The ZK sumcheck rounds are host-bound: between a
+// round's evaluations and its challenge the prover thread commits to the four coefficients of the round polynomial — four independent fixed-base scalar
+// multiplications of ~4 us each.  run(n, fn) executes fn(0) .. fn(n-1), fn(0) on the caller and the rest on helpers that spin for work while proofs are in
+// flight (they fall asleep on a condition variable after ~200 us without any).  SP_HOST_THREADS=0 (or fewer than 8 hardware threads) keeps everything on the
+// calling thread; results do not depend on it (group addition is commutative, encodings are canonical).
+class HostPool {
+ public:
+  static HostPool& get();
+  int helpers() const { return (int)th_.size(); }
+  void run(int njobs, const std::function<void(int)>& fn);
+  ~HostPool();
+ private:
+  HostPool();
+  void worker();
+  std::vector<std::thread> th_;
+  std::atomic<uint64_t> epoch_{0};
+  // next_ = (run tag << 32) | next job index, desc_ = (run tag << 32) | job count: a helper that drew an index from an earlier run's counter sees the
+  // tag mismatch and drops it (index and job count are never read from two different runs)
+  std::atomic<uint64_t> next_{0}, desc_{0};
+  std::atomic<int> pending_{0}, sleepers_{0};
+  std::atomic<bool> stop_{false};
+  std::atomic<const std::function<void(int)>*> fn_{nullptr};
+  uint64_t tag_ = 0;                   // caller side only
+  std::mutex mu_;
+  std::condition_variable cv_;
 };
 
 struct Term { size_t base; Fq k; };

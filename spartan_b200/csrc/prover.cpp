@@ -209,7 +209,87 @@ hge GenSet::host_point(size_t base) const {
   hge acc = hge_identity();
   return hge_madd(acc, tab(base).e[0], false);
 }
+// ---- HostPool
+HostPool& HostPool::get() { static HostPool p; return p; }
+HostPool::HostPool() {
+  int n = 3;
+  if (const char* e = getenv("SP_HOST_THREADS")) n = atoi(e);
+  if (std::thread::hardware_concurrency() < 8) n = 0;
+  if (n < 0) n = 0;
+  if (n > 7) n = 7;
+  for (int i = 0; i < n; i++) th_.emplace_back([this] { worker(); });
+}
+HostPool::~HostPool() {
+  stop_.store(true);
+  { std::lock_guard<std::mutex> lk(mu_); cv_.notify_all(); }
+  for (auto& t : th_) t.join();
+}
+void HostPool::worker() {
+  uint64_t seen = 0;
+  auto last_work = std::chrono::steady_clock::now();
+  unsigned spins = 0;
+  while (!stop_.load(std::memory_order_relaxed)) {
+    const uint64_t e = epoch_.load(std::memory_order_acquire);
+    if (e != seen) {
+      seen = e;
+      for (;;) {
+        const uint64_t v = next_.fetch_add(1, std::memory_order_acq_rel);
+        const uint64_t d = desc_.load(std::memory_order_acquire);
+        if ((v >> 32) != (d >> 32) || (uint32_t)v >= (uint32_t)d) break;
+        (*fn_.load(std::memory_order_acquire))((int)(uint32_t)v);
+        pending_.fetch_sub(1, std::memory_order_acq_rel);
+      }
+      last_work = std::chrono::steady_clock::now();
+      spins = 0;
+      continue;
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0x3ff) == 0 && std::chrono::steady_clock::now() - last_work > std::chrono::microseconds(200)) {
+      std::unique_lock<std::mutex> lk(mu_);
+      sleepers_.fetch_add(1);
+      cv_.wait_for(lk, std::chrono::milliseconds(50), [&] { return stop_.load() || epoch_.load(std::memory_order_acquire) != seen; });
+      sleepers_.fetch_sub(1);
+      last_work = std::chrono::steady_clock::now();
+    }
+  }
+}
+void HostPool::run(int njobs, const std::function<void(int)>& fn) {
+  if (njobs <= 1 || th_.empty()) { for (int i = 0; i < njobs; i++) fn(i); return; }
+  const uint64_t tag = ++tag_ & 0xffffffu;
+  fn_.store(&fn, std::memory_order_relaxed);
+  pending_.store(njobs - 1, std::memory_order_relaxed);
+  desc_.store(tag << 32 | (uint32_t)njobs, std::memory_order_release);
+  next_.store(tag << 32 | 1u, std::memory_order_release);
+  epoch_.fetch_add(1, std::memory_order_release);
+  if (sleepers_.load(std::memory_order_acquire) > 0) { std::lock_guard<std::mutex> lk(mu_); cv_.notify_all(); }
+  fn(0);
+  for (;;) {   // the caller takes whatever the helpers have not started
+    const uint64_t v = next_.fetch_add(1, std::memory_order_acq_rel);
+    if ((uint32_t)v >= (uint32_t)njobs) break;
+    fn((int)(uint32_t)v);
+    pending_.fetch_sub(1, std::memory_order_acq_rel);
+  }
+  while (pending_.load(std::memory_order_acquire) > 0) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 hge host_commit(const GenSet& gs, const Term* terms, size_t nterms) {
+  if (nterms >= 3 && HostPool::get().helpers() > 0) {   // one fixed-base scalar multiplication per job, partial points added here
+    hge part[8];
+    const int n = (int)std::min<size_t>(nterms, 8);
+    const HostBaseTable* tb[8];
+    for (int i = 0; i < n; i++) tb[i] = &gs.tab(terms[i].base);   // look-ups (and their exceptions) stay on this thread
+    HostPool::get().run(n, [&](int i) { part[i] = hge_identity(); host_fixed_mul_acc(part[i], *tb[i], terms[i].k); });
+    hge acc = part[0];
+    for (int i = 1; i < n; i++) acc = hge_add(acc, part[i]);
+    for (size_t i = (size_t)n; i < nterms; i++) host_fixed_mul_acc(acc, gs.tab(terms[i].base), terms[i].k);
+    return acc;
+  }
   hge acc = hge_identity();
   for (size_t i = 0; i < nterms; i++) host_fixed_mul_acc(acc, gs.tab(terms[i].base), terms[i].k);
   return acc;
@@ -807,18 +887,13 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
   while (((size_t)1 << ell) < num_vars) ell++;
   const size_t L_size = (size_t)1 << (ell / 2), R_size = (size_t)1 << (ell - ell / 2);
   std::vector<Fq> blinds_vars;
-  ZkPre zk_pre1;
-  size_t log2_rounds_x = 0;
-  while (((size_t)1 << log2_rounds_x) < num_cons) log2_rounds_x++;
   {
     PhaseTimer t(ctx, "polycommit");
     // dense_mlpoly.rs:193-196; the blinds are the tape's first draw and are made while the rows' MSM already runs
-    commit_rows_and_compress(ctx, gens.gens_pc.gens_n, d_vars, R_size, L_size, R_size, nullptr, proof.comm_vars.C, [&]() {
-      blinds_vars = tape.random_vector("poly_blinds", L_size);
-      // the tape's next draws are phase one's (nothing in between touches the tape): draw them and queue their commitments behind the rows' MSM too
-      zk_pre1.enqueue(ctx, 3, log2_rounds_x, gens.gens_1, gens.gens_4, tape);
-      return blinds_vars.data();
-    });
+    // (queueing phase one's tape-only commitments here as well — ZkPre::enqueue behind the rows' MSM — was measured and lost 0.3 ms: their small kernels
+    //  lengthen this commitment's chain by what they save phase one, whose rounds are host-bound anyway; profiles/r02_tuning.md section 10)
+    commit_rows_and_compress(ctx, gens.gens_pc.gens_n, d_vars, R_size, L_size, R_size, nullptr, proof.comm_vars.C,
+                             [&]() { blinds_vars = tape.random_vector("poly_blinds", L_size); return blinds_vars.data(); });
     append_poly_commitment(T, "poly_commitment", proof.comm_vars);
   }
 
@@ -859,7 +934,7 @@ void r1cs_prove(Ctx& ctx, const Instance& inst, const u256* d_vars, const std::v
     }
     u256* tabs[4] = {d_tau.p, d_Az.p, d_Bz.p, d_Cz.p};
     zk_sumcheck_prove(ctx, dev::SC_CUBIC4, Fq::zero(), Fq::zero(), num_rounds_x, tabs, 4, gens.gens_1, gens.gens_4, T, tape, proof.sc_proof_phase1, rx, claims1,
-                      blind_claim_postsc1, sh1, &zk_pre1);
+                      blind_claim_postsc1, sh1);
   }
   if (hooks && hooks->on_rx) hooks->on_rx(rx);
   const Fq tau_claim = claims1[0], Az_claim = claims1[1], Bz_claim = claims1[2], Cz_claim = claims1[3];

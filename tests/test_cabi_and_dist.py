@@ -118,3 +118,13 @@ def test_transcript_state_helpers_match_merlin():
         assert a.challenge_bytes(b"c", 64) == b.challenge_bytes(b"c", 64)
         assert a.challenge_bytes(b"long", 700) == b.challenge_bytes(b"long", 700)
     assert len(a.state.raw) == 203 and a.state.raw[200] < 166
+
+
+def test_host_pool_runs_every_job_exactly_once():
+    """engine.hpp HostPool (helper threads for the host's single-point commitments): 60000 runs of 1..6 jobs, every job exactly once (CPU only)"""
+    import ctypes as C
+    from spartan_b200 import api
+    helpers = C.c_int(-1)
+    api.lib.sp_host_pool_selftest.restype = C.c_int
+    bad = api.lib.sp_host_pool_selftest(C.c_int(60000), C.byref(helpers))
+    assert bad == 0 and helpers.value >= 0
