@@ -187,8 +187,8 @@ struct CommitKey {
 // A few helper threads for the host's single-point commitments (process-wide, created on first use).  The ZK sumcheck rounds are host-bound: between a
 // round's evaluations and its challenge the prover thread commits to the four coefficients of the round polynomial — four independent fixed-base scalar
 // multiplications of ~4 us each.  run(n, fn) executes fn(0) .. fn(n-1), fn(0) on the caller and the rest on helpers that spin for work while proofs are in
-// flight (they fall asleep on a condition variable after ~200 us without any).  SP_HOST_THREADS=0 (or fewer than 8 hardware threads) keeps everything on the
-// calling thread; results do not depend on it (group addition is commutative, encodings are canonical).
+// flight (they fall asleep on a condition variable after ~200 us without any).  SP_HOST_THREADS=<n> switches them on (default 0: measured, no gain — the
+// hand-over costs what the parallel scalar multiplications save); results do not depend on it (group addition is commutative, encodings are canonical).
 class HostPool {
  public:
   static HostPool& get();

@@ -212,7 +212,7 @@ hge GenSet::host_point(size_t base) const {
 // ---- HostPool
 HostPool& HostPool::get() { static HostPool p; return p; }
 HostPool::HostPool() {
-  int n = 3;
+  int n = 0;   // off by default: measured on the B200 box (profiles/r02_tuning.md section 10), three helpers cost the ZK rounds as much as they save
   if (const char* e = getenv("SP_HOST_THREADS")) n = atoi(e);
   if (std::thread::hardware_concurrency() < 8) n = 0;
   if (n < 0) n = 0;

@@ -121,10 +121,14 @@ def test_transcript_state_helpers_match_merlin():
 
 
 def test_host_pool_runs_every_job_exactly_once():
-    """engine.hpp HostPool (helper threads for the host's single-point commitments): 60000 runs of 1..6 jobs, every job exactly once (CPU only)"""
-    import ctypes as C
-    from spartan_b200 import api
-    helpers = C.c_int(-1)
-    api.lib.sp_host_pool_selftest.restype = C.c_int
-    bad = api.lib.sp_host_pool_selftest(C.c_int(60000), C.byref(helpers))
-    assert bad == 0 and helpers.value >= 0
+    """engine.hpp HostPool (optional helper threads for the host's single-point commitments, SP_HOST_THREADS): 60000 runs of 1..6 jobs, every job exactly
+    once, with three helpers and with none (CPU only; own processes because the pool is created once per process)"""
+    import subprocess, sys
+    code = ("import ctypes as C, sys; sys.path.insert(0, %r); from spartan_b200 import api; h = C.c_int(-1); api.lib.sp_host_pool_selftest.restype = C.c_int; "
+            "bad = api.lib.sp_host_pool_selftest(C.c_int(60000), C.byref(h)); print(bad, h.value)") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for threads, want in (("3", 3), ("0", 0)):
+        env = dict(os.environ); env["SP_HOST_THREADS"] = threads
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        bad, helpers = (int(x) for x in out.stdout.split())
+        assert bad == 0 and helpers in (want, 0)   # 0: fewer than 8 hardware threads on this box
