@@ -169,7 +169,10 @@ void pool_free(void* p) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
   auto it = g_pool_live.find(p);
   if (it == g_pool_live.end()) { cudaFree(p); return; }
-  if (it->second.second > ((size_t)1 << 30)) cudaFree(p);   // multi-GB blocks (generator tables) are long-lived: do not hoard them
+  // blocks of tens of GB (generator tables) are long-lived: do not hoard them.  Per-proof buffers stay cached even when they pass 1 GiB (2^22 constraints: the
+  // 1.2 GB dot-product circuit buffer) — a cudaFree synchronises the device, i.e. waits for the background stream's MSM, and the cudaMalloc of the next proof
+  // made SNARK::prove at 2^22 bimodal (101 / 200 ms, GPU call 20)
+  if (it->second.second > ((size_t)8 << 30)) cudaFree(p);
   else g_pool_free.insert({it->second, p});
   g_pool_live.erase(it);
 }
