@@ -745,31 +745,13 @@ int sp_instance_export(const sp_instance* inst, int m, uint64_t* row, uint64_t* 
   return SP_OK;
 }
 
-static DevBuf<u256> upload_padded_vars(Ctx& c, const Instance& I, const uint64_t* vars, size_t nvars, bool pipelined = false) {
+static DevBuf<u256> upload_padded_vars(Ctx& c, const Instance& I, const uint64_t* vars, size_t nvars) {
   if (nvars > I.num_vars) throw SpError(SP_ERR_INVALID_INPUTS, "R1CSError::InvalidNumberOfInputs (vars)");
   DevBuf<u256> d(I.num_vars);
-  // pipelined (the prove entry points, large witnesses): eight pieces on the context's copy stream, an event after each; the witness commitment starts on
-  // the first piece while the others are still crossing PCIe (commit_rows_and_compress).  The caller drains the copy stream before `d` is released.
-  if (pipelined && nvars == I.num_vars && nvars >= ((size_t)1 << 16) && nvars % 8 == 0 && c.world() == 1) {
-    if (!c.copy_stream) { c.copy_stream = dev::stream_create_prio(0); for (auto& e : c.wit_upload.ev) e = dev::event_create(); }
-    dev::event_record(c.ev_fork, c.stream);                 // `d` may have been in use by earlier work of the prover's stream
-    dev::stream_wait_event(c.copy_stream, c.ev_fork);
-    const size_t ce = nvars / 8;
-    for (int k = 0; k < 8; k++) {
-      dev::h2d(d.p + (size_t)k * ce, vars + 4 * (size_t)k * ce, ce * 32, c.copy_stream);
-      dev::event_record(c.wit_upload.ev[k], c.copy_stream);
-    }
-    c.wit_upload.base = d.p; c.wit_upload.chunk_elems = ce; c.wit_upload.chunks = 8;
-    return d;
-  }
   dev::h2d(d.p, vars, nvars * 32, c.stream);
   if (nvars < I.num_vars) dev::dzero(d.p + nvars, (I.num_vars - nvars) * 32, c.stream);  // Assignment::pad (lib.rs:91-104)
   return d;
 }
-struct UploadDrain {   // whatever happens inside the prove call, the copy stream is idle before the witness buffer goes back to the pool
-  Ctx& c;
-  ~UploadDrain() { c.upload_drain(); }
-};
 
 int sp_instance_is_sat(sp_ctx* ctx, const sp_instance* inst, const uint64_t* vars, size_t nvars, const uint64_t* inputs, size_t ninputs, int* sat) {
   SP_TRY(ctx)
@@ -830,8 +812,7 @@ static int nizk_prove_common(sp_ctx* ctx, const sp_instance* inst, const u256* d
 int sp_nizk_prove(sp_ctx* ctx, const sp_instance* inst, const uint64_t* vars, size_t nvars, const uint64_t* inputs, size_t ninputs, const sp_nizk_gens* gens,
                   const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   DevBuf<u256> d_vars;
-  UploadDrain drain{ctx->c};
-  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars, true); }
+  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
   catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
   catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
   return nizk_prove_common(ctx, inst, d_vars.p, inputs, ninputs, gens, TranscriptArg{label, label_len, nullptr}, seed, proof, proof_len);
@@ -841,8 +822,7 @@ int sp_nizk_prove_t(sp_ctx* ctx, const sp_instance* inst, const uint64_t* vars, 
                     uint8_t* strobe_state, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   if (!strobe_state) { ctx->c.last_error = "transcript state is NULL"; return SP_ERR_INVALID_ARG; }
   DevBuf<u256> d_vars;
-  UploadDrain drain{ctx->c};
-  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars, true); }
+  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
   catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
   catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
   return nizk_prove_common(ctx, inst, d_vars.p, inputs, ninputs, gens, TranscriptArg{nullptr, 0, strobe_state}, seed, proof, proof_len);
@@ -914,8 +894,7 @@ static int snark_prove_common(sp_ctx* ctx, const sp_instance* inst, const sp_sna
 int sp_snark_prove(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encoding* enc, const uint64_t* vars, size_t nvars, const uint64_t* inputs, size_t ninputs,
                    const sp_snark_gens* gens, const uint8_t* label, size_t label_len, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   DevBuf<u256> d_vars;
-  UploadDrain drain{ctx->c};
-  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars, true); }
+  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
   catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
   catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
   return snark_prove_common(ctx, inst, enc, d_vars.p, inputs, ninputs, gens, TranscriptArg{label, label_len, nullptr}, seed, proof, proof_len);
@@ -925,8 +904,7 @@ int sp_snark_prove_t(sp_ctx* ctx, const sp_instance* inst, const sp_snark_encodi
                      const sp_snark_gens* gens, uint8_t* strobe_state, const uint64_t seed[4], uint8_t** proof, size_t* proof_len) {
   if (!strobe_state) { ctx->c.last_error = "transcript state is NULL"; return SP_ERR_INVALID_ARG; }
   DevBuf<u256> d_vars;
-  UploadDrain drain{ctx->c};
-  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars, true); }
+  try { d_vars = upload_padded_vars(ctx->c, inst->inst, vars, nvars); }
   catch (const SpError& e) { ctx->c.last_error = e.what(); return e.code; }
   catch (const std::exception& e) { ctx->c.last_error = e.what(); return SP_ERR_CUDA; }
   return snark_prove_common(ctx, inst, enc, d_vars.p, inputs, ninputs, gens, TranscriptArg{nullptr, 0, strobe_state}, seed, proof, proof_len);

@@ -86,13 +86,6 @@ struct Ctx {
   // background stream (least priority) for throughput work whose inputs are known early and whose result the transcript needs late: the commitment
   // to the dereferenced SPARK values runs there under the second sumcheck phase and the witness evaluation proof (snark.cpp)
   cudaStream_t stream2 = nullptr;
-  // Host -> device upload of the witness in flight on its own stream (capi.cpp: upload_padded_vars): `chunks` equal pieces of `chunk_elems` scalars from
-  // `base`, ev[k] recorded after piece k.  commit_rows_and_compress consumes it (one MSM launch per piece, each waiting for its own event only), so the
-  // PCIe copy of the witness overlaps the rows' MSM instead of preceding it; any other first use waits for the whole copy (upload_wait).
-  struct Upload { const u256* base = nullptr; size_t chunk_elems = 0; int chunks = 0; void* ev[8] = {}; } wit_upload;
-  cudaStream_t copy_stream = nullptr;
-  void upload_wait();     // make the prover's stream wait for the whole upload (idempotent)
-  void upload_drain();    // host-side: block until the copy stream is idle (before the destination buffer may be released)
   bool overlap = true;                 // sp_ctx_set_overlap: 0 keeps every kernel on the prover's stream (profiling: per-kernel event times free of concurrent work)
   bool bg_busy = false;                // between fork and join of background work (snark.cpp): latency kernels shape their grids for the free SMs
   int stream2_sms = 0;                 // > 0: stream2 is confined to that many SMs (green context); 0: it shares every SM with the prover's stream

@@ -63,15 +63,6 @@ Ctx::Ctx(int dev_) : device(dev_) {
   dev::dzero(red.p, red.n, stream);
   sync();
 }
-void Ctx::upload_wait() {
-  if (!wit_upload.base) return;
-  dev::stream_wait_event(stream, wit_upload.ev[wit_upload.chunks - 1]);   // the copies are ordered on one stream: the last event covers them all
-  wit_upload.base = nullptr;
-}
-void Ctx::upload_drain() {
-  if (copy_stream) { try { dev::stream_sync(copy_stream); } catch (...) {} }
-  wit_upload.base = nullptr;
-}
 void Ctx::comm_create() {
   if (comm) return;
   dev::set_device(device);
@@ -82,8 +73,6 @@ void Ctx::comm_create() {
 Ctx::~Ctx() {
   try { sync(); } catch (...) {}
   try { dev::stream_sync(stream2); } catch (...) {}
-  if (copy_stream) { try { dev::stream_sync(copy_stream); } catch (...) {} dev::stream_destroy(copy_stream); }
-  for (void* e : wit_upload.ev) if (e) dev::event_destroy(e);
   scratch.release(); scratch2.release(); red.release(); small.release(); dmail.release();
   dev::event_destroy(ev_fork); dev::event_destroy(ev_join);
   dev::stream_destroy(stream2);
@@ -599,7 +588,6 @@ Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalar
   if (key.off != 0 || R > key.n) throw std::runtime_error("spartan_b200: commit_rows key mismatch");
   const bool blind_on_host = !blinds || blinds[0].is_zero() || key.set->host_tab.count(key.h) != 0;   // the blind term needs the host copy of h's table
   if (L == 1 && R >= 2 && R % 2 == 0 && !blinds_late && ctx.shard_world() == 1 && blind_on_host) {
-    ctx.upload_wait();
     // one row (the Cx commitment of DotProductProofLog, nizk/mod.rs:466): a latency problem.  The inner-product round kernel with a = (1, 1) and
     // blocks of two generators returns sum_{j odd} x_j G_j and sum_{j even} x_j G_j straight to the host; the blind term, the two additions and the
     // encoding happen there (5 us instead of a 265-product chain on one GPU thread): ~60 us instead of ~200 us for msm_rows + reduce + k_compress + copy
@@ -627,19 +615,7 @@ Cp commit_rows_and_compress(Ctx& ctx, const CommitKey& key, const u256* d_scalar
   // rows are independent MSMs over the same generators: when sharded, rank r commits rows [r*L/W, (r+1)*L/W) and the 32-byte encodings are all-gathered
   const bool split = W > 1 && L >= 2 * W && L % W == 0;
   const size_t Lr = split ? L / W : L, row0 = split ? (size_t)ctx.rank() * Lr : 0;
-  const Ctx::Upload up = ctx.wit_upload;
-  if (up.base == d_scalars && !split && !blinds && stride == R && up.chunk_elems % R == 0 && up.chunk_elems * (size_t)up.chunks == L * R) {
-    // the scalars are still arriving from the host (the witness of sp_*_prove): one MSM launch per uploaded piece, each behind its own event
-    const size_t Lc = up.chunk_elems / R;
-    for (int k = 0; k < up.chunks; k++) {
-      dev::stream_wait_event(ctx.stream, up.ev[k]);
-      dev::msm_rows(rows.p + (size_t)k * Lc, key.set->table.p, key.set->wbits, d_scalars + (size_t)k * up.chunk_elems, stride, Lc, R, nullptr, key.h, ctx.scratch.p, ctx.stream);
-    }
-    ctx.wit_upload.base = nullptr;
-  } else {
-    ctx.upload_wait();
-    dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars + row0 * stride, stride, Lr, R, blinds ? d_bl.p + row0 : nullptr, key.h, ctx.scratch.p, ctx.stream);
-  }
+  dev::msm_rows(rows.p, key.set->table.p, key.set->wbits, d_scalars + row0 * stride, stride, Lr, R, blinds ? d_bl.p + row0 : nullptr, key.h, ctx.scratch.p, ctx.stream);
   if (!blinds && blinds_late) {
     const Fq* bl = blinds_late();
     d_bl.alloc(L); bh.alloc(Lr);
