@@ -112,3 +112,32 @@ def test_row_partition_of_commitments():
         lo, hi = rk * L // W, (rk + 1) * L // W
         parts += oc.commit_rows(np.ascontiguousarray(Z[lo * R:hi * R]), hi - lo, R, blinds[lo:hi], gens)
     assert parts == whole
+
+
+@pytest.mark.parametrize("W", [1, 2, 4, 8])
+@pytest.mark.parametrize("logN", [12, 16, 20])
+def test_background_derefs_commitment_row_partition(W, logN):
+    """snark.cpp (background-stream commitment of the dereferenced values): the 8N-entry derefs polynomial is an L x R matrix; rows [0, n_part) depend on rx,
+    [n_part, 2 n_part) on ry, the rest are zero.  Rank r commits rows [p n_part + r cnt, p n_part + (r+1) cnt) of part p; the all-gather delivers, per rank, its
+    part-0 rows followed by its part-1 rows; the host puts them back in matrix order.  Every non-zero row must be committed exactly once and land at its own index."""
+    N = 1 << logN
+    ell = (8 * N).bit_length() - 1
+    L, R = 1 << (ell // 2), 1 << (ell - ell // 2)
+    assert L * R == 8 * N and N % R == 0
+    n_part = 3 * N // R
+    shard_rows = W > 1 and n_part % W == 0
+    cnt = n_part // W if shard_rows else n_part
+    ranks = W if shard_rows else 1
+    gathered = []                                             # rank-major: [rank][part][cnt] row ids, as allgather_block lays the 32-byte encodings out
+    for r in range(ranks):
+        for p in range(2):
+            first = p * n_part + (r * cnt if shard_rows else 0)
+            gathered.extend(range(first, first + cnt))
+    C = [None] * L
+    for r in range(ranks):
+        for p in range(2):
+            for i in range(cnt):
+                C[p * n_part + r * cnt + i] = gathered[(r * 2 + p) * cnt + i]
+    assert all(C[i] == i for i in range(2 * n_part)) and all(c is None for c in C[2 * n_part:])
+    # the rows of part 0 hold exactly the row-derefs (first 3N entries), part 1 the column-derefs (next 3N)
+    assert n_part * R == 3 * N
